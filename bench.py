@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""Benchmark of the Gated-CCVAE ELBO training step (BASELINE.json metric: training images/sec of the
+supervised + unsupervised ELBO step).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+
+One "step" = one supervised train_step + one unsupervised train_step (forward, backward, gradient
+all-reduce, Adam), each on `--batch` images per GPU (default: BASELINE.json configs[1], fixed-inferred
+gating from gating_matrix_0.2, batch 1024 per GPU).  Data parallel, weak scaling: every rank processes
+its own shard; value = images all ranks processed / max-over-ranks device time.
+
+Prints ONE JSON line (rank 0).  Keys beyond the base contract: roofline, cpu_baseline, e2e, clocks,
+gpu_launches.  `--impl reference` times the CPU oracle (the reference cannot run here: it needs
+TensorFlow) on the host cores on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import numpy as np
+import torch
+
+METRIC = "training images/sec (sup+unsup ELBO step)"
+UNIT = "images/s"
+WORKLOAD = "Gated CCVAE fixed-inferred gating (gating_matrix_0.2), 64x64x3, 18 attrs, K=100, batch {} per GPU"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=30)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("GCCVAE_PRECISION", "auto"))
+    ap.add_argument("--batch", type=int, default=1024)
+    ap.add_argument("--ref-batch", type=int, default=256)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+def train_cfg():
+    mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.2.npy"))
+    return dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4,
+                gating_init_temp=0.3, batch_size=1024, init_temp=0.1)
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm: the oracle in the reference's literal structure (two encoder passes, python K loop)
+# ---------------------------------------------------------------------------------------------------
+def cpu_oracle_rate(batch, steps, warmup):
+    import gccvae_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = train_cfg()
+    p = O.init_params(0)
+    mu, _ = O.initialise_mu(cfg)
+    opt = O.KerasAdam(cfg["lr"])
+    x, y, noise = O.make_inputs(batch, k=100)
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        for sup in (True, False):
+            _, g = O.loss_and_grads(p, mu, x, y, noise, cfg, cfg["gating_init_temp"], sup)
+            opt.apply(p, g)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    ms = 1e3 * float(np.mean(times))
+    return 2 * batch / (ms / 1e3), ms
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    rate, ms = cpu_oracle_rate(args.ref_batch, max(1, args.steps), max(1, args.warmup))
+    cores = os.cpu_count() or 1
+    sample = "oracle (PyTorch-CPU restatement of the TF reference), sup+unsup step on batch {} per step".format(
+        args.ref_batch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(args.batch), "reference_sample_batch": args.ref_batch},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# clocks sampler
+# ---------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# our arm
+# ---------------------------------------------------------------------------------------------------
+def run_ours(args, rank, world, local_rank):
+    import torch.distributed as dist
+    import gccvae_b200 as G
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    precision = args.precision
+    if precision == "auto":
+        precision = "bf16" if os.path.exists(os.path.join(ROOT, "semi-supervised-gated-lt-vae_b200",
+                                                           "engine_tc.py")) else "fp32"
+    B = args.batch
+    cfg = train_cfg()
+    lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234)
+
+    # synthetic data: a ring of NBUF different batches (> L2 in total) resident in HBM for `value`,
+    # and the same ring in pinned host memory for `e2e`
+    gen = torch.Generator().manual_seed(1234 + rank)
+    NBUF = 4
+    host_x = [torch.rand(B, 64, 64, 3, generator=gen).pin_memory() for _ in range(NBUF)]
+    host_y = [(torch.rand(B, 18, generator=gen) < 0.5).to(torch.int64).pin_memory() for _ in range(NBUF)]
+    dev_x = [t.to(dev) for t in host_x]
+    dev_y = [t.to(dev) for t in host_y]
+
+    def step_resident(i):
+        j = i % NBUF
+        lrn.train_step(dev_x[j], dev_y[j], True)
+        return lrn.train_step(dev_x[(j + 1) % NBUF], None, False)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup):
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        lrn.lib.gccvae_reset_launch_count()
+        e0.record()
+        for i in range(steps):
+            fn(warmup + i)
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        launches = lrn.lib.gccvae_launch_count()
+        if world > 1:
+            t = torch.tensor([ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms, launches
+
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_total, launches = timed(step_resident, args.steps, max(3, args.warmup))
+    clocks = sampler.stop() if rank == 0 else None
+    ms_step = ms_total / args.steps
+    value = 2 * B * world / (ms_step / 1e3)
+
+    # ---- e2e: host buffers in, loss out, every step --------------------------------------------------------
+    copy_stream = torch.cuda.Stream(device=dev)
+    stage_x = [torch.empty(B, 64, 64, 3, device=dev) for _ in range(2)]
+    stage_y = [torch.empty(B, 18, dtype=torch.int64, device=dev) for _ in range(2)]
+    loss_host = torch.zeros(1).pin_memory()
+
+    def step_e2e(i):
+        # the public API call with HOST (pinned) buffers: H2D of x (sup + unsup batch) and y, D2H of the loss
+        j = i % NBUF
+        lrn.train_step(host_x[j], host_y[j], True)
+        loss, _ = lrn.train_step(host_x[(j + 1) % NBUF], None, False)
+        loss_host.copy_(loss.reshape(1), non_blocking=False)
+
+    ms_e2e, _ = timed(step_e2e, args.steps, 3)
+    ms_e2e_step = ms_e2e / args.steps
+    e2e_value = 2 * B * world / (ms_e2e_step / 1e3)
+    h2d = 2 * B * 64 * 64 * 3 * 4 + B * 18 * 8
+    d2h = 4
+
+    # ---- per-kernel timing for the roofline of the dominant kernel ---------------------------------------------
+    roof = None
+    if hasattr(lrn.engine, "profile_step"):
+        roof = lrn.engine.profile_step(lrn, dev_x[0], dev_y[0])
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
+        "config": {"workload": WORKLOAD.format(B), "step": "1 supervised + 1 unsupervised train_step "
+                   "(fwd+bwd+allreduce+Adam)", "precision": precision, "noise": "in-kernel Philox4x32-10",
+                   "l2": "ring of 4 input batches (201 MB) + ~1 GB of activations per step exceed the 126 MB L2",
+                   "parallelism": "dp{}".format(world)},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": ms_e2e_step},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+    }
+    if roof is not None:
+        pk = peaks.get("hbm_gbs") if roof["bound"] == "hbm" else peaks.get("bf16_tflops_sustained")
+        src = "measured"
+        if pk is None:
+            pk, src = (6650.0 if roof["bound"] == "hbm" else 1590.0), "fallback"
+        roof["peak"], roof["peak_source"] = pk, src
+        roof["frac"] = roof["achieved"] / pk
+        line["roofline"] = roof
+    if not args.no_cpu_baseline:
+        rate, ms = cpu_oracle_rate(args.ref_batch, args.cpu_baseline_steps, 1)
+        line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
+                                "sample": "oracle sup+unsup step, batch {}, {} timed steps ({:.0f} ms each)".format(
+                                    args.ref_batch, args.cpu_baseline_steps, ms)}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus and world == 1 and args.gpus > 1:
+        # launched without torchrun: re-exec under torch.distributed.run
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(args.gpus),
+               "--master-addr", "127.0.0.1", "--master-port", "29531", os.path.abspath(__file__)] + sys.argv[1:]
+        os.execv(sys.executable, cmd)
+    run_ours(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

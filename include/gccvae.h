@@ -1,0 +1,214 @@
+/* gccvae.h — C ABI of the B200-native Gated-CCVAE ELBO-step kernels (libgccvae.so).
+ *
+ * The reference (jabhinav/Semi-Supervised-Gated-LT-VAE) is a pure TensorFlow-2/Keras script with
+ * NO plugin / FFI layer: its boundary is the Python class API of gated_ccvae.py
+ * and networks.py.  This header is the boundary a maintainer would bind underneath that API
+ * (ctypes stub in INTEGRATION.md).  Every entry point cites the reference lines it replaces.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; every pointer is DEVICE memory owned by the caller unless a
+ *    parameter is documented as host memory; nothing is allocated inside the library;
+ *  - all launches are asynchronous on `stream` (a cudaStream_t passed as void*);
+ *  - return value: 0 on success, negative gccvae_status otherwise; gccvae_last_error() returns
+ *    a thread-local message for the last failure on the calling thread;
+ *  - activations are NHWC, fp32 ("f32" entry points) or bf16 ("bf16" entry points);
+ *  - conv kernels are the Keras layouts: Conv2D [kh,kw,Cin,Cout], Conv2DTranspose
+ *    [kh,kw,Cout,Cin], Dense [in,out].  Both conv layouts are [kh,kw,C_L,C_S] where L is the
+ *    tensor with the LARGER spatial extent and S the smaller one, so one "relation" geometry
+ *    describes a layer and three kernels (L->S, S->L, weight-gradient) cover forward, dgrad and
+ *    wgrad of Conv2D, Conv2DTranspose and Dense alike.
+ */
+#ifndef GCCVAE_H
+#define GCCVAE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GCCVAE_ABI_VERSION 1
+
+typedef enum {
+  GCCVAE_OK = 0,
+  GCCVAE_EINVAL = -1, /* bad shape / alignment / null pointer */
+  GCCVAE_EARCH = -2,  /* device is not sm_100 */
+  GCCVAE_ECUDA = -3,  /* CUDA runtime / driver error, see gccvae_last_error() */
+  GCCVAE_ENOMEM = -4  /* caller-provided workspace too small */
+} gccvae_status;
+
+typedef enum { GCCVAE_ACT_NONE = 0, GCCVAE_ACT_RELU = 1, GCCVAE_ACT_SIGMOID = 2 } gccvae_act;
+/* OR-ed into `act`: add the previous contents of the output (out = act(acc + bias + out)) */
+#define GCCVAE_ACT_ACCUMULATE 0x100
+
+/* dimensions fixed by the reference model (gated_ccvae.py:481,517-518; configs.py:10) */
+#define GCCVAE_Z 45
+#define GCCVAE_ZS 27
+#define GCCVAE_ZC 18
+#define GCCVAE_Y 18
+
+int gccvae_abi_version(void);
+const char* gccvae_last_error(void);
+/* 0 if `device` is compute capability 10.x, GCCVAE_EARCH otherwise. */
+int gccvae_arch_check(int device);
+/* number of kernels launched by this library on the calling thread since the last reset */
+long long gccvae_launch_count(void);
+void gccvae_reset_launch_count(void);
+
+/* ---- layer relation ------------------------------------------------------------------------
+ * S[n,oh,ow,cs] <-> L[n, stride*oh - pad + kh, stride*ow - pad + kw, cl] through W[kh,kw,cl,cs].
+ *   Conv2D   (networks.py:11-15,21-29): L = input, S = output.
+ *   Conv2DTranspose (networks.py:45-49,55-58): S = input, L = output.
+ *   Dense    (networks.py:17-18,43): KH=KW=HL=WL=HS=WS=1.                                     */
+typedef struct {
+  int batch;
+  int HL, WL, CL; /* large-spatial side */
+  int HS, WS, CS; /* small-spatial side */
+  int KH, KW, stride, pad;
+} gccvae_geom;
+
+/* S = act( gather(L) * W + bias ) [optionally * (mask > 0)]
+ * = Conv2D / Dense forward, Conv2DTranspose dgrad.  bias, mask may be NULL. */
+int gccvae_ls_f32(const gccvae_geom* g, const float* L, const float* W, const float* bias, int act,
+                  const float* mask, float* S, void* stream);
+/* L = act( scatter(S) * W^T + bias ) [optionally * (mask > 0)]
+ * = Conv2DTranspose forward, Conv2D / Dense dgrad.  Supported: (KH=KW=4,stride 2,pad 1),
+ * and any geometry with HS=WS=1, pad=0, stride=1 (Dense, conv5, conv1t). */
+int gccvae_sl_f32(const gccvae_geom* g, const float* S, const float* W, const float* bias, int act,
+                  const float* mask, float* L, void* stream);
+/* dW[kh,kw,cl,cs] = sum_{n,oh,ow} gather(L) * S  = wgrad of all three layer kinds.
+ * Deterministic split-K: workspace >= gccvae_wg_f32_workspace_bytes(g). */
+size_t gccvae_wg_f32_workspace_bytes(const gccvae_geom* g);
+int gccvae_wg_f32(const gccvae_geom* g, const float* L, const float* S, float* dW, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* out[c] = sum_r in[r*cols + c]   (bias gradients) */
+size_t gccvae_colsum_f32_workspace_bytes(long long rows, int cols);
+int gccvae_colsum_f32(const float* in, long long rows, int cols, float* out, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- gate (gated_ccvae.py:62-64,102-111; networks.py:72-74,83-86,104-106,118-127) ------------
+ * One relaxed-Bernoulli sample c[18,18] per step from mu, shared by the batch and by all K
+ * importance samples, plus the gated parameter products the latent kernels consume.
+ * U1,U2: explicit uniforms [18,18], or NULL to draw them from Philox4x32-10(seed, offset [+ *step_dev]).
+ * c_in (optional): use this c instead of sampling (classifier_loss(x,y,c), gated_ccvae.py:167); then
+ * mu/U1/U2 are ignored and dc/dmu is zero.
+ * gate_ws: >= GCCVAE_GATE_WS_FLOATS floats: c | M=c*Wcls | bcls | P_lt | P_lf | P_st | P_sf | dc/dmu
+ * (P_x[j,i] = c[i,j]*W_x[j,i]; dc/dmu is kept for gccvae_gate_bwd).  `c_out` (may be NULL) receives a copy of c. */
+#define GCCVAE_GATE_WS_FLOATS (7 * 324 + 32)
+int gccvae_gate_fwd(const float* mu, const float* c_in, const float* U1, const float* U2, uint64_t seed,
+                    uint64_t offset, const int* step_dev, float temperature, const float* Wcls, const float* bcls, const float* Wlt,
+                    const float* Wlf, const float* Wst, const float* Wsf, float* gate_ws, float* c_out,
+                    void* stream);
+
+/* ---- fused latent kernel (SURVEY.md A3,A6-A10,A12,A13) ------------------------------------------
+ * forward: reparameterised z, gated classifier q(y|z_c,c), (sup) K-sample log q(y|x),
+ * (unsup) label sampling, conditional prior p(z_c|y,c), KL, importance weight w.
+ *   gated_ccvae.py:237-268,280-287 (sup), :187-218 (unsup), :167-182 (K loop);
+ *   networks.py:17-18,33-34 (relu / clipped softplus of the posterior heads).              */
+typedef struct {
+  int batch;         /* images on this rank */
+  int batch_global;  /* divisor of the mean (data parallel: sum of all ranks' batches) */
+  int supervised;    /* 1: sup_loss, 0: unsup_loss */
+  int K;             /* importance samples (gated_ccvae.py:167, k=100); ignored when unsup */
+  /* inputs */
+  const float* loc_pre;    /* [B,45] encoder locs head BEFORE relu */
+  const float* scale_pre;  /* [B,45] encoder std head BEFORE softplus/clip */
+  const long long* y;      /* [B,18] int64 labels (sup) */
+  const float* eps;        /* [B,45] N(0,1) or NULL -> Philox */
+  const float* eps_k;      /* [K,B,18] N(0,1) for the classify dims (cols 27: of the reference's
+                              [K,B,45] draw) or NULL -> Philox */
+  const float* U_y;        /* [B,18] uniforms (unsup) or NULL -> Philox */
+  uint64_t seed, offset;   /* Philox key / per-step counter base */
+  const int* step_dev;     /* optional device int added to `offset` (CUDA-graph replay) */
+  const float* gate_ws;    /* from gccvae_gate_fwd */
+  /* outputs */
+  float* loc;    /* [B,45] */
+  float* scale;  /* [B,45] */
+  float* z;      /* [B,45] */
+  float* terms;  /* [6,B]: kl | log_qy_zc | log_qy_x | w | log_py | coef_pxz (= -w/batch_global) */
+  float* logits; /* [B,18] */
+  int* y_out;    /* [B,18] int32 sampled labels (unsup) or copy of y (sup); may be NULL */
+} gccvae_latent_fwd_args;
+int gccvae_latent_fwd(const gccvae_latent_fwd_args* a, void* stream);
+
+/* backward of the same: consumes dz (from the decoder) and log_pxz, produces the gradients of
+ * the two encoder heads' pre-activations and per-CTA partial sums of the small parameters,
+ * which gccvae_gate_bwd reduces.  (gradient routes: SURVEY.md §8a "Gradient routes") */
+#define GCCVAE_LATENT_PARTIAL_FLOATS (5 * 324 + 32)
+typedef struct {
+  int batch, batch_global, supervised, K;
+  const float* loc_pre;
+  const float* scale_pre;
+  const int* y;          /* [B,18] int32 labels as written to y_out by the forward */
+  const float* eps;
+  const float* eps_k;
+  uint64_t seed, offset;
+  const int* step_dev;
+  const float* gate_ws;
+  const float* terms;    /* [6,B] from the forward */
+  const float* log_pxz;  /* [B] */
+  const float* dz;       /* [B,45] dLoss/dz from the decoder */
+  float* dloc_pre;       /* [B,45] */
+  float* dscale_pre;     /* [B,45] */
+  float* partials;       /* [n_partials, GCCVAE_LATENT_PARTIAL_FLOATS] */
+  int n_partials;        /* = gccvae_latent_bwd_partials(batch) */
+  float* loss_out;       /* [1]: sum_b -(elbo_b)/batch_global for this rank (no L1 term) */
+} gccvae_latent_bwd_args;
+int gccvae_latent_bwd_partials(int batch);
+int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream);
+
+/* reduce the partials; chain through c to mu (clip / pow / ratio of gated_ccvae.py:103-109) and
+ * add the L1 term gating_reg*mean|mu| (gated_ccvae.py:229-230,297-298) scaled by l1_scale
+ * (1/world in data parallel).  d* may be NULL when the tensor is frozen. */
+int gccvae_gate_bwd(const float* partials, int n_partials, const float* mu, const float* Wcls,
+                    const float* Wlt, const float* Wlf, const float* Wst, const float* Wsf,
+                    const float* gate_ws, float gating_reg, float l1_scale, float* dWcls, float* dbcls,
+                    float* dWlt, float* dWlf, float* dWst, float* dWsf, float* dmu, float* loss_inout,
+                    void* stream);
+
+/* ---- reconstruction log-likelihood (utils.py:101-105) ---------------------------------------------
+ * log_pxz[b] = -sum|x - xhat| - 12288 ln2; optionally also the gradient w.r.t. the decoder's
+ * pre-sigmoid logits, dlogit = coef[b] * sign(x - xhat) * xhat (1 - xhat). */
+int gccvae_recon_f32(const float* x, const float* xhat, int batch, int per_image, const float* coef,
+                     float* log_pxz, float* dlogit, void* stream);
+
+/* ---- Keras-2.8 Adam on the flat parameter buffer (gated_ccvae.py:144,310) ---------------------------
+ * theta -= lr*sqrt(1-b2^t)/(1-b1^t) * m/(sqrt(v)+eps); `step` is t (1-based).  If `step_dev`
+ * (device int) is given it is incremented first and used as t, so a captured CUDA graph of the
+ * whole step can be replayed. */
+int gccvae_adam_f32(float* param, const float* grad, float* m, float* v, long long n, float lr,
+                    float beta1, float beta2, float eps, int step, int* step_dev, void* stream);
+
+/* loss[0] = sum_b(-elbo_b)/batch_global (+ gating_reg*mean|mu| when mu != NULL): the forward-only
+ * value of sup_loss / unsup_loss (gated_ccvae.py:225-230, 291-298). */
+int gccvae_elbo_loss_f32(const float* terms, const float* log_pxz, int batch, int batch_global,
+                         int supervised, const float* mu, float gating_reg, float* loss, void* stream);
+
+/* networks.py:17-18,33-34: loc = relu(loc_pre), scale = clip(softplus(scale_pre), 1e-3, 1e3). */
+int gccvae_head_act_f32(const float* loc_pre, const float* scale_pre, long long n, float* loc, float* scale,
+                        void* stream);
+/* gated_ccvae.py:436-445: out[0] = mean( round(sigmoid(logits)) == y ), y int64, n = B*18. */
+int gccvae_accuracy_f32(const float* logits, const long long* y, int n, float* out, void* stream);
+
+/* test/debug aid: write the noise the kernels would draw in Philox mode.
+ * kind 0: eps [B,45]; 1: eps_k [K,B,18]; 2: U_y [B,18]; 3: U1|U2 [2,18,18]. */
+int gccvae_draw_noise_f32(int kind, uint64_t seed, uint64_t offset, int batch, int K, float* out, void* stream);
+
+/* ---- tiled module API (networks.py:72-74,83-86,104-106,118-127) --------------------------------------
+ * logits[b,j] = sum_i zt[b,i,j]*gates[i,j]*W[i,j] + bias[j];  zt strides allow broadcasting. */
+int gccvae_classifier_tiled_f32(const float* zt, long long sb, long long si, long long sj, int batch,
+                                const float* gates, const float* W, const float* bias, float* logits,
+                                void* stream);
+/* (loc,scale)[b,i] from tiled y[b,j,i], c[i,j] and the four [j,i] kernels. */
+int gccvae_cond_prior_tiled_f32(const float* yt, long long sb, long long sj, long long si, int batch,
+                                const float* c, const float* Wlt, const float* Wlf, const float* Wst,
+                                const float* Wsf, float* loc, float* scale, void* stream);
+/* sum_d KL(N(lq,sq) || N(lp,sp)) over `dims` (utils.py:108-119); lp/sp may be NULL (0 / 1). */
+int gccvae_gaussian_kl_f32(const float* lq, const float* sq, const float* lp, const float* sp, int batch,
+                           int dims, float* out, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GCCVAE_H */

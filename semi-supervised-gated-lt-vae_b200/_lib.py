@@ -1,0 +1,117 @@
+"""ctypes binding of libgccvae.so (include/gccvae.h).  There is NO fallback: if the library is
+missing or fails to load, every op raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import threading
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "csrc", "libgccvae.so")
+
+ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ACCUMULATE = 0, 1, 2, 0x100
+GATE_WS_FLOATS = 7 * 324 + 32
+LATENT_PARTIAL_FLOATS = 5 * 324 + 32
+
+
+class Geom(C.Structure):
+    """gccvae_geom: the L<->S relation of one layer (include/gccvae.h)."""
+    _fields_ = [(n, C.c_int) for n in ("batch", "HL", "WL", "CL", "HS", "WS", "CS", "KH", "KW", "stride", "pad")]
+
+
+
+class LatentFwdArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("batch_global", C.c_int), ("supervised", C.c_int), ("K", C.c_int),
+        ("loc_pre", C.c_void_p), ("scale_pre", C.c_void_p), ("y", C.c_void_p), ("eps", C.c_void_p),
+        ("eps_k", C.c_void_p), ("U_y", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("step_dev", C.c_void_p), ("gate_ws", C.c_void_p), ("loc", C.c_void_p), ("scale", C.c_void_p), ("z", C.c_void_p),
+        ("terms", C.c_void_p), ("logits", C.c_void_p), ("y_out", C.c_void_p),
+    ]
+
+
+class LatentBwdArgs(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int), ("batch_global", C.c_int), ("supervised", C.c_int), ("K", C.c_int),
+        ("loc_pre", C.c_void_p), ("scale_pre", C.c_void_p), ("y", C.c_void_p), ("eps", C.c_void_p),
+        ("eps_k", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("step_dev", C.c_void_p),
+        ("gate_ws", C.c_void_p),
+        ("terms", C.c_void_p), ("log_pxz", C.c_void_p), ("dz", C.c_void_p), ("dloc_pre", C.c_void_p),
+        ("dscale_pre", C.c_void_p), ("partials", C.c_void_p), ("n_partials", C.c_int), ("loss_out", C.c_void_p),
+    ]
+
+
+_P, _I, _F, _LL, _SZ, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_uint64
+_G = C.POINTER(Geom)
+
+# name -> (restype, argtypes); mirrors include/gccvae.h one to one
+SIGNATURES = {
+    "gccvae_abi_version": (_I, []),
+    "gccvae_last_error": (C.c_char_p, []),
+    "gccvae_arch_check": (_I, [_I]),
+    "gccvae_launch_count": (_LL, []),
+    "gccvae_reset_launch_count": (None, []),
+    "gccvae_ls_f32": (_I, [_G, _P, _P, _P, _I, _P, _P, _P]),
+    "gccvae_sl_f32": (_I, [_G, _P, _P, _P, _I, _P, _P, _P]),
+    "gccvae_wg_f32_workspace_bytes": (_SZ, [_G]),
+    "gccvae_wg_f32": (_I, [_G, _P, _P, _P, _P, _SZ, _P]),
+    "gccvae_colsum_f32_workspace_bytes": (_SZ, [_LL, _I]),
+    "gccvae_colsum_f32": (_I, [_P, _LL, _I, _P, _P, _SZ, _P]),
+    "gccvae_gate_fwd": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),
+    "gccvae_latent_bwd_partials": (_I, [_I]),
+    "gccvae_latent_bwd": (_I, [C.POINTER(LatentBwdArgs), _P]),
+    "gccvae_gate_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gccvae_recon_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
+    "gccvae_adam_f32": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _P, _P]),
+    "gccvae_elbo_loss_f32": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P]),
+    "gccvae_draw_noise_f32": (_I, [_I, _U64, _U64, _I, _I, _P, _P]),
+    "gccvae_head_act_f32": (_I, [_P, _P, _LL, _P, _P, _P]),
+    "gccvae_accuracy_f32": (_I, [_P, _P, _I, _P, _P]),
+    "gccvae_classifier_tiled_f32": (_I, [_P, _LL, _LL, _LL, _I, _P, _P, _P, _P, _P]),
+    "gccvae_cond_prior_tiled_f32": (_I, [_P, _LL, _LL, _LL, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
+    "gccvae_gaussian_kl_f32": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+}
+
+
+class GccvaeError(RuntimeError):
+    pass
+
+
+_lock = threading.Lock()
+_lib = None
+
+
+def load():
+    """Load (once) and return the ctypes library.  Raises GccvaeError if it is not built."""
+    global _lib
+    with _lock:
+        if _lib is not None:
+            return _lib
+        if not os.path.exists(LIB_PATH):
+            raise GccvaeError(
+                "libgccvae.so is not built ({}).  Run `python __graft_entry__.py build` (needs nvcc). "
+                "There is no CPU or PyTorch fallback for the Gated-CCVAE kernels.".format(LIB_PATH))
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            try:
+                fn = getattr(lib, name)
+            except AttributeError as e:
+                raise GccvaeError("libgccvae.so does not export {} (stale build?)".format(name)) from e
+            fn.restype = res
+            fn.argtypes = args
+        if lib.gccvae_abi_version() != 1:
+            raise GccvaeError("libgccvae.so ABI version mismatch")
+        _lib = lib
+        return lib
+
+
+def check(rc: int, what: str = ""):
+    if rc != 0:
+        msg = load().gccvae_last_error()
+        raise GccvaeError("{} failed (status {}): {}".format(what or "gccvae call", rc, (msg or b"").decode()))
+
+
+def ptr(t):
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()

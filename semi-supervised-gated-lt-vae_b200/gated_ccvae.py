@@ -1,0 +1,374 @@
+"""Host-side mirror of the reference's CCVAE / Learner (gated_ccvae.py:23-311, 421-455) on top of the
+sm_100a kernels.  Same class names, constructor arguments, method names and return conventions:
+
+    learner = Learner(ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config)
+    loss, c = learner.sup_loss(x, y)         # gated_ccvae.py:234-300
+    loss, c = learner.unsup_loss(x)          # :184-232
+    lqx     = learner.classifier_loss(x, y, c, k=100)   # :167-182
+    loss, c = learner.train_step(x, y, supervised)      # :302-311  (fwd + bwd + Adam)
+    acc     = learner.classifier_accuracy(x, y)         # :421-446
+
+Extensions the reference lacks (needed for parity testing and for data parallelism):
+  * every stochastic call takes an optional `noise=` dict of explicit draws
+    (eps [B,45], eps_k [K,B,45], U_y [B,18], U1/U2 [18,18]); without it noise comes from an
+    in-kernel Philox4x32-10 keyed by (seed, step counter);
+  * `Learner.last` exposes every per-image term of the last loss call;
+  * if torch.distributed is initialised the step is data parallel: the batch given to each rank is
+    its shard, gradients are all-reduced (sum) over the flat gradient buffer, the loss is the global
+    mean, and the gate sample c is identical on all ranks.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import logging
+import math
+import os
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, LatentBwdArgs, LatentFwdArgs, ptr
+from .engine import Engine, _stream
+from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
+from .params import ParamStore, keras_default_init
+from .utils_data import load_learned_gating_matrix
+
+logger = logging.getLogger(__name__)
+
+
+class CCVAE:
+    """gated_ccvae.py:23-111."""
+
+    def __init__(self, z_dim, z_classify, y_dim, train_config, device=None, precision="fp32", init_seed=0):
+        if (z_dim, z_classify, y_dim) != (45, 18, 18):
+            raise ValueError("the sm_100a kernels are specialised for z_dim=45, z_classify=y_dim=18")
+        self.z_dim = z_dim
+        self.z_classify = z_classify
+        self.z_style = z_dim - z_classify
+        self.y_dim = y_dim
+        self.device = torch.device(device) if device is not None else _default_device()
+        self.store = ParamStore(self.device)
+        keras_default_init(self.store, init_seed)
+        self.engine = make_engine(self.store, precision)
+        self.lib = self.engine.lib
+        kw = dict(store=self.store, engine=self.engine)
+        self.encoder = Encoder(z_dim, **kw)
+        self.decoder = Decoder(hidden_dim=z_dim, **kw)
+        self.classifier = Classifier(y_dim, **kw)
+        self.cond_prior = Conditional_Prior(z_classify, **kw)
+        self.initialise_mu(train_config)
+
+    # gated_ccvae.py:42-60
+    def initialise_mu(self, train_config):
+        gt, gs = train_config["gate_type"], train_config.get("gate_subtype")
+        if gt == "learnable":
+            logging.info("Initialising mu with fixed value (learnable)")
+            mu_init, self.mu_trainable = np.asarray(train_config["mu_init"]), True
+        elif gt == "fixed" and gs == "inferred":
+            logging.info("Initialising mu with fixed value")
+            mu_init, self.mu_trainable = np.asarray(train_config["mu_init"]), False
+        elif gt == "fixed" and gs == "one-one":
+            mu_init, self.mu_trainable = np.eye(self.z_classify, self.y_dim), False
+        else:
+            raise ValueError("Invalid gate type/subtype: {}/{}".format(gt, gs))
+        if mu_init.shape != (self.z_classify, self.y_dim):
+            raise ValueError("mu_init must be [{}, {}], got {}".format(self.z_classify, self.y_dim, mu_init.shape))
+        with torch.no_grad():
+            self.store.view("mu").copy_(torch.from_numpy(mu_init.astype(np.float32)))
+
+    @property
+    def mu(self):
+        return self.store.view("mu")
+
+    @property
+    def trainable_variables(self):
+        names = [k for k in self.store.names() if k != "mu" or self.mu_trainable]
+        return [self.store.view(k) for k in names]
+
+    # gated_ccvae.py:90-93 (explicit noise instead of tf.random)
+    def sample_normal(self, mu, std, latent_dim, epsilon=None):
+        mu, std = as_device_f32(mu, self.device), as_device_f32(std, self.device)
+        if epsilon is None:
+            epsilon = torch.randn_like(std)
+        return (mu + std * as_device_f32(epsilon, self.device)).reshape(-1, latent_dim)
+
+    # gated_ccvae.py:102-111
+    def sample_gating_parameter(self, mu, temperature, EPSILON=1e-20, U1=None, U2=None, seed=0, offset=0):
+        if EPSILON != 1e-20:
+            raise ValueError("the gate kernel hard-codes EPSILON=1e-20 (gated_ccvae.py:102)")
+        mu = as_device_f32(mu, self.device)
+        ws = torch.empty(GATE_WS_FLOATS, dtype=torch.float32, device=self.device)
+        c = torch.empty(18, 18, dtype=torch.float32, device=self.device)
+        U1 = None if U1 is None else as_device_f32(U1, self.device)
+        U2 = None if U2 is None else as_device_f32(U2, self.device)
+        v = self.store.view
+        _lib.check(self.lib.gccvae_gate_fwd(ptr(mu), None, ptr(U1), ptr(U2), seed, offset, None, float(temperature),
+                                            ptr(v("cls.w")), ptr(v("cls.b")), ptr(v("prior.loc_true")),
+                                            ptr(v("prior.loc_false")), ptr(v("prior.scale_true")),
+                                            ptr(v("prior.scale_false")), ptr(ws), ptr(c), _stream()), "gate_fwd")
+        return c
+
+
+def make_engine(store, precision):
+    if precision == "fp32":
+        return Engine(store)
+    if precision == "bf16":
+        from .engine_tc import EngineTC
+        return EngineTC(store)
+    raise ValueError("precision must be 'fp32' or 'bf16', got {!r}".format(precision))
+
+
+class KerasAdam:
+    """tf.keras.optimizers.Adam(lr) of Keras 2.8 (gated_ccvae.py:144): beta_1=.9, beta_2=.999,
+    epsilon=1e-7 outside the sqrt; one fused kernel over the flat parameter buffer."""
+
+    def __init__(self, lr, store, n_params, beta_1=0.9, beta_2=0.999, epsilon=1e-7):
+        self.lr, self.beta_1, self.beta_2, self.epsilon = float(lr), beta_1, beta_2, epsilon
+        self.store, self.n = store, n_params
+        self.m = torch.zeros_like(store.flat)
+        self.v = torch.zeros_like(store.flat)
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=store.device)  # t, bumped on device
+        self.lib = _lib.load()
+
+    @property
+    def iterations(self):
+        return int(self.step_dev.item())
+
+    def apply_gradients(self):
+        _lib.check(self.lib.gccvae_adam_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
+                                            self.n, self.lr, self.beta_1, self.beta_2, self.epsilon, 0,
+                                            ptr(self.step_dev), _stream()), "adam")
+
+
+class Learner:
+    """gated_ccvae.py:114-311, 421-455."""
+
+    def __init__(self, ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config, device=None,
+                 precision="fp32", seed=1234, init_seed=0):
+        if tuple(ip_shape) != (64, 64, 3):
+            raise ValueError("the kernels are specialised for 64x64x3 inputs (gated_ccvae.py:481)")
+        self.train_config = train_config
+        self.ip_shape = tuple(ip_shape)
+        self.z_dim, self.z_classify, self.z_style, self.y_dim = z_dim, z_classify, z_dim - z_classify, y_dim
+        self.supervision = supervision
+        self.eps = 1e-20
+        self.lr = train_config["lr"]
+        self.alpha = 0.1 * num_samples
+        self.latent_sampler_temp = train_config.get("init_temp", 0.1)
+        self.gating_sampler_temp = train_config["gating_init_temp"]
+        self.model = CCVAE(z_dim, z_classify, y_dim, train_config, device=device, precision=precision,
+                           init_seed=init_seed)
+        self.device = self.model.device
+        self.p_Y = torch.full((1, y_dim), 0.5, dtype=torch.float32, device=self.device)  # gated_ccvae.py:141
+        self.store, self.engine, self.lib = self.model.store, self.model.engine, self.model.lib
+        self.n_trainable = self.store.total if self.model.mu_trainable else self.store.n_without_mu
+        self.optimiser = KerasAdam(self.lr, self.store, self.n_trainable)
+        self.seed = int(seed)
+        self.last = {}
+        self._lat = {}
+        self._gate_ws = torch.zeros(GATE_WS_FLOATS, dtype=torch.float32, device=self.device)
+        self._c = torch.zeros(18, 18, dtype=torch.float32, device=self.device)
+        self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
+        self._acc = torch.zeros(1, dtype=torch.float32, device=self.device)
+        # data parallel
+        import torch.distributed as dist
+        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
+        self.world = self._dist.get_world_size() if self._dist else 1
+        self.rank = self._dist.get_rank() if self._dist else 0
+
+    # ---- buffers of the latent stage -------------------------------------------------------------------
+    def _latent_bufs(self, B):
+        lb = self._lat.get(B)
+        if lb is None:
+            e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=self.device)
+            npart = self.lib.gccvae_latent_bwd_partials(B)
+            lb = dict(loc=e(B, 45), scale=e(B, 45), z=e(B, 45), terms=e(6, B), logits=e(B, 18),
+                      y_i32=e(B, 18, dt=torch.int32), log_pxz=e(B), partials=e(npart, LATENT_PARTIAL_FLOATS),
+                      npart=npart)
+            self._lat[B] = lb
+        return lb
+
+    def _prep_inputs(self, x, y):
+        x = as_device_f32(x, self.device)
+        if x.dim() != 4 or tuple(x.shape[1:]) != self.ip_shape:
+            raise ValueError("x must be [B,64,64,3] NHWC, got {}".format(tuple(x.shape)))
+        if y is not None:
+            y = (torch.as_tensor(y) if not torch.is_tensor(y) else y).to(self.device, torch.int64,
+                                                                         non_blocking=True).contiguous()
+            if tuple(y.shape) != (x.shape[0], self.y_dim):
+                raise ValueError("y must be [B,{}], got {}".format(self.y_dim, tuple(y.shape)))
+        return x, y
+
+    def _noise(self, noise, B, supervised, K):
+        n = {}
+        noise = noise or {}
+        for k in ("eps", "eps_k", "U_y", "U1", "U2"):
+            v = noise.get(k)
+            n[k] = None if v is None else as_device_f32(v, self.device)
+        if not supervised:
+            n["eps_k"] = None
+        if n["eps_k"] is not None:
+            ek = n["eps_k"]
+            if ek.shape[-1] == self.z_dim:
+                ek = ek[..., self.z_style:].clone()   # only the classify dims are consumed (:173)
+            if tuple(ek.shape) != (K, B, self.z_classify):
+                raise ValueError("eps_k must be [K,B,45] or [K,B,18], got {}".format(tuple(ek.shape)))
+            n["eps_k"] = ek
+        if (n["U1"] is None) != (n["U2"] is None):
+            raise ValueError("U1 and U2 go together")
+        return n
+
+    # ---- the ELBO step ----------------------------------------------------------------------------------------
+    def _gate(self, n, c_in=None, temperature=None):
+        v = self.store.view
+        T = float(self.gating_sampler_temp if temperature is None else temperature)
+        _lib.check(self.lib.gccvae_gate_fwd(ptr(self.store.view("mu")), ptr(c_in), ptr(n["U1"]), ptr(n["U2"]),
+                                            self.seed, 0, ptr(self.optimiser.step_dev), T, ptr(v("cls.w")),
+                                            ptr(v("cls.b")), ptr(v("prior.loc_true")), ptr(v("prior.loc_false")),
+                                            ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
+                                            ptr(self._gate_ws), ptr(self._c), _stream()), "gate_fwd")
+
+    def _latent_fwd(self, B, lb, b, y, n, supervised, K):
+        a = LatentFwdArgs()
+        a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
+        a.loc_pre, a.scale_pre = ptr(b["enc.locs.out"]), ptr(b["enc.std.out"])
+        a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
+        a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
+        a.step_dev = ptr(self.optimiser.step_dev)
+        a.gate_ws = ptr(self._gate_ws)
+        a.loc, a.scale, a.z, a.terms, a.logits, a.y_out = (ptr(lb["loc"]), ptr(lb["scale"]), ptr(lb["z"]),
+                                                           ptr(lb["terms"]), ptr(lb["logits"]), ptr(lb["y_i32"]))
+        _lib.check(self.lib.gccvae_latent_fwd(C.byref(a), _stream()), "latent_fwd")
+
+    def _latent_bwd(self, B, lb, b, n, supervised, K):
+        a = LatentBwdArgs()
+        a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
+        a.loc_pre, a.scale_pre = ptr(b["enc.locs.out"]), ptr(b["enc.std.out"])
+        a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
+        a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
+        a.step_dev = ptr(self.optimiser.step_dev)
+        a.gate_ws, a.terms, a.log_pxz, a.dz = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"]), ptr(b["dz"])
+        a.dloc_pre, a.dscale_pre = ptr(b["enc.locs.dout"]), ptr(b["enc.std.dout"])
+        a.partials, a.n_partials, a.loss_out = ptr(lb["partials"]), lb["npart"], None
+        _lib.check(self.lib.gccvae_latent_bwd(C.byref(a), _stream()), "latent_bwd")
+
+    def _elbo(self, x, y, supervised, noise=None, backward=False, k=100):
+        x, y = self._prep_inputs(x, y if supervised else None)
+        B = x.shape[0]
+        n = self._noise(noise, B, supervised, k)
+        b, lb = self.engine.bufs(B), self._latent_bufs(B)
+        st = _stream()
+        learnable = self.model.mu_trainable
+        self._gate(n)
+        self.engine.encoder_fwd(x, b)
+        self._latent_fwd(B, lb, b, y, n, supervised, k)
+        xhat = self.engine.decoder_fwd(lb["z"], b)
+        coef = lb["terms"][5]
+        dlogit = b["dec.conv5t.dout"] if backward else None
+        _lib.check(self.lib.gccvae_recon_f32(ptr(x), ptr(xhat), B, 64 * 64 * 3, ptr(coef) if backward else None,
+                                             ptr(lb["log_pxz"]), ptr(dlogit), st), "recon")
+        if backward:
+            self.engine.decoder_bwd(lb["z"], b)
+            self._latent_bwd(B, lb, b, n, supervised, k)
+            v, g = self.store.view, self.store.g
+            _lib.check(self.lib.gccvae_gate_bwd(
+                ptr(lb["partials"]), lb["npart"], ptr(v("mu")), ptr(v("cls.w")), ptr(v("prior.loc_true")),
+                ptr(v("prior.loc_false")), ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
+                ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), 1.0 / self.world,
+                ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
+                ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
+                ptr(self._loss), st), "gate_bwd")
+            self.engine.encoder_bwd(x, b)
+        else:
+            _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B, B * self.world,
+                                                     int(supervised), ptr(v_mu(self)) if learnable else None,
+                                                     float(self.train_config.get("gating_reg", 0.0)) / self.world,
+                                                     ptr(self._loss), st), "elbo_loss")
+        t = lb["terms"]
+        self.last = dict(post_locs=lb["loc"], post_scales=lb["scale"], z=lb["z"], logits=lb["logits"], kl=t[0],
+                         log_qy_zc=t[1], log_qy_x=t[2], w=t[3], log_py=t[4], log_pxz=lb["log_pxz"], recon=xhat,
+                         y=lb["y_i32"], c=self._c, supervised=supervised)
+        return self._loss[0], self._c
+
+    # ---- reference API ---------------------------------------------------------------------------------------------
+    def sup_loss(self, x, y, noise=None, k=100):
+        """gated_ccvae.py:234-300 -> (loss, c).  Forward only; train_step also runs the backward."""
+        loss, c = self._elbo(x, y, True, noise, backward=False, k=k)
+        return self._global_loss(loss).clone(), c.clone()
+
+    def unsup_loss(self, x, noise=None):
+        """gated_ccvae.py:184-232 -> (loss, c)."""
+        loss, c = self._elbo(x, None, False, noise, backward=False)
+        return self._global_loss(loss).clone(), c.clone()
+
+    def classifier_loss(self, x, y, c, k=100, noise=None):
+        """gated_ccvae.py:167-182: log q(y|x) ~ logsumexp_k log q(y|z_c^k, c) - log k  -> [B]."""
+        x, y = self._prep_inputs(x, y)
+        B = x.shape[0]
+        n = self._noise(noise, B, True, k)
+        b, lb = self.engine.bufs(B), self._latent_bufs(B)
+        self._gate(n, c_in=as_device_f32(c, self.device))
+        self.engine.encoder_fwd(x, b)
+        self._latent_fwd(B, lb, b, y, n, True, k)
+        return lb["terms"][2].clone()
+
+    def loss_and_grads(self, x, y, supervised, noise=None, k=100):
+        """forward + backward without the optimiser: (loss, c), gradients in self.store.grad."""
+        loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
+        self._allreduce_grads()
+        return self._global_loss(loss).clone(), c.clone()
+
+    def train_step(self, x, y, supervised, noise=None, k=100):
+        """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update."""
+        loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
+        self._allreduce_grads()
+        self.optimiser.apply_gradients()
+        return self._global_loss(loss), c
+
+    def classifier_accuracy(self, x, y, noise=None):
+        """gated_ccvae.py:421-446."""
+        x, y = self._prep_inputs(x, y)
+        B = x.shape[0]
+        n = self._noise(noise, B, False, 0)
+        b, lb = self.engine.bufs(B), self._latent_bufs(B)
+        self._gate(n)
+        self.engine.encoder_fwd(x, b)
+        self._latent_fwd(B, lb, b, None, n, False, 0)
+        _lib.check(self.lib.gccvae_accuracy_f32(ptr(lb["logits"]), ptr(y), B * self.y_dim, ptr(self._acc),
+                                                _stream()), "accuracy")
+        return self._acc[0].clone()
+
+    def accuracy(self, data_loader):
+        """gated_ccvae.py:448-455 (data_loader.step() yields (xs, ys); .n_s = number of samples)."""
+        acc = 0.0
+        iterator = iter(data_loader.step())
+        num_batches = math.ceil(data_loader.n_s / self.train_config["batch_size"])
+        for _ in range(int(num_batches)):
+            xs, ys = next(iterator)
+            acc += float(self.classifier_accuracy(xs, ys))
+        return acc / num_batches
+
+    def load_model(self, param_dir, model_id):
+        """gated_ccvae.py:146-165.  Only the learned gating matrix (.npy) is on the ELBO path; the Keras
+        .h5 weight files need an HDF5 reader and are not read here."""
+        if self.train_config["gate_type"] == "learnable":
+            mu_init = load_learned_gating_matrix(param_dir, model_id)
+            with torch.no_grad():
+                self.store.view("mu").copy_(torch.from_numpy(np.asarray(mu_init, dtype=np.float32)))
+            logging.info("Loaded learned mu")
+
+    # ---- data parallel ---------------------------------------------------------------------------------------------------
+    def _allreduce_grads(self):
+        if self._dist is not None and self.world > 1:
+            self._dist.all_reduce(self.store.grad[: self.n_trainable], op=self._dist.ReduceOp.SUM)
+
+    def _global_loss(self, loss):
+        if self._dist is not None and self.world > 1:
+            loss = loss.clone()
+            self._dist.all_reduce(loss, op=self._dist.ReduceOp.SUM)
+        return loss
+
+
+def v_mu(learner):
+    return learner.store.view("mu")
