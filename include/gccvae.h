@@ -87,6 +87,23 @@ size_t gccvae_colsum_f32_workspace_bytes(long long rows, int cols);
 int gccvae_colsum_f32(const float* in, long long rows, int cols, float* out, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* ---- bf16 tensor-core path (tcgen05 + TMEM + TMA), NHWC bf16 activations ------------------------------
+ * Same relation as the f32 entry points; weights are pre-packed bf16 GEMM operands:
+ *   which=0 "ls": [CS (padded to 16)][(kh,kw,cl)]      used by gccvae_ls_bf16
+ *   which=1 "sl": k4/s2/p1: [4 phases][CL (padded to 16)][(th,tw,cs)]; 1x1-spatial S: W itself as bf16.
+ * out_f32 != 0 stores the result as fp32 instead of bf16.                                           */
+size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
+int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, void* Wp_ls, void* Wp_sl, void* stream);
+int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const float* bias, int act,
+                   const void* mask, void* S, int out_f32, void* stream);
+int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const float* bias, int act,
+                   const void* mask, void* L, int out_f32, void* stream);
+int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream);
+int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream);
+/* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
+int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
+                       int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream);
+
 /* ---- gate (gated_ccvae.py:62-64,102-111; networks.py:72-74,83-86,104-106,118-127) ------------
  * One relaxed-Bernoulli sample c[18,18] per step from mu, shared by the batch and by all K
  * importance samples, plus the gated parameter products the latent kernels consume.

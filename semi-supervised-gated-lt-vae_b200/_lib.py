@@ -57,6 +57,13 @@ SIGNATURES = {
     "gccvae_wg_f32": (_I, [_G, _P, _P, _P, _P, _SZ, _P]),
     "gccvae_colsum_f32_workspace_bytes": (_SZ, [_LL, _I]),
     "gccvae_colsum_f32": (_I, [_P, _LL, _I, _P, _P, _SZ, _P]),
+    "gccvae_packed_weight_elems": (_SZ, [_G, _I]),
+    "gccvae_pack_weights_bf16": (_I, [_G, _P, _P, _P, _P]),
+    "gccvae_ls_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "gccvae_sl_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
+    "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
+    "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),
     "gccvae_gate_fwd": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),
     "gccvae_latent_bwd_partials": (_I, [_I]),

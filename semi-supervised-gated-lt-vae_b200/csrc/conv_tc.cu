@@ -1,0 +1,520 @@
+// bf16 tensor-core path of the encoder / decoder convolutions (networks.py:11-15,45-49):
+// implicit GEMM on tcgen05 (accumulators in TMEM), operands staged in shared memory by TMA.
+//
+// "tap-GEMM" (this file): for a tile of 128 output pixels,
+//     D[128, N] = sum_{tap t} sum_{chunk c}  A_t[128, KC] * B_t[N, KC]^T
+// where A_t is ONE 4-D TMA box of the NHWC activation tensor, shifted by the tap's (dh, dw) and (for
+// stride-2 convolutions) traversed with elementStrides (1,2,2,1); out-of-image coordinates are
+// zero-filled by TMA, which implements the padding.  B_t is a 2-D TMA box of the pre-packed bf16
+// weight matrix.  Both land in the canonical K-major swizzled layout the UMMA descriptors expect
+// (swizzle width = KC*2 bytes).  The same kernel runs
+//   * L->S  (Conv2D forward / Conv2DTranspose dgrad): 16 taps, stride-2 box,
+//   * S->L  (Conv2DTranspose forward / Conv2D dgrad): 4 output-parity phases (blockIdx.z) x 4 taps,
+//   * dense (conv5 as [B,2048]x[2048,256], ...): 1 tap, many chunks.
+// Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
+// (TMEM -> registers -> bias/activation/mask -> bf16 -> global).  One tile per CTA; several CTAs are
+// resident per SM so one CTA's epilogue overlaps another's main loop.
+#include <string.h>
+
+#include <mutex>
+
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gccvae {
+using namespace tc;
+
+struct alignas(64) TapGemmParams {
+  CUtensorMap tmA, tmB;
+  int num_taps, chunks, KC, swz;
+  int a_scale;
+  int BW, BH, BN;
+  int tiles_w, tiles_h;
+  int N, n_store;
+  int b_tap_stride;
+  short a_dw[4][16], a_dh[4][16];
+  int b_row0[4];
+  void* out;
+  const void* mask;
+  const float* bias;
+  int bias_mod;  // bias index = channel % bias_mod (dense S->L: channel = (kh,kw,cl))
+  int act;
+  int out_f32;
+  int OH, OW, OC, oys, oxs;
+  int oy0[4], ox0[4];
+  int batch;
+  int stages;
+  int n_slabs;  // blockIdx.y: slabs of N output channels (B rows / output channels offset by y*N)
+};
+
+constexpr int TG_THREADS = 192;
+
+__global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int a_bytes = 128 * p.KC * 2, b_bytes = p.N * p.KC * 2;
+  const int a_stride = (a_bytes + 1023) & ~1023, b_stride = (b_bytes + 1023) & ~1023;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * a_stride;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_stride);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int phase_id = blockIdx.z;
+  const int slab0 = blockIdx.y * p.N;
+  // tile origin (output-pixel units)
+  const int tiles_per_group = p.tiles_w * p.tiles_h;
+  const int grp = blockIdx.x / tiles_per_group, tin = blockIdx.x % tiles_per_group;
+  const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.N) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int k_iters = p.num_taps * p.chunks;
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < k_iters; ++it) {
+        const int t = it / p.chunks, c = it % p.chunks;
+        mbar_wait(&empty[stage], ph ^ 1);
+        mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
+        tma_load_4d(sA + stage * a_stride, &p.tmA, &full[stage], c * p.KC, p.a_scale * w0 + p.a_dw[phase_id][t],
+                    p.a_scale * h0 + p.a_dh[phase_id][t], n0);
+        tma_load_2d(sB + stage * b_stride, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, p.b_row0[phase_id] + slab0);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
+    const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;  // 8 rows of the swizzle atom
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int it = 0; it < k_iters; ++it) {
+      mbar_wait(&full[stage], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(sA + stage * a_stride), b0 = smem_u32(sB + stage * b_stride);
+        for (int kk = 0; kk < p.KC / 16; ++kk) {
+          const uint64_t ad = smem_desc(a0 + kk * 32, 16, sbo, (uint32_t)p.swz);
+          const uint64_t bd = smem_desc(b0 + kk * 32, 16, sbo, (uint32_t)p.swz);
+          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        if (it == k_iters - 1) umma_commit(tmem_full);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int dx = m % p.BW, dy = (m / p.BW) % p.BH, dn = m / (p.BW * p.BH);
+    const int n = n0 + dn, y = h0 + dy, x = w0 + dx;
+    const bool valid = n < p.batch;
+    const size_t opix = ((size_t)n * p.OH + (size_t)(y * p.oys + p.oy0[phase_id])) * p.OW + (x * p.oxs + p.ox0[phase_id]);
+    mbar_wait(tmem_full, 0);
+    tc_fence_after();
+    for (int c0 = 0; c0 < p.N; c0 += 16) {
+      uint32_t r[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+      tmem_ld_wait();
+      const int cg = slab0 + c0;  // global output channel of this chunk
+      if (!valid || cg >= p.n_store) continue;
+      float v[16];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        float f = __uint_as_float(r[i]);
+        if (p.bias != nullptr && cg + i < p.n_store) f += __ldg(p.bias + (cg + i) % p.bias_mod);
+        if (p.act == GCCVAE_ACT_RELU) f = fmaxf(f, 0.0f);
+        else if (p.act == GCCVAE_ACT_SIGMOID) f = sigmoid_f(f);
+        v[i] = f;
+      }
+      const size_t o = opix * p.OC + cg;
+      if (p.mask != nullptr) {
+        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
+        const uint4 m0 = __ldg(mk), m1 = __ldg(mk + 1);
+        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+          const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+          if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
+          if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+        }
+      }
+      if (p.out_f32) {
+        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+      } else {
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                            pack_bf16x2(v[14], v[15]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// debug aid: one 4-D TMA box load, raw shared-memory image copied out (layout / OOB / stride checks)
+__global__ void tma_dump_kernel(const __grid_constant__ CUtensorMap tm, int c0, int c1, int c2, int c3, int bytes,
+                                uint8_t* __restrict__ out) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  __shared__ uint64_t bar;
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) smem[i] = 0xEE;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    mbar_expect_tx(&bar, (uint32_t)bytes);
+    tma_load_4d(smem, &tm, &bar, c0, c1, c2, c3);
+  }
+  mbar_wait(&bar, 0);
+  for (int i = threadIdx.x; i < bytes; i += blockDim.x) out[i] = smem[i];
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight packing: fp32 Keras kernel W[kh,kw,CL,CS] -> bf16 GEMM operands
+//   ls[cs][ (kh,kw,cl) ]                       (rows padded to a multiple of 16, zero filled)
+//   sl[phase][cl][ (th,tw,cs) ], kh = (ph+1)%2 + 2 th  (k4/s2/p1 only)
+//   dense S->L:  sl[(kh,kw,cl)][cs] is W itself cast to bf16
+// ---------------------------------------------------------------------------------------------------
+__global__ void pack_ls_kernel(const float* __restrict__ W, int taps, int CL, int CS, int rows_pad,
+                               __nv_bfloat16* __restrict__ out) {
+  const int K = taps * CL;
+  const long long n = (long long)rows_pad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int cs = (int)(i / K), k = (int)(i % K);
+    out[i] = __float2bfloat16(cs < CS ? W[(size_t)k * CS + cs] : 0.0f);
+  }
+}
+__global__ void pack_sl2_kernel(const float* __restrict__ W, int CL, int CS, int rows_pad,
+                                __nv_bfloat16* __restrict__ out) {
+  const int K = 4 * CS;
+  const long long n = 4LL * rows_pad * K;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(i % K);
+    const int cl = (int)((i / K) % rows_pad), phase = (int)(i / ((long long)K * rows_pad));
+    const int ph = phase >> 1, pw = phase & 1, t = k / CS, cs = k % CS;
+    const int kh = ((ph + 1) & 1) + 2 * (t >> 1), kw = ((pw + 1) & 1) + 2 * (t & 1);
+    out[i] = __float2bfloat16(cl < CL ? W[((size_t)(kh * 4 + kw) * CL + cl) * CS + cs] : 0.0f);
+  }
+}
+__global__ void cast_bf16_kernel(const float* __restrict__ in, long long n, __nv_bfloat16* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __float2bfloat16(in[i]);
+}
+__global__ void cast_f32_kernel(const __nv_bfloat16* __restrict__ in, long long n, float* __restrict__ out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    out[i] = __bfloat162float(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)f;
+  });
+  return fn;
+}
+
+static CUtensorMapSwizzle tma_swizzle_for(int inner_bytes) {
+  return inner_bytes >= 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+         : inner_bytes >= 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+         : inner_bytes >= 32 ? CU_TENSOR_MAP_SWIZZLE_32B
+                             : CU_TENSOR_MAP_SWIZZLE_NONE;
+}
+static int umma_swizzle_for(int inner_bytes) {
+  return inner_bytes >= 128 ? SW_128 : inner_bytes >= 64 ? SW_64 : inner_bytes >= 32 ? SW_32 : SW_NONE;
+}
+
+// bf16 NHWC tensor [N,H,W,C] -> 4-D map (c,w,h,n); box = (kc, bw, bh, bn) OUTPUT pixels traversed with
+// element stride `es` along w and h.
+static int encode_act_map(CUtensorMap* m, const void* ptr, int N, int H, int W, int C, int kc, int bw, int bh, int bn,
+                          int es) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    return GCCVAE_ECUDA;
+  }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)N};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2};
+  cuuint32_t box[4] = {(cuuint32_t)kc, (cuuint32_t)(bw * es), (cuuint32_t)(bh * es), (cuuint32_t)bn};
+  cuuint32_t estr[4] = {1, (cuuint32_t)es, (cuuint32_t)es, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, tma_swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(act %dx%dx%dx%d box %d,%d,%d,%d es %d) failed: %d", N, H, W, C, kc, bw * es,
+              bh * es, bn, es, (int)r);
+    return GCCVAE_ECUDA;
+  }
+  return GCCVAE_OK;
+}
+
+// bf16 row-major matrix [rows, K] -> 2-D map (k, row); box = (kc, nrows)
+static int encode_mat_map(CUtensorMap* m, const void* ptr, long long rows, long long K, int kc, int nrows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) {
+    set_error("cuTensorMapEncodeTiled is unavailable (driver too old?)");
+    return GCCVAE_ECUDA;
+  }
+  cuuint64_t dims[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t strides[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)kc, (cuuint32_t)nrows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(ptr), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, tma_swizzle_for(kc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled(mat %lldx%lld box %d,%d) failed: %d", rows, K, kc, nrows, (int)r);
+    return GCCVAE_ECUDA;
+  }
+  return GCCVAE_OK;
+}
+
+static int pick_kc(int C) {
+  if (C % 64 == 0) return 64;
+  if (C == 32) return 32;
+  if (C == 16) return 16;
+  return 0;
+}
+
+// tile box for a plane of H x W output pixels: BW*BH*BN = 128
+static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
+  if (W >= 128 || 128 % W != 0) return -1;
+  *bw = W;
+  int rest = 128 / W;
+  if (H >= rest) {
+    if (H % rest != 0) return -1;
+    *bh = rest;
+    *bn = 1;
+  } else {
+    if (rest % H != 0) return -1;
+    *bh = H;
+    *bn = rest / H;
+  }
+  return 0;
+}
+
+static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
+  const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
+  int stages = 4;
+  const int k_iters = p.num_taps * p.chunks;
+  if (stages > k_iters) stages = k_iters;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * (a_stride + b_stride) + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  GCC_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory", name, smem);
+  if (p.n_slabs < 1) p.n_slabs = 1;
+  if (p.bias_mod < 1) p.bias_mod = 1 << 30;
+  dim3 grid(groups * p.tiles_w * p.tiles_h, p.n_slabs, phases);
+  tapgemm_kernel<<<grid, TG_THREADS, smem, st>>>(p);
+  GCC_CHECK_LAUNCH(name);
+  return GCCVAE_OK;
+}
+
+}  // namespace gccvae
+
+using namespace gccvae;
+
+// S = act(gather(L) W + b) (* mask>0): bf16 NHWC in/out, Wp = pack "ls" layout.
+extern "C" int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const float* bias, int act,
+                              const void* mask, void* S, int out_f32, void* stream) {
+  GCC_REQUIRE(g && L && Wp_ls && S, "ls_bf16: null pointer");
+  const int kc = pick_kc(g->CL);
+  GCC_REQUIRE(kc > 0, "ls_bf16: CL=%d unsupported (need 16, 32 or a multiple of 64)", g->CL);
+  GCC_REQUIRE(g->CS % 16 == 0 && g->CS <= 256, "ls_bf16: CS=%d must be a multiple of 16, <= 256", g->CS);
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  const bool dense = (g->HS == 1 && g->WS == 1 && g->pad == 0 && g->stride == 1);
+  int rc;
+  if (dense) {
+    // [B, KH*KW*CL] x [KH*KW*CL, CS]: one tap, many chunks
+    const int Kt = g->KH * g->KW * g->CL;
+    if ((rc = encode_act_map(&p.tmA, L, g->batch, 1, 1, Kt, kc, 1, 1, 128, 1))) return rc;
+    p.num_taps = 1; p.chunks = Kt / kc; p.a_scale = 1; p.BW = 1; p.BH = 1; p.BN = 128; p.tiles_w = p.tiles_h = 1;
+    p.b_tap_stride = 0;
+    if ((rc = encode_mat_map(&p.tmB, Wp_ls, g->CS, Kt, kc, g->CS))) return rc;
+  } else {
+    GCC_REQUIRE(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1, "ls_bf16: only k4/s2/p1 or dense");
+    int bw, bh, bn;
+    GCC_REQUIRE(pick_tile(g->HS, g->WS, &bw, &bh, &bn) == 0, "ls_bf16: cannot tile %dx%d", g->HS, g->WS);
+    if ((rc = encode_act_map(&p.tmA, L, g->batch, g->HL, g->WL, g->CL, kc, bw, bh, bn, 2))) return rc;
+    p.num_taps = 16; p.chunks = g->CL / kc; p.a_scale = 2; p.BW = bw; p.BH = bh; p.BN = bn;
+    p.tiles_w = g->WS / bw; p.tiles_h = g->HS / bh;
+    for (int t = 0; t < 16; ++t) { p.a_dh[0][t] = (short)(t / 4 - 1); p.a_dw[0][t] = (short)(t % 4 - 1); }
+    p.b_tap_stride = g->CL;
+    if ((rc = encode_mat_map(&p.tmB, Wp_ls, g->CS, 16LL * g->CL, kc, g->CS))) return rc;
+  }
+  p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
+  p.N = g->CS; p.n_store = g->CS;
+  p.out = S; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
+  p.OH = g->HS; p.OW = g->WS; p.OC = g->CS; p.oys = p.oxs = 1;
+  p.batch = g->batch;
+  const int groups = (g->batch + p.BN - 1) / p.BN;
+  return launch_tapgemm(p, groups, 1, (cudaStream_t)stream, "ls_bf16");
+}
+
+// L = act(scatter(S) W^T + b) (* mask>0): bf16 NHWC in/out, Wp = pack "sl" layout.
+extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const float* bias, int act,
+                              const void* mask, void* L, int out_f32, void* stream) {
+  GCC_REQUIRE(g && S && Wp_sl && L, "sl_bf16: null pointer");
+  const int kc = pick_kc(g->CS);
+  GCC_REQUIRE(kc > 0, "sl_bf16: CS=%d unsupported (need 16, 32 or a multiple of 64)", g->CS);
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc, phases;
+  const bool dense = (g->HS == 1 && g->WS == 1 && g->pad == 0 && g->stride == 1);
+  if (dense) {
+    // [B, CS] x [CS, KH*KW*CL]: N = KH*KW*CL is tiled in slabs of <= 256 over blockIdx.y
+    const int Nt = g->KH * g->KW * g->CL;
+    const int nslab = Nt <= 256 ? Nt : (Nt % 256 == 0 ? 256 : (Nt % 128 == 0 ? 128 : 0));
+    GCC_REQUIRE(nslab > 0 && nslab % 16 == 0, "sl_bf16(dense): N=%d unsupported", Nt);
+    phases = 1;
+    if ((rc = encode_act_map(&p.tmA, S, g->batch, 1, 1, g->CS, kc, 1, 1, 128, 1))) return rc;
+    p.num_taps = 1; p.chunks = g->CS / kc; p.a_scale = 1; p.BW = 1; p.BH = 1; p.BN = 128; p.tiles_w = p.tiles_h = 1;
+    if ((rc = encode_mat_map(&p.tmB, Wp_sl, Nt, g->CS, kc, nslab))) return rc;
+    p.N = nslab; p.n_store = Nt; p.n_slabs = Nt / nslab;
+    p.OH = 1; p.OW = 1; p.OC = Nt; p.oys = p.oxs = 1;
+    p.bias_mod = g->CL;
+  } else {
+    GCC_REQUIRE(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1, "sl_bf16: only k4/s2/p1 or dense");
+    int bw, bh, bn;
+    GCC_REQUIRE(pick_tile(g->HS, g->WS, &bw, &bh, &bn) == 0, "sl_bf16: cannot tile %dx%d", g->HS, g->WS);
+    const int rows_pad = (g->CL + 15) / 16 * 16;
+    GCC_REQUIRE(rows_pad <= 256, "sl_bf16: CL too large");
+    phases = 4;
+    if ((rc = encode_act_map(&p.tmA, S, g->batch, g->HS, g->WS, g->CS, kc, bw, bh, bn, 1))) return rc;
+    p.num_taps = 4; p.chunks = g->CS / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
+    p.tiles_w = g->WS / bw; p.tiles_h = g->HS / bh;
+    for (int z = 0; z < 4; ++z) {
+      const int ph = z >> 1, pw = z & 1;
+      for (int t = 0; t < 4; ++t) { p.a_dh[z][t] = (short)(ph - (t >> 1)); p.a_dw[z][t] = (short)(pw - (t & 1)); }
+      p.b_row0[z] = z * rows_pad;
+      p.oy0[z] = ph; p.ox0[z] = pw;
+    }
+    p.b_tap_stride = g->CS;
+    if ((rc = encode_mat_map(&p.tmB, Wp_sl, 4LL * rows_pad, 4LL * g->CS, kc, rows_pad))) return rc;
+    p.N = rows_pad; p.n_store = g->CL;
+    p.OH = g->HL; p.OW = g->WL; p.OC = g->CL; p.oys = p.oxs = 2;
+    GCC_REQUIRE(g->CL % 16 == 0, "sl_bf16: CL=%d must be a multiple of 16 in this kernel", g->CL);
+  }
+  p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
+  p.out = L; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
+  p.batch = g->batch;
+  const int groups = (g->batch + p.BN - 1) / p.BN;
+  return launch_tapgemm(p, groups, phases, (cudaStream_t)stream, "sl_bf16");
+}
+
+extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
+                                  int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream) {
+  CUtensorMap tm;
+  if (int rc = encode_act_map(&tm, src_bf16, N, H, W, C, kc, bw, bh, bn, es)) return rc;
+  const int bytes = kc * bw * bh * bn * 2;
+  GCC_REQUIRE(out && out_bytes >= bytes && bytes <= 64 * 1024, "debug_tma4d: bad output size (%d needed)", bytes);
+  GCC_CUDA(cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
+  tma_dump_kernel<<<1, 128, bytes + 1024, (cudaStream_t)stream>>>(tm, c0, c1, c2, c3, bytes, (uint8_t*)out);
+  GCC_CHECK_LAUNCH("debug_tma4d");
+  return GCCVAE_OK;
+}
+
+extern "C" size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which) {
+  if (!g) return 0;
+  const int taps = g->KH * g->KW;
+  if (which == 0) return (size_t)((g->CS + 15) / 16 * 16) * taps * g->CL;                 // ls
+  if (g->HS == 1 && g->WS == 1) return (size_t)taps * g->CL * g->CS;                        // sl dense
+  return (size_t)4 * ((g->CL + 15) / 16 * 16) * 4 * g->CS;                                  // sl phases
+}
+
+extern "C" int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, void* Wp_ls, void* Wp_sl, void* stream) {
+  GCC_REQUIRE(g && W, "pack_weights: null pointer");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int taps = g->KH * g->KW;
+  if (Wp_ls) {
+    const int rows_pad = (g->CS + 15) / 16 * 16;
+    const long long n = (long long)rows_pad * taps * g->CL;
+    pack_ls_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(W, taps, g->CL, g->CS,
+                                                                                         rows_pad, (__nv_bfloat16*)Wp_ls);
+    GCC_CHECK_LAUNCH("pack_ls");
+  }
+  if (Wp_sl) {
+    if (g->HS == 1 && g->WS == 1) {
+      const long long n = (long long)taps * g->CL * g->CS;
+      cast_bf16_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(W, n,
+                                                                                             (__nv_bfloat16*)Wp_sl);
+      GCC_CHECK_LAUNCH("pack_sl_dense");
+    } else {
+      GCC_REQUIRE(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1, "pack_weights: sl needs k4/s2/p1");
+      const int rows_pad = (g->CL + 15) / 16 * 16;
+      const long long n = 4LL * rows_pad * 4 * g->CS;
+      pack_sl2_kernel<<<(int)((n + 255) / 256 > 1184 ? 1184 : (n + 255) / 256), 256, 0, st>>>(W, g->CL, g->CS, rows_pad,
+                                                                                            (__nv_bfloat16*)Wp_sl);
+      GCC_CHECK_LAUNCH("pack_sl2");
+    }
+  }
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream) {
+  GCC_REQUIRE(in && out && n > 0, "cast: bad args");
+  cast_bf16_kernel<<<(int)((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      in, n, (__nv_bfloat16*)out);
+  GCC_CHECK_LAUNCH("cast_bf16");
+  return GCCVAE_OK;
+}
+extern "C" int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream) {
+  GCC_REQUIRE(in && out && n > 0, "cast: bad args");
+  cast_f32_kernel<<<(int)((n + 255) / 256 > 2368 ? 2368 : (n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)in, n, out);
+  GCC_CHECK_LAUNCH("cast_f32");
+  return GCCVAE_OK;
+}
