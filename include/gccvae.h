@@ -98,6 +98,16 @@ int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const
                    const void* mask, void* S, int out_f32, void* stream);
 int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const float* bias, int act,
                    const void* mask, void* L, int out_f32, void* stream);
+/* dW (fp32, Keras [kh,kw,cl,cs]) += gather(L)^T S; out[c] += column sums.  Accumulating: zero first. */
+int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream);
+int gccvae_colsum_bf16(const void* in, long long rows, int cols, float* out, void* stream);
+/* 3-channel end layers (conv1 input, conv5t output) go through a K=64 im2col matrix
+ * M64[(n,oh,ow),(kh,kw,c4)] (bf16, 128-byte rows) so that they are dense tcgen05 GEMMs too. */
+int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* stream);
+int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, const float* coef, float* log_pxz,
+                             void* G64, float* db, void* stream);
+int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
+int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
 int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream);
 int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream);
 /* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */

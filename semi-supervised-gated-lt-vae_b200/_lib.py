@@ -61,6 +61,12 @@ SIGNATURES = {
     "gccvae_pack_weights_bf16": (_I, [_G, _P, _P, _P, _P]),
     "gccvae_ls_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_sl_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
+    "gccvae_wg_bf16": (_I, [_G, _P, _P, _P, _P]),
+    "gccvae_colsum_bf16": (_I, [_P, _LL, _I, _P, _P]),
+    "gccvae_im2col_x_bf16": (_I, [_P, _I, _P, _P]),
+    "gccvae_recon_im2col_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
+    "gccvae_pack_c4_bf16": (_I, [_P, _I, _P, _P]),
+    "gccvae_wg_c4_bf16": (_I, [_LL, _P, _P, _I, _P, _P]),
     "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
     "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
     "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),

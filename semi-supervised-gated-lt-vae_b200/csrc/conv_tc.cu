@@ -164,7 +164,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
         }
       }
-      if (p.out_f32) {
+      if (p.out_f32 == 2) {
+        // 3-channel image padded to 4 (decoder output): one float4 per pixel, pad channel = 0
+        if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix] = make_float4(v[0], v[1], v[2], 0.0f);
+      } else if (p.out_f32) {
         float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
 #pragma unroll
         for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
@@ -183,6 +186,259 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// weight-gradient kernel: dW[(tap,cl), cs] += sum_pix gather(L)[pix,(tap,cl)] * S[pix, cs]
+// The reduction axis of this GEMM is the PIXEL axis, so both operands are MN-major: a TMA box
+// [128 pixels x channels] is, as it lands, the canonical MN-major swizzled layout (channels
+// contiguous, 8-pixel groups at SBO, further 64/32-channel blocks - here: further taps - at LBO).
+// One CTA owns one 128-row slice of dW (128/CL taps) and a range of pixel tiles (split-K);
+// the fp32 TMEM accumulator is added to dW with red.global at the end.
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) WgParams {
+  CUtensorMap tmA, tmB;
+  int blocks_per_mtile, blocks_per_tap, taps, kcA, b_loads, kcB, swzA, swzB;
+  int c4_rows;  // rows are (tap, c4): scatter row m -> (m/4)*3 + m%4, dropping the pad channel
+  int a_scale, BW, BH, BN, tiles_w, tiles_h;
+  short a_dw[16], a_dh[16];
+  int N;
+  int tiles_total, tiles_per_cta;
+  float* dW;
+  int m_total;
+  int stages;
+};
+
+__global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int a_slab = 128 * p.kcA * 2, b_slab = 128 * p.kcB * 2;
+  const int a_bytes = p.blocks_per_mtile * a_slab, b_bytes = p.b_loads * b_slab;
+  uint8_t* sA = smem;
+  uint8_t* sB = smem + p.stages * a_bytes;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_bytes);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tmem_full = empty + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int mtile = blockIdx.y;
+  const int tile_beg = blockIdx.x * p.tiles_per_cta;
+  int tile_end = tile_beg + p.tiles_per_cta;
+  if (tile_end > p.tiles_total) tile_end = p.tiles_total;
+  const int n_tiles = tile_end - tile_beg;  // may be <= 0 for trailing CTAs
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < p.N) tmem_cols <<= 1;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(tmem_full, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (n_tiles > 0) {
+    const int tiles_per_group = p.tiles_w * p.tiles_h;
+    if (warp == 0) {
+      if (elect_one()) {
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < n_tiles; ++it) {
+          const int tile = tile_beg + it;
+          const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
+          const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
+          mbar_wait(&empty[stage], ph ^ 1);
+          mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
+          for (int bl = 0; bl < p.blocks_per_mtile; ++bl) {
+            const int bg = mtile * p.blocks_per_mtile + bl;
+            const int t = bg / p.blocks_per_tap, cb = bg % p.blocks_per_tap;
+            // blocks past the last tap are loaded from out-of-range images: TMA zero-fills them
+            const bool real = t < p.taps;
+            tma_load_4d(sA + stage * a_bytes + bl * a_slab, &p.tmA, &full[stage], cb * p.kcA,
+                        p.a_scale * w0 + (real ? p.a_dw[t] : 0), p.a_scale * h0 + (real ? p.a_dh[t] : 0),
+                        real ? n0 : 0x3fffff00);
+          }
+          for (int h = 0; h < p.b_loads; ++h)
+            tma_load_4d(sB + stage * b_bytes + h * b_slab, &p.tmB, &full[stage], h * p.kcB, w0, h0, n0);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
+      }
+    } else if (warp == 1) {
+      const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);
+      const uint32_t rowA = (uint32_t)p.kcA * 2u, rowB = (uint32_t)p.kcB * 2u;
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int it = 0; it < n_tiles; ++it) {
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sA + stage * a_bytes), b0 = smem_u32(sB + stage * b_bytes);
+          for (int kk = 0; kk < 8; ++kk) {  // 16 pixels per MMA
+            const uint64_t ad = smem_desc(a0 + kk * 16 * rowA, (uint32_t)a_slab, 8 * rowA, (uint32_t)p.swzA);
+            const uint64_t bd = smem_desc(b0 + kk * 16 * rowB, (uint32_t)b_slab, 8 * rowB, (uint32_t)p.swzB);
+            umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (it == n_tiles - 1) umma_commit(tmem_full);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    } else {
+      const int q = warp & 3;
+      const int m = mtile * 128 + q * 32 + lane;
+      mbar_wait(tmem_full, 0);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
+        tmem_ld_wait();
+        const int mrow = p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m;
+        if (m < p.m_total && !(p.c4_rows && (m & 3) == 3)) {
+          float* dst = p.dW + (size_t)mrow * p.N + c0;
+#pragma unroll
+          for (int i = 0; i < 16; i += 4)
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
+                         "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
+                         : "memory");
+        }
+      }
+      tc_fence_before();
+    }
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// bias gradient from a bf16 [rows, cols] tensor: out[c] += sum_r in[r,c]  (fp32 atomics; out pre-zeroed)
+__global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols,
+                                                          int rows_per_cta, float* __restrict__ out) {
+  // thread handles column pair (2 bf16) ; cols even, cols/2 <= 128 -> 256 threads cover (cols/2) x (256/(cols/2)) rows
+  const int cp = cols >> 1;
+  const int tc = threadIdx.x % cp, tr = threadIdx.x / cp, nr = 256 / cp;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float a0 = 0.0f, a1 = 0.0f;
+  if (tr < nr)
+    for (long long r = r0 + tr; r < r1; r += nr) {
+      const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(in + r * cols + 2 * tc);
+      a0 += __low2float(v);
+      a1 += __high2float(v);
+    }
+  __shared__ float red[256][2];
+  red[threadIdx.x][0] = a0;
+  red[threadIdx.x][1] = a1;
+  __syncthreads();
+  if (tr == 0) {
+    for (int q = 1; q < nr; ++q) {
+      a0 += red[q * cp + tc][0];
+      a1 += red[q * cp + tc][1];
+    }
+    atomicAdd(out + 2 * tc, a0);
+    atomicAdd(out + 2 * tc + 1, a1);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// The two 3-channel end layers (conv1 input x, conv5t output xhat) cannot feed TMA directly (6-byte
+// pixels).  Both are turned into a K=64 im2col matrix  M64[(n,oh,ow), (kh,kw,c4)]  (c4 = 3 channels +
+// 1 zero; 128-byte rows = exactly one SWIZZLE_128B chunk) so that conv1 forward / wgrad and conv5t
+// dgrad / wgrad are plain dense tcgen05 GEMMs.  Pixel of tap (kh,kw): (2*oh-1+kh, 2*ow-1+kw).
+// One thread per (row, tap): 16 consecutive threads write one 128-byte row.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) im2col_x_kernel(const float* __restrict__ x, long long total,
+                                                       uint2* __restrict__ out) {
+  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
+    const int t = (int)(i & 15);
+    const long long row = i >> 4;
+    const int ow = (int)(row & 31), oh = (int)((row >> 5) & 31);
+    const long long n = row >> 10;
+    const int ih = 2 * oh - 1 + (t >> 2), iw = 2 * ow - 1 + (t & 3);
+    uint2 v = make_uint2(0u, 0u);
+    if ((unsigned)ih < 64u && (unsigned)iw < 64u) {
+      const float* px = x + ((n * 64 + ih) * 64 + iw) * 3;
+      v.x = pack_bf16x2(__ldg(px), __ldg(px + 1));
+      v.y = pack_bf16x2(__ldg(px + 2), 0.0f);
+    }
+    out[i] = v;
+  }
+}
+
+// utils.py:101-105 fused with the im2col of its gradient: per (row, tap) thread
+//   dlogit = coef[n] * sign(x - xhat) * xhat (1 - xhat)   -> G64[row, tap, c4]  (bf16)
+//   taps (1,1),(1,2),(2,1),(2,2) own their pixel: they add -|x - xhat| to log_pxz[n] and dlogit to db.
+// log_pxz must be pre-set to -12288 ln2 ... it is initialised here by the owner of pixel (0,0).
+__global__ void __launch_bounds__(256) recon_im2col_kernel(const float* __restrict__ x, const float4* __restrict__ xh4,
+                                                           const float* __restrict__ coef, long long total,
+                                                           float* __restrict__ log_pxz, uint2* __restrict__ G,
+                                                           float* __restrict__ db) {
+  __shared__ float red[8][4];
+  float l1 = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
+  // grid is sized so that one CTA never straddles two images: 256 threads = 16 rows, 1024 rows per image
+  const long long i = blockIdx.x * 256LL + threadIdx.x;
+  const long long n = i >> 14;
+  if (i < total) {
+    const int t = (int)(i & 15);
+    const long long row = i >> 4;
+    const int ow = (int)(row & 31), oh = (int)((row >> 5) & 31);
+    const int kh = t >> 2, kw = t & 3;
+    const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+    uint2 v = make_uint2(0u, 0u);
+    if ((unsigned)ih < 64u && (unsigned)iw < 64u) {
+      const long long pix = (n * 64 + ih) * 64 + iw;
+      const float* px = x + pix * 3;
+      const float4 r = __ldg(xh4 + pix);
+      const float cb = coef ? __ldg(coef + n) : 0.0f;
+      const float e0 = __ldg(px) - r.x, e1 = __ldg(px + 1) - r.y, e2 = __ldg(px + 2) - r.z;
+      const float g0 = cb * ((e0 > 0.f) - (e0 < 0.f)) * r.x * (1.0f - r.x);
+      const float g1 = cb * ((e1 > 0.f) - (e1 < 0.f)) * r.y * (1.0f - r.y);
+      const float g2 = cb * ((e2 > 0.f) - (e2 < 0.f)) * r.z * (1.0f - r.z);
+      v.x = pack_bf16x2(g0, g1);
+      v.y = pack_bf16x2(g2, 0.0f);
+      if ((kh == 1 || kh == 2) && (kw == 1 || kw == 2)) {
+        l1 = fabsf(e0) + fabsf(e1) + fabsf(e2);
+        d0 = g0; d1 = g1; d2 = g2;
+      }
+    }
+    if (G != nullptr) G[i] = v;
+  }
+  l1 = warp_sum(l1); d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+  const int w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31) == 0) { red[w][0] = l1; red[w][1] = d0; red[w][2] = d1; red[w][3] = d2; }
+  __syncthreads();
+  if (threadIdx.x < 4 && i - threadIdx.x < total) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) tot += red[q][threadIdx.x];
+    if (threadIdx.x == 0) atomicAdd(log_pxz + n, -tot);
+    else if (db != nullptr) atomicAdd(db + (threadIdx.x - 1), tot);
+  }
+}
+__global__ void fill_kernel(float* __restrict__ p, int n, float v) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// W[16 taps][3][CS] fp32 -> out[CS][(tap, c4)] bf16 (K = 64, pad channel zero)
+__global__ void pack_c4_kernel(const float* __restrict__ W, int CS, __nv_bfloat16* __restrict__ out) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= CS * 64) return;
+  const int cs = i / 64, k = i % 64, t = k >> 2, c = k & 3;
+  out[i] = __float2bfloat16(c < 3 ? W[(size_t)(t * 3 + c) * CS + cs] : 0.0f);
 }
 
 // debug aid: one 4-D TMA box load, raw shared-memory image copied out (layout / OOB / stride checks)
@@ -446,7 +702,8 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
     if ((rc = encode_mat_map(&p.tmB, Wp_sl, 4LL * rows_pad, 4LL * g->CS, kc, rows_pad))) return rc;
     p.N = rows_pad; p.n_store = g->CL;
     p.OH = g->HL; p.OW = g->WL; p.OC = g->CL; p.oys = p.oxs = 2;
-    GCC_REQUIRE(g->CL % 16 == 0, "sl_bf16: CL=%d must be a multiple of 16 in this kernel", g->CL);
+    GCC_REQUIRE(g->CL % 16 == 0 || (g->CL == 3 && out_f32 == 2 && mask == nullptr),
+                "sl_bf16: CL=%d must be a multiple of 16 (or 3 with the float4 image output)", g->CL);
   }
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
   p.out = L; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
@@ -464,6 +721,88 @@ extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int
   GCC_CUDA(cudaFuncSetAttribute(tma_dump_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024));
   tma_dump_kernel<<<1, 128, bytes + 1024, (cudaStream_t)stream>>>(tm, c0, c1, c2, c3, bytes, (uint8_t*)out);
   GCC_CHECK_LAUNCH("debug_tma4d");
+  return GCCVAE_OK;
+}
+
+// dW[kh,kw,cl,cs] (fp32, Keras layout) += wgrad; dW must be zeroed by the caller (accumulating entry).
+static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, float* dW, int c4_rows, void* stream) {
+  GCC_REQUIRE(g && L && S && dW, "wg_bf16: null pointer");
+  const int CL = g->CL, CS = g->CS, taps = g->KH * g->KW;
+  GCC_REQUIRE(CL == 32 || (CL % 64 == 0 && CL <= 256), "wg_bf16: CL=%d unsupported (32, 64, 128, 256)", CL);
+  GCC_REQUIRE(CS == 32 || (CS % 64 == 0 && CS <= 256), "wg_bf16: CS=%d unsupported (32, 64, 128, 256)", CS);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.kcA = CL > 64 ? 64 : CL;
+  p.blocks_per_tap = CL / p.kcA;
+  p.blocks_per_mtile = 128 / p.kcA;
+  p.taps = taps;
+  p.c4_rows = c4_rows;
+  p.kcB = CS > 64 ? 64 : CS;
+  p.b_loads = CS / p.kcB;
+  p.swzA = umma_swizzle_for(p.kcA * 2);
+  p.swzB = umma_swizzle_for(p.kcB * 2);
+  int rc, bw, bh, bn, es;
+  const bool dense = (g->HS == 1 && g->WS == 1 && g->pad == 0 && g->stride == 1);
+  if (dense) {
+    bw = 1; bh = 1; bn = 128; es = 1; p.a_scale = 1;
+    for (int t = 0; t < taps; ++t) { p.a_dh[t] = (short)(t / g->KW); p.a_dw[t] = (short)(t % g->KW); }
+  } else {
+    GCC_REQUIRE(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1, "wg_bf16: only k4/s2/p1 or 1x1-spatial S");
+    GCC_REQUIRE(pick_tile(g->HS, g->WS, &bw, &bh, &bn) == 0, "wg_bf16: cannot tile %dx%d", g->HS, g->WS);
+    es = 2; p.a_scale = 2;
+    for (int t = 0; t < 16; ++t) { p.a_dh[t] = (short)(t / 4 - 1); p.a_dw[t] = (short)(t % 4 - 1); }
+  }
+  if ((rc = encode_act_map(&p.tmA, L, g->batch, g->HL, g->WL, CL, p.kcA, bw, bh, bn, es))) return rc;
+  if ((rc = encode_act_map(&p.tmB, S, g->batch, g->HS, g->WS, CS, p.kcB, bw, bh, bn, 1))) return rc;
+  p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = g->WS / bw; p.tiles_h = g->HS / bh;
+  p.N = CS; p.dW = dW; p.m_total = taps * CL;
+  const int groups = (g->batch + bn - 1) / bn;
+  p.tiles_total = groups * p.tiles_w * p.tiles_h;
+  const int mtiles = (taps * p.blocks_per_tap + p.blocks_per_mtile - 1) / p.blocks_per_mtile;
+  int splits = (148 * 2 + mtiles - 1) / mtiles;
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
+  splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
+  int stages = (190 * 1024) / stage_bytes;
+  if (stages > 4) stages = 4;
+  if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  dim3 grid(splits, mtiles, 1);
+  wgrad_kernel<<<grid, TG_THREADS, smem, (cudaStream_t)stream>>>(p);
+  GCC_CHECK_LAUNCH("wg_bf16");
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream) {
+  return wg_bf16_impl(g, L, S, dW, 0, stream);
+}
+
+// conv1 / conv5t weight gradient from the K=64 im2col matrix X64[rows, (tap, c4)]:
+// dW[(tap, c<3), cs] += X64^T S   (S = [rows, CS] bf16)
+extern "C" int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream) {
+  GCC_REQUIRE(rows > 0 && rows < (1LL << 31), "wg_c4: bad row count");
+  gccvae_geom g = {(int)rows, 1, 1, 64, 1, 1, CS, 1, 1, 1, 0};
+  return wg_bf16_impl(&g, X64, S, dW, 1, stream);
+}
+
+// out[c] += sum_r in[r,c] for a bf16 [rows, cols] tensor (out fp32, pre-zeroed by the caller)
+extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, float* out, void* stream) {
+  GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256, "colsum_bf16: bad args (cols=%d)", cols);
+  long long ctas = (rows + 255) / 256;
+  if (ctas > 148 * 4) ctas = 148 * 4;
+  const int rpc = (int)((rows + ctas - 1) / ctas);
+  ctas = (rows + rpc - 1) / rpc;
+  colsum_bf16_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, cols, rpc, out);
+  GCC_CHECK_LAUNCH("colsum_bf16");
   return GCCVAE_OK;
 }
 
@@ -501,6 +840,39 @@ extern "C" int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, vo
       GCC_CHECK_LAUNCH("pack_sl2");
     }
   }
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* stream) {
+  GCC_REQUIRE(x && X64 && batch > 0, "im2col_x: bad args");
+  const long long total = (long long)batch * 1024 * 16;
+  long long ctas = (total + 255) / 256;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  im2col_x_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>(x, total, (uint2*)X64);
+  GCC_CHECK_LAUNCH("im2col_x");
+  return GCCVAE_OK;
+}
+
+// xhat4: decoder output as [B,64,64,4] fp32 (channel 3 = pad).  log_pxz[b] = -|x-xhat|_1 - 12288 ln2;
+// when coef != NULL also G64 = im2col(dLoss/dlogit) (bf16 [B*1024, 64]) and db[3] += sum dlogit.
+extern "C" int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, const float* coef,
+                                        float* log_pxz, void* G64, float* db, void* stream) {
+  GCC_REQUIRE(x && xhat4 && log_pxz && batch > 0, "recon_im2col: bad args");
+  GCC_REQUIRE((coef == nullptr) == (G64 == nullptr), "recon_im2col: coef and G64 go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
+  GCC_CHECK_LAUNCH("recon_fill");
+  const long long total = (long long)batch * 1024 * 16;
+  recon_im2col_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x, (const float4*)xhat4, coef, total, log_pxz,
+                                                                  (uint2*)G64, db);
+  GCC_CHECK_LAUNCH("recon_im2col");
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream) {
+  GCC_REQUIRE(W && out && CS > 0, "pack_c4: bad args");
+  pack_c4_kernel<<<(CS * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, CS, (__nv_bfloat16*)out);
+  GCC_CHECK_LAUNCH("pack_c4");
   return GCCVAE_OK;
 }
 
