@@ -106,6 +106,76 @@ def param_count(p) -> int:
 
 
 # --------------------------------------------------------------------------------------
+# bf16 emulation.  The reference computes everything in fp32.  The B200 tensor-core path stores the
+# activations between convolutions (and their gradients) in bf16 and feeds bf16 weights to the
+# tensor cores.  With EMULATE_BF16 the oracle rounds at exactly those tensor boundaries (round to
+# nearest even, straight-through), so that the bf16 kernels can be checked tightly: the Laplace
+# likelihood's gradient is sign(x - xhat), a discontinuous function of the forward pass, so without
+# identical rounding points ~3e-4 of the pixels flip sign and gradients differ by a few percent.
+# --------------------------------------------------------------------------------------
+EMULATE_BF16 = False
+
+
+class bf16_emulation:
+    def __init__(self, on=True):
+        self.on = on
+
+    def __enter__(self):
+        global EMULATE_BF16
+        self.prev, EMULATE_BF16 = EMULATE_BF16, self.on
+
+    def __exit__(self, *a):
+        global EMULATE_BF16
+        EMULATE_BF16 = self.prev
+
+
+def _r16(t):
+    return t.to(torch.bfloat16).to(t.dtype)
+
+
+class _RoundBoth(torch.autograd.Function):        # activation stored in bf16, and so is its gradient
+    @staticmethod
+    def forward(ctx, t):
+        return _r16(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return _r16(g)
+
+
+class _RoundBwd(torch.autograd.Function):         # fp32 forward value, gradient handed back in bf16
+    @staticmethod
+    def forward(ctx, t):
+        return t.clone()
+
+    @staticmethod
+    def backward(ctx, g):
+        return _r16(g)
+
+
+class _RoundFwd(torch.autograd.Function):         # bf16 operand copy of an fp32 master weight
+    @staticmethod
+    def forward(ctx, t):
+        return _r16(t)
+
+    @staticmethod
+    def backward(ctx, g):
+        return g
+
+
+def _act16(t):
+    return _RoundBoth.apply(t) if EMULATE_BF16 else t
+
+
+def _grad16(t):
+    return _RoundBwd.apply(t) if EMULATE_BF16 else t
+
+
+def _w16(t):
+    return _RoundFwd.apply(t) if EMULATE_BF16 else t
+
+
+# --------------------------------------------------------------------------------------
 # Networks (networks.py)
 # --------------------------------------------------------------------------------------
 def _conv(h_nhwc, w, b, stride, pad):
@@ -127,11 +197,13 @@ def clipped_softplus(t):
 
 def encoder(p, x, return_acts: bool = False):
     """networks.py:20-37.  x [B,64,64,3] -> (locs [B,45], scale [B,45])."""
-    h1 = F.relu(_conv(x, p["enc.conv1.w"], p["enc.conv1.b"], 2, 1))
-    h2 = F.relu(_conv(h1, p["enc.conv2.w"], p["enc.conv2.b"], 2, 1))
-    h3 = F.relu(_conv(h2, p["enc.conv3.w"], p["enc.conv3.b"], 2, 1))
-    h4 = F.relu(_conv(h3, p["enc.conv4.w"], p["enc.conv4.b"], 2, 1))
-    h5 = F.relu(_conv(h4, p["enc.conv5.w"], p["enc.conv5.b"], 1, 0))
+    if EMULATE_BF16:
+        x = _r16(x)
+    h1 = _act16(F.relu(_conv(x, _w16(p["enc.conv1.w"]), p["enc.conv1.b"], 2, 1)))
+    h2 = _act16(F.relu(_conv(h1, _w16(p["enc.conv2.w"]), p["enc.conv2.b"], 2, 1)))
+    h3 = _act16(F.relu(_conv(h2, _w16(p["enc.conv3.w"]), p["enc.conv3.b"], 2, 1)))
+    h4 = _act16(F.relu(_conv(h3, _w16(p["enc.conv4.w"]), p["enc.conv4.b"], 2, 1)))
+    h5 = _grad16(F.relu(_conv(h4, _w16(p["enc.conv5.w"]), p["enc.conv5.b"], 1, 0)))
     hf = h5.reshape(h5.shape[0], -1)
     locs = F.relu(hf @ p["enc.locs.w"] + p["enc.locs.b"])
     scale = clipped_softplus(hf @ p["enc.std.w"] + p["enc.std.b"])
@@ -144,11 +216,11 @@ def decoder(p, z, return_acts: bool = False):
     """networks.py:51-59 with hidden_dim = z_dim (gated_ccvae.py:34)."""
     g0 = F.relu(z @ p["dec.fc1.w"] + p["dec.fc1.b"])
     g0r = g0.reshape(g0.shape[0], 1, 1, g0.shape[1])
-    g1 = F.relu(_convT(g0r, p["dec.conv1t.w"], p["dec.conv1t.b"], 1, 0))
-    g2 = F.relu(_convT(g1, p["dec.conv2t.w"], p["dec.conv2t.b"], 2, 1))
-    g3 = F.relu(_convT(g2, p["dec.conv3t.w"], p["dec.conv3t.b"], 2, 1))
-    g4 = F.relu(_convT(g3, p["dec.conv4t.w"], p["dec.conv4t.b"], 2, 1))
-    xh = torch.sigmoid(_convT(g4, p["dec.conv5t.w"], p["dec.conv5t.b"], 2, 1))
+    g1 = _act16(F.relu(_convT(g0r, p["dec.conv1t.w"], p["dec.conv1t.b"], 1, 0)))
+    g2 = _act16(F.relu(_convT(g1, _w16(p["dec.conv2t.w"]), p["dec.conv2t.b"], 2, 1)))
+    g3 = _act16(F.relu(_convT(g2, _w16(p["dec.conv3t.w"]), p["dec.conv3t.b"], 2, 1)))
+    g4 = _act16(F.relu(_convT(g3, _w16(p["dec.conv4t.w"]), p["dec.conv4t.b"], 2, 1)))
+    xh = torch.sigmoid(_grad16(_convT(g4, _w16(p["dec.conv5t.w"]), p["dec.conv5t.b"], 2, 1)))
     if return_acts:
         return xh, (g0, g1, g2, g3, g4)
     return xh

@@ -117,6 +117,19 @@ class Engine:
             fn = self.lib.gccvae_sl_f32 if lay[1] == "LS" else self.lib.gccvae_ls_f32
             _lib.check(fn(C.byref(g), ptr(dout), ptr(W), None, act, ptr(mask), ptr(dx), st), lay[0] + " dgrad")
 
+    # ---- step hooks shared with the tensor-core engine ------------------------------------------------
+    def zero_grads(self):
+        """the fp32 kernels overwrite every gradient; nothing to clear."""
+
+    def recon(self, x, b, coef, log_pxz, backward):
+        """utils.py:101-105 (+ gradient w.r.t. the decoder's pre-sigmoid logits when backward)."""
+        B = x.shape[0]
+        xhat = b["dec.conv5t.out"]
+        dlogit = b["dec.conv5t.dout"] if backward else None
+        _lib.check(self.lib.gccvae_recon_f32(ptr(x), ptr(xhat), B, 64 * 64 * 3, ptr(coef) if backward else None,
+                                             ptr(log_pxz), ptr(dlogit), _stream()), "recon")
+        return xhat
+
     # ---- encoder / decoder chains ---------------------------------------------------------------------
     def encoder_fwd(self, x, b):
         B = x.shape[0]

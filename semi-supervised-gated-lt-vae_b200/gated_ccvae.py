@@ -260,14 +260,13 @@ class Learner:
         b, lb = self.engine.bufs(B), self._latent_bufs(B)
         st = _stream()
         learnable = self.model.mu_trainable
+        if backward:
+            self.engine.zero_grads()
         self._gate(n)
         self.engine.encoder_fwd(x, b)
         self._latent_fwd(B, lb, b, y, n, supervised, k)
-        xhat = self.engine.decoder_fwd(lb["z"], b)
-        coef = lb["terms"][5]
-        dlogit = b["dec.conv5t.dout"] if backward else None
-        _lib.check(self.lib.gccvae_recon_f32(ptr(x), ptr(xhat), B, 64 * 64 * 3, ptr(coef) if backward else None,
-                                             ptr(lb["log_pxz"]), ptr(dlogit), st), "recon")
+        self.engine.decoder_fwd(lb["z"], b)
+        xhat = self.engine.recon(x, b, lb["terms"][5], lb["log_pxz"], backward)
         if backward:
             self.engine.decoder_bwd(lb["z"], b)
             self._latent_bwd(B, lb, b, n, supervised, k)
