@@ -164,7 +164,8 @@ def run_ours(args, rank, world, local_rank):
                                                            "engine_tc.py")) else "fp32"
     B = args.batch
     cfg = train_cfg()
-    lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234)
+    lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234,
+                    graphs=not args.no_graph)
 
     # synthetic data: a ring of NBUF different batches (> L2 in total) resident in HBM for `value`,
     # and the same ring in pinned host memory for `e2e`
@@ -214,9 +215,6 @@ def run_ours(args, rank, world, local_rank):
     value = 2 * B * world / (ms_step / 1e3)
 
     # ---- e2e: host buffers in, loss out, every step --------------------------------------------------------
-    copy_stream = torch.cuda.Stream(device=dev)
-    stage_x = [torch.empty(B, 64, 64, 3, device=dev) for _ in range(2)]
-    stage_y = [torch.empty(B, 18, dtype=torch.int64, device=dev) for _ in range(2)]
     loss_host = torch.zeros(1).pin_memory()
 
     def step_e2e(i):

@@ -55,6 +55,8 @@ int gccvae_arch_check(int device);
 /* number of kernels launched by this library on the calling thread since the last reset */
 long long gccvae_launch_count(void);
 void gccvae_reset_launch_count(void);
+/* a replayed CUDA graph launches the kernels that were counted while it was captured */
+void gccvae_add_launch_count(long long n);
 
 /* ---- layer relation ------------------------------------------------------------------------
  * S[n,oh,ow,cs] <-> L[n, stride*oh - pad + kh, stride*ow - pad + kw, cl] through W[kh,kw,cl,cs].
@@ -93,6 +95,14 @@ int gccvae_colsum_f32(const float* in, long long rows, int cols, float* out, voi
  *   which=1 "sl": k4/s2/p1: [4 phases][CL (padded to 16)][(th,tw,cs)]; 1x1-spatial S: W itself as bf16.
  * out_f32 != 0 stores the result as fp32 instead of bf16.                                           */
 size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
+/* batched form of the packing entry points below: ONE launch for all layers of a step.
+ * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below) */
+typedef struct {
+  int kind, taps, CL, CS;
+  const float* W;
+  void* out;
+} gccvae_pack_job;
+int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, void* stream);
 int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, void* Wp_ls, void* Wp_sl, void* stream);
 int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const float* bias, int act,
                    const void* mask, void* S, int out_f32, void* stream);
@@ -178,7 +188,7 @@ typedef struct {
   const float* dz;       /* [B,45] dLoss/dz from the decoder */
   float* dloc_pre;       /* [B,45] */
   float* dscale_pre;     /* [B,45] */
-  float* partials;       /* [n_partials, GCCVAE_LATENT_PARTIAL_FLOATS] */
+  float* partials;       /* [n_partials + 1, GCCVAE_LATENT_PARTIAL_FLOATS] (last row: scratch of gate_bwd) */
   int n_partials;        /* = gccvae_latent_bwd_partials(batch) */
   float* loss_out;       /* [1]: sum_b -(elbo_b)/batch_global for this rank (no L1 term) */
 } gccvae_latent_bwd_args;
@@ -188,7 +198,7 @@ int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream);
 /* reduce the partials; chain through c to mu (clip / pow / ratio of gated_ccvae.py:103-109) and
  * add the L1 term gating_reg*mean|mu| (gated_ccvae.py:229-230,297-298) scaled by l1_scale
  * (1/world in data parallel).  d* may be NULL when the tensor is frozen. */
-int gccvae_gate_bwd(const float* partials, int n_partials, const float* mu, const float* Wcls,
+int gccvae_gate_bwd(float* partials /* [n_partials + 1 rows]: the last row is scratch */, int n_partials, const float* mu, const float* Wcls,
                     const float* Wlt, const float* Wlf, const float* Wst, const float* Wsf,
                     const float* gate_ws, float gating_reg, float l1_scale, float* dWcls, float* dbcls,
                     float* dWlt, float* dWlf, float* dWst, float* dWsf, float* dmu, float* loss_inout,

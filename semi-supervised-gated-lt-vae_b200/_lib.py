@@ -41,6 +41,11 @@ class LatentBwdArgs(C.Structure):
     ]
 
 
+class PackJob(C.Structure):
+    _fields_ = [("kind", C.c_int), ("taps", C.c_int), ("CL", C.c_int), ("CS", C.c_int), ("W", C.c_void_p),
+                ("out", C.c_void_p)]
+
+
 _P, _I, _F, _LL, _SZ, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_uint64
 _G = C.POINTER(Geom)
 
@@ -51,6 +56,7 @@ SIGNATURES = {
     "gccvae_arch_check": (_I, [_I]),
     "gccvae_launch_count": (_LL, []),
     "gccvae_reset_launch_count": (None, []),
+    "gccvae_add_launch_count": (None, [_LL]),
     "gccvae_ls_f32": (_I, [_G, _P, _P, _P, _I, _P, _P, _P]),
     "gccvae_sl_f32": (_I, [_G, _P, _P, _P, _I, _P, _P, _P]),
     "gccvae_wg_f32_workspace_bytes": (_SZ, [_G]),
@@ -58,6 +64,7 @@ SIGNATURES = {
     "gccvae_colsum_f32_workspace_bytes": (_SZ, [_LL, _I]),
     "gccvae_colsum_f32": (_I, [_P, _LL, _I, _P, _P, _SZ, _P]),
     "gccvae_packed_weight_elems": (_SZ, [_G, _I]),
+    "gccvae_pack_jobs_bf16": (_I, [C.POINTER(PackJob), _I, _P]),
     "gccvae_pack_weights_bf16": (_I, [_G, _P, _P, _P, _P]),
     "gccvae_ls_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_sl_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),

@@ -9,11 +9,12 @@
 // weight matrix.  Both land in the canonical K-major swizzled layout the UMMA descriptors expect
 // (swizzle width = KC*2 bytes).  The same kernel runs
 //   * L->S  (Conv2D forward / Conv2DTranspose dgrad): 16 taps, stride-2 box,
-//   * S->L  (Conv2DTranspose forward / Conv2D dgrad): 4 output-parity phases (blockIdx.z) x 4 taps,
+//   * S->L  (Conv2DTranspose forward / Conv2D dgrad): 4 output-parity phases x 4 taps,
 //   * dense (conv5 as [B,2048]x[2048,256], ...): 1 tap, many chunks.
 // Warp roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue
-// (TMEM -> registers -> bias/activation/mask -> bf16 -> global).  One tile per CTA; several CTAs are
-// resident per SM so one CTA's epilogue overlaps another's main loop.
+// (TMEM -> registers -> bias/activation/mask -> bf16 -> global).  Persistent: one CTA per SM walks a
+// contiguous range of (tile, N-slab, phase) work items; the accumulator is double-buffered in TMEM so
+// the epilogue of item i overlaps the TMA/MMA main loop of item i+1.
 #include <string.h>
 
 #include <mutex>
@@ -44,7 +45,10 @@ struct alignas(64) TapGemmParams {
   int oy0[4], ox0[4];
   int batch;
   int stages;
-  int n_slabs;  // blockIdx.y: slabs of N output channels (B rows / output channels offset by y*N)
+  int n_slabs;  // slabs of N output channels (B rows / output channels offset by slab*N)
+  int phases;
+  int total_items;  // tiles * n_slabs * phases, spread contiguously over the persistent CTAs
+  int bias_n;       // number of valid bias entries (channels >= bias_n get no bias)
 };
 
 constexpr int TG_THREADS = 192;
@@ -59,18 +63,20 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   uint8_t* sB = smem + p.stages * a_stride;
   uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_stride);
   uint64_t* empty = full + p.stages;
-  uint64_t* tmem_full = empty + p.stages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  uint64_t* tfull = empty + p.stages;   // [2] accumulator stage ready for the epilogue
+  uint64_t* tempty = tfull + 2;         // [2] accumulator stage drained by the epilogue
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int phase_id = blockIdx.z;
-  const int slab0 = blockIdx.y * p.N;
-  // tile origin (output-pixel units)
+  // persistent: this CTA owns a contiguous range of work items; item = (tile, slab, phase), phase fastest,
+  // so the 4 output-parity phases that re-read one input tile run back to back on the same SM.
+  const int per_cta = (p.total_items + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int item_beg = blockIdx.x * per_cta;
+  const int item_end = min(item_beg + per_cta, p.total_items);
   const int tiles_per_group = p.tiles_w * p.tiles_h;
-  const int grp = blockIdx.x / tiles_per_group, tin = blockIdx.x % tiles_per_group;
-  const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
-  uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < p.N) tmem_cols <<= 1;
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < p.N) acc_cols <<= 1;
+  const uint32_t tmem_cols = acc_cols * 2;   // two accumulator stages
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -79,7 +85,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       mbar_init(&full[s], 1);
       mbar_init(&empty[s], 1);
     }
-    mbar_init(tmem_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
@@ -94,14 +103,20 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     if (elect_one()) {
       int stage = 0;
       uint32_t ph = 0;
-      for (int it = 0; it < k_iters; ++it) {
-        const int t = it / p.chunks, c = it % p.chunks;
-        mbar_wait(&empty[stage], ph ^ 1);
-        mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
-        tma_load_4d(sA + stage * a_stride, &p.tmA, &full[stage], c * p.KC, p.a_scale * w0 + p.a_dw[phase_id][t],
-                    p.a_scale * h0 + p.a_dh[phase_id][t], n0);
-        tma_load_2d(sB + stage * b_stride, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, p.b_row0[phase_id] + slab0);
-        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      for (int item = item_beg; item < item_end; ++item) {
+        const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
+        const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
+        const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
+        for (int it = 0; it < k_iters; ++it) {
+          const int t = it / p.chunks, c = it % p.chunks;
+          mbar_wait(&empty[stage], ph ^ 1);
+          mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
+          tma_load_4d(sA + stage * a_stride, &p.tmA, &full[stage], c * p.KC, p.a_scale * w0 + p.a_dw[phase_id][t],
+                      p.a_scale * h0 + p.a_dh[phase_id][t], n0);
+          tma_load_2d(sB + stage * b_stride, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC,
+                      p.b_row0[phase_id] + slab * p.N);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
       }
     }
   } else if (warp == 1) {
@@ -110,73 +125,114 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;  // 8 rows of the swizzle atom
     int stage = 0;
     uint32_t ph = 0;
-    for (int it = 0; it < k_iters; ++it) {
-      mbar_wait(&full[stage], ph);
+    for (int item = item_beg; item < item_end; ++item) {
+      const int li = item - item_beg, as = li & 1;
+      mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
       tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a0 = smem_u32(sA + stage * a_stride), b0 = smem_u32(sB + stage * b_stride);
-        for (int kk = 0; kk < p.KC / 16; ++kk) {
-          const uint64_t ad = smem_desc(a0 + kk * 32, 16, sbo, (uint32_t)p.swz);
-          const uint64_t bd = smem_desc(b0 + kk * 32, 16, sbo, (uint32_t)p.swz);
-          umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+      const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
+      for (int it = 0; it < k_iters; ++it) {
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        if (elect_one()) {
+          const uint32_t a0 = smem_u32(sA + stage * a_stride), b0 = smem_u32(sB + stage * b_stride);
+          for (int kk = 0; kk < p.KC / 16; ++kk) {
+            const uint64_t ad = smem_desc(a0 + kk * 32, 16, sbo, (uint32_t)p.swz);
+            const uint64_t bd = smem_desc(b0 + kk * 32, 16, sbo, (uint32_t)p.swz);
+            umma_bf16(tacc, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[stage]);
+          if (it == k_iters - 1) umma_commit(&tfull[as]);
         }
-        umma_commit(&empty[stage]);
-        if (it == k_iters - 1) umma_commit(tmem_full);
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; ph ^= 1; }
     }
   } else {
     // ===== epilogue: warps 2..5 own TMEM lanes 32*(warp%4) .. +31 =====
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int dx = m % p.BW, dy = (m / p.BW) % p.BH, dn = m / (p.BW * p.BH);
-    const int n = n0 + dn, y = h0 + dy, x = w0 + dx;
-    const bool valid = n < p.batch;
-    const size_t opix = ((size_t)n * p.OH + (size_t)(y * p.oys + p.oy0[phase_id])) * p.OW + (x * p.oxs + p.ox0[phase_id]);
-    mbar_wait(tmem_full, 0);
-    tc_fence_after();
-    for (int c0 = 0; c0 < p.N; c0 += 16) {
-      uint32_t r[16];
-      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
-      tmem_ld_wait();
-      const int cg = slab0 + c0;  // global output channel of this chunk
-      if (!valid || cg >= p.n_store) continue;
-      float v[16];
+    for (int item = item_beg; item < item_end; ++item) {
+      const int li = item - item_beg, as = li & 1;
+      const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
+      const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
+      const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
+      const int slab0 = slab * p.N;
+      const int n = n0 + dn, y = h0 + dy, x = w0 + dx;
+      const bool valid = n < p.batch;
+      const size_t opix =
+          ((size_t)n * p.OH + (size_t)(y * p.oys + p.oy0[phase_id])) * p.OW + (x * p.oxs + p.ox0[phase_id]);
+      const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
+      // the mask (ReLU derivative of the consumer) does not depend on the accumulator: fetch the first
+      // 64 channels of it BEFORE waiting for the MMAs so its latency hides behind the main loop
+      uint4 mpre[8];
+      const bool use_mask = p.mask != nullptr && valid;
+      if (use_mask) {
+        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.OC + slab0);
 #pragma unroll
-      for (int i = 0; i < 16; ++i) {
-        float f = __uint_as_float(r[i]);
-        if (p.bias != nullptr && cg + i < p.n_store) f += __ldg(p.bias + (cg + i) % p.bias_mod);
-        if (p.act == GCCVAE_ACT_RELU) f = fmaxf(f, 0.0f);
-        else if (p.act == GCCVAE_ACT_SIGMOID) f = sigmoid_f(f);
-        v[i] = f;
+        for (int i = 0; i < 8; ++i)
+          if (i * 8 < p.N && slab0 + i * 8 < p.n_store) mpre[i] = __ldg(mk + i);
       }
-      const size_t o = opix * p.OC + cg;
-      if (p.mask != nullptr) {
-        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
-        const uint4 m0 = __ldg(mk), m1 = __ldg(mk + 1);
-        const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          // bf16 > 0  <=>  sign bit clear and magnitude non-zero
-          const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
-          if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
-          if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+      mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      for (int c0 = 0; c0 < p.N; c0 += 16) {
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[as]);
         }
-      }
-      if (p.out_f32 == 2) {
-        // 3-channel image padded to 4 (decoder output): one float4 per pixel, pad channel = 0
-        if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix] = make_float4(v[0], v[1], v[2], 0.0f);
-      } else if (p.out_f32) {
-        float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+        const int cg = slab0 + c0;  // global output channel of this chunk
+        if (!valid || cg >= p.n_store) continue;
+        float v[16];
 #pragma unroll
-        for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
-      } else {
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                            pack_bf16x2(v[6], v[7]));
-        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                            pack_bf16x2(v[14], v[15]));
+        for (int i = 0; i < 16; ++i) {
+          float f = __uint_as_float(r[i]);
+          if (p.bias != nullptr && cg + i < p.bias_n) f += __ldg(p.bias + (cg + i) % p.bias_mod);
+          if (p.act == GCCVAE_ACT_RELU) f = fmaxf(f, 0.0f);
+          else if (p.act == GCCVAE_ACT_SIGMOID) f = sigmoid_f(f);
+          v[i] = f;
+        }
+        const size_t o = opix * p.OC + cg;
+        if (use_mask) {
+          uint4 m0, m1;
+          if (c0 < 64) {
+            // static indexing keeps mpre[] in registers
+            switch (c0 >> 4) {
+              case 0: m0 = mpre[0]; m1 = mpre[1]; break;
+              case 1: m0 = mpre[2]; m1 = mpre[3]; break;
+              case 2: m0 = mpre[4]; m1 = mpre[5]; break;
+              default: m0 = mpre[6]; m1 = mpre[7]; break;
+            }
+          } else {
+            const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
+            m0 = __ldg(mk);
+            m1 = __ldg(mk + 1);
+          }
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            // bf16 > 0  <=>  sign bit clear and magnitude non-zero
+            const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+            if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
+            if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+          }
+        }
+        if (p.out_f32 == 2) {
+          // 3-channel image padded to 4 (decoder output): one float4 per pixel, pad channel = 0
+          if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix] = make_float4(v[0], v[1], v[2], 0.0f);
+        } else if (p.out_f32) {
+          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+        } else {
+          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+          dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                              pack_bf16x2(v[6], v[7]));
+          dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                              pack_bf16x2(v[14], v[15]));
+        }
       }
     }
     tc_fence_before();
@@ -378,49 +434,57 @@ __global__ void __launch_bounds__(256) im2col_x_kernel(const float* __restrict__
   }
 }
 
-// utils.py:101-105 fused with the im2col of its gradient: per (row, tap) thread
-//   dlogit = coef[n] * sign(x - xhat) * xhat (1 - xhat)   -> G64[row, tap, c4]  (bf16)
-//   taps (1,1),(1,2),(2,1),(2,2) own their pixel: they add -|x - xhat| to log_pxz[n] and dlogit to db.
-// log_pxz must be pre-set to -12288 ln2 ... it is initialised here by the owner of pixel (0,0).
+// utils.py:101-105 fused with the im2col of its gradient.  One CTA = (image n, 4 output rows):
+//  phase 1: the 10 input rows it touches are read coalesced (x: 768 B/row, xhat4: 1 KB/row),
+//           dlogit = coef[n] * sign(x - xhat) * xhat (1 - xhat) goes to shared memory as bf16x4;
+//           the 8 rows the CTA owns add -|x - xhat| to log_pxz[n] and dlogit to db;
+//  phase 2: the 128 G64 rows (16 taps x 8 bytes each) are written fully coalesced from shared memory.
 __global__ void __launch_bounds__(256) recon_im2col_kernel(const float* __restrict__ x, const float4* __restrict__ xh4,
-                                                           const float* __restrict__ coef, long long total,
+                                                           const float* __restrict__ coef,
                                                            float* __restrict__ log_pxz, uint2* __restrict__ G,
                                                            float* __restrict__ db) {
+  __shared__ uint2 sD[10][66];   // [input row - (2*oh0-1)][input col + 1], zero border
   __shared__ float red[8][4];
+  const int n = blockIdx.x >> 3, oh0 = (blockIdx.x & 7) * 4;
+  const int ih0 = 2 * oh0 - 1;
+  const float cb = coef ? __ldg(coef + n) : 0.0f;
   float l1 = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-  // grid is sized so that one CTA never straddles two images: 256 threads = 16 rows, 1024 rows per image
-  const long long i = blockIdx.x * 256LL + threadIdx.x;
-  const long long n = i >> 14;
-  if (i < total) {
-    const int t = (int)(i & 15);
-    const long long row = i >> 4;
-    const int ow = (int)(row & 31), oh = (int)((row >> 5) & 31);
-    const int kh = t >> 2, kw = t & 3;
-    const int ih = 2 * oh - 1 + kh, iw = 2 * ow - 1 + kw;
+  if (threadIdx.x < 20) sD[threadIdx.x >> 1][(threadIdx.x & 1) * 65] = make_uint2(0u, 0u);
+  for (int i = threadIdx.x; i < 640; i += 256) {
+    const int r = i >> 6, col = i & 63;
+    const int ih = ih0 + r;
     uint2 v = make_uint2(0u, 0u);
-    if ((unsigned)ih < 64u && (unsigned)iw < 64u) {
-      const long long pix = (n * 64 + ih) * 64 + iw;
+    if ((unsigned)ih < 64u) {
+      const size_t pix = ((size_t)n * 64 + ih) * 64 + col;
       const float* px = x + pix * 3;
-      const float4 r = __ldg(xh4 + pix);
-      const float cb = coef ? __ldg(coef + n) : 0.0f;
-      const float e0 = __ldg(px) - r.x, e1 = __ldg(px + 1) - r.y, e2 = __ldg(px + 2) - r.z;
-      const float g0 = cb * ((e0 > 0.f) - (e0 < 0.f)) * r.x * (1.0f - r.x);
-      const float g1 = cb * ((e1 > 0.f) - (e1 < 0.f)) * r.y * (1.0f - r.y);
-      const float g2 = cb * ((e2 > 0.f) - (e2 < 0.f)) * r.z * (1.0f - r.z);
+      const float4 rr = __ldg(xh4 + pix);
+      const float e0 = __ldg(px) - rr.x, e1 = __ldg(px + 1) - rr.y, e2 = __ldg(px + 2) - rr.z;
+      const float g0 = cb * ((e0 > 0.f) - (e0 < 0.f)) * rr.x * (1.0f - rr.x);
+      const float g1 = cb * ((e1 > 0.f) - (e1 < 0.f)) * rr.y * (1.0f - rr.y);
+      const float g2 = cb * ((e2 > 0.f) - (e2 < 0.f)) * rr.z * (1.0f - rr.z);
       v.x = pack_bf16x2(g0, g1);
       v.y = pack_bf16x2(g2, 0.0f);
-      if ((kh == 1 || kh == 2) && (kw == 1 || kw == 2)) {
-        l1 = fabsf(e0) + fabsf(e1) + fabsf(e2);
-        d0 = g0; d1 = g1; d2 = g2;
+      if (r >= 1 && r <= 8) {  // rows 2*oh0 .. 2*oh0+7 belong to this CTA
+        l1 += fabsf(e0) + fabsf(e1) + fabsf(e2);
+        d0 += g0; d1 += g1; d2 += g2;
       }
     }
-    if (G != nullptr) G[i] = v;
+    sD[r][col + 1] = v;
+  }
+  __syncthreads();
+  if (G != nullptr) {
+    uint2* gout = G + ((size_t)n * 1024 + (size_t)oh0 * 32) * 16;
+    for (int i = threadIdx.x; i < 2048; i += 256) {
+      const int t = i & 15, row = i >> 4;
+      const int ow = row & 31, dh = row >> 5;
+      gout[i] = sD[2 * dh + (t >> 2)][2 * ow + (t & 3)];
+    }
   }
   l1 = warp_sum(l1); d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
   const int w = threadIdx.x >> 5;
   if ((threadIdx.x & 31) == 0) { red[w][0] = l1; red[w][1] = d0; red[w][2] = d1; red[w][3] = d2; }
   __syncthreads();
-  if (threadIdx.x < 4 && i - threadIdx.x < total) {
+  if (threadIdx.x < 4) {
     float tot = 0.0f;
 #pragma unroll
     for (int q = 0; q < 8; ++q) tot += red[q][threadIdx.x];
@@ -439,6 +503,46 @@ __global__ void pack_c4_kernel(const float* __restrict__ W, int CS, __nv_bfloat1
   if (i >= CS * 64) return;
   const int cs = i / 64, k = i % 64, t = k >> 2, c = k & 3;
   out[i] = __float2bfloat16(c < 3 ? W[(size_t)(t * 3 + c) * CS + cs] : 0.0f);
+}
+
+// all weight repacking of one step in ONE launch: blockIdx.y = job
+struct PackJobs {
+  gccvae_pack_job j[32];
+};
+__global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
+  const gccvae_pack_job& jb = jobs.j[blockIdx.y];
+  const float* __restrict__ W = jb.W;
+  __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(jb.out);
+  const int CL = jb.CL, CS = jb.CS, taps = jb.taps;
+  const long long stride = (long long)gridDim.x * 256;
+  const long long i0 = blockIdx.x * 256LL + threadIdx.x;
+  if (jb.kind == 0) {          // ls: out[cs][(tap,cl)]
+    const int K = taps * CL, rows_pad = (CS + 15) / 16 * 16;
+    const long long n = (long long)rows_pad * K;
+    for (long long i = i0; i < n; i += stride) {
+      const int cs = (int)(i / K), k = (int)(i % K);
+      out[i] = __float2bfloat16(cs < CS ? W[(size_t)k * CS + cs] : 0.0f);
+    }
+  } else if (jb.kind == 1) {   // sl, k4/s2/p1: out[phase][cl][(th,tw,cs)]
+    const int K = 4 * CS, rows_pad = (CL + 15) / 16 * 16;
+    const long long n = 4LL * rows_pad * K;
+    for (long long i = i0; i < n; i += stride) {
+      const int k = (int)(i % K);
+      const int cl = (int)((i / K) % rows_pad), phase = (int)(i / ((long long)K * rows_pad));
+      const int ph = phase >> 1, pw = phase & 1, t = k / CS, cs = k % CS;
+      const int kh = ((ph + 1) & 1) + 2 * (t >> 1), kw = ((pw + 1) & 1) + 2 * (t & 1);
+      out[i] = __float2bfloat16(cl < CL ? W[((size_t)(kh * 4 + kw) * CL + cl) * CS + cs] : 0.0f);
+    }
+  } else if (jb.kind == 2) {   // plain cast
+    const long long n = (long long)taps * CL * CS;
+    for (long long i = i0; i < n; i += stride) out[i] = __float2bfloat16(W[i]);
+  } else {                     // c4: out[cs][(tap, c4)], W = [16][3][CS]
+    const long long n = (long long)CS * 64;
+    for (long long i = i0; i < n; i += stride) {
+      const int cs = (int)(i / 64), k = (int)(i % 64), t = k >> 2, c = k & 3;
+      out[i] = __float2bfloat16(c < 3 ? W[(size_t)(t * 3 + c) * CS + cs] : 0.0f);
+    }
+  }
 }
 
 // debug aid: one 4-D TMA box load, raw shared-memory image copied out (layout / OOB / stride checks)
@@ -599,9 +703,17 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
 
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
   const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
-  int stages = 4;
-  const int k_iters = p.num_taps * p.chunks;
-  if (stages > k_iters) stages = k_iters;
+  // up to 4 persistent CTAs per SM (their epilogues overlap); each gets a ring of >= 3 stages.
+  // TMEM: two accumulator stages per CTA, 512 columns per SM.
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < p.N) acc_cols <<= 1;
+  int per_sm = 512 / (2 * (int)acc_cols);
+  if (per_sm > 4) per_sm = 4;
+  if (per_sm < 1) per_sm = 1;
+  while (per_sm > 1 && (200 * 1024 / per_sm) < 3 * (a_stride + b_stride) + 2048) --per_sm;
+  int stages = ((200 * 1024 / per_sm) - 2048) / (a_stride + b_stride);
+  if (stages > 8) stages = 8;
+  if (stages < 2) stages = 2;
   p.stages = stages;
   const size_t smem = (size_t)stages * (a_stride + b_stride) + 1024 + 256;
   static bool attr_set = false;
@@ -612,7 +724,11 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   GCC_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory", name, smem);
   if (p.n_slabs < 1) p.n_slabs = 1;
   if (p.bias_mod < 1) p.bias_mod = 1 << 30;
-  dim3 grid(groups * p.tiles_w * p.tiles_h, p.n_slabs, phases);
+  if (p.bias_n < 1) p.bias_n = p.n_store;
+  p.phases = phases;
+  p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
+  int ctas = p.total_items < 148 * per_sm ? p.total_items : 148 * per_sm;
+  dim3 grid(ctas, 1, 1);
   tapgemm_kernel<<<grid, TG_THREADS, smem, st>>>(p);
   GCC_CHECK_LAUNCH(name);
   return GCCVAE_OK;
@@ -632,14 +748,17 @@ extern "C" int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* W
   TapGemmParams p;
   memset(&p, 0, sizeof(p));
   const bool dense = (g->HS == 1 && g->WS == 1 && g->pad == 0 && g->stride == 1);
-  int rc;
+  int rc, n_slab = g->CS;
   if (dense) {
     // [B, KH*KW*CL] x [KH*KW*CL, CS]: one tap, many chunks
     const int Kt = g->KH * g->KW * g->CL;
     if ((rc = encode_act_map(&p.tmA, L, g->batch, 1, 1, Kt, kc, 1, 1, 128, 1))) return rc;
     p.num_taps = 1; p.chunks = Kt / kc; p.a_scale = 1; p.BW = 1; p.BH = 1; p.BN = 128; p.tiles_w = p.tiles_h = 1;
     p.b_tap_stride = 0;
-    if ((rc = encode_mat_map(&p.tmB, Wp_ls, g->CS, Kt, kc, g->CS))) return rc;
+    // few M tiles (conv5: batch/128): tile N in slabs of 64 so that more SMs take part
+    const int m_tiles = (g->batch + 127) / 128;
+    n_slab = (m_tiles < 74 && g->CS % 64 == 0 && g->CS > 64) ? 64 : g->CS;
+    if ((rc = encode_mat_map(&p.tmB, Wp_ls, g->CS, Kt, kc, n_slab))) return rc;
   } else {
     GCC_REQUIRE(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1, "ls_bf16: only k4/s2/p1 or dense");
     int bw, bh, bn;
@@ -652,7 +771,7 @@ extern "C" int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* W
     if ((rc = encode_mat_map(&p.tmB, Wp_ls, g->CS, 16LL * g->CL, kc, g->CS))) return rc;
   }
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
-  p.N = g->CS; p.n_store = g->CS;
+  p.N = n_slab; p.n_store = g->CS; p.n_slabs = g->CS / n_slab;
   p.out = S; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
   p.OH = g->HS; p.OW = g->WS; p.OC = g->CS; p.oys = p.oxs = 1;
   p.batch = g->batch;
@@ -862,9 +981,7 @@ extern "C" int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int 
   cudaStream_t st = (cudaStream_t)stream;
   fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
   GCC_CHECK_LAUNCH("recon_fill");
-  const long long total = (long long)batch * 1024 * 16;
-  recon_im2col_kernel<<<(int)((total + 255) / 256), 256, 0, st>>>(x, (const float4*)xhat4, coef, total, log_pxz,
-                                                                  (uint2*)G64, db);
+  recon_im2col_kernel<<<batch * 8, 256, 0, st>>>(x, (const float4*)xhat4, coef, log_pxz, (uint2*)G64, db);
   GCC_CHECK_LAUNCH("recon_im2col");
   return GCCVAE_OK;
 }
@@ -873,6 +990,19 @@ extern "C" int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stre
   GCC_REQUIRE(W && out && CS > 0, "pack_c4: bad args");
   pack_c4_kernel<<<(CS * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, CS, (__nv_bfloat16*)out);
   GCC_CHECK_LAUNCH("pack_c4");
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, void* stream) {
+  GCC_REQUIRE(jobs && n_jobs > 0 && n_jobs <= 32, "pack_jobs: 1..32 jobs");
+  PackJobs pj;
+  memset(&pj, 0, sizeof(pj));
+  for (int i = 0; i < n_jobs; ++i) {
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 3, "pack_jobs: bad job %d", i);
+    pj.j[i] = jobs[i];
+  }
+  pack_jobs_kernel<<<dim3(64, n_jobs, 1), 256, 0, (cudaStream_t)stream>>>(pj);
+  GCC_CHECK_LAUNCH("pack_jobs");
   return GCCVAE_OK;
 }
 

@@ -555,6 +555,23 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
   }
 }
 
+// column-wise sum of the per-CTA partial rows -> one row (4 independent accumulators per thread)
+__global__ void __launch_bounds__(128) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
+                                                              float* __restrict__ out) {
+  const int c = blockIdx.x * 128 + threadIdx.x;
+  if (c >= PT_TOTAL) return;
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  int n = 0;
+  for (; n + 4 <= n_partials; n += 4) {
+    a0 += partials[(size_t)(n + 0) * PT_TOTAL + c];
+    a1 += partials[(size_t)(n + 1) * PT_TOTAL + c];
+    a2 += partials[(size_t)(n + 2) * PT_TOTAL + c];
+    a3 += partials[(size_t)(n + 3) * PT_TOTAL + c];
+  }
+  for (; n < n_partials; ++n) a0 += partials[(size_t)n * PT_TOTAL + c];
+  out[c] = (a0 + a1) + (a2 + a3);
+}
+
 // ---------------------------------------------------------------------------------------------
 // gate backward: reduce partials, un-gate, chain to mu, add L1.  One CTA.
 // ---------------------------------------------------------------------------------------------
@@ -827,13 +844,19 @@ extern "C" int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream) 
   return GCCVAE_OK;
 }
 
-extern "C" int gccvae_gate_bwd(const float* partials, int n_partials, const float* mu, const float* Wcls,
+extern "C" int gccvae_gate_bwd(float* partials, int n_partials, const float* mu, const float* Wcls,
                                const float* Wlt, const float* Wlf, const float* Wst, const float* Wsf,
                                const float* gate_ws, float gating_reg, float l1_scale, float* dWcls, float* dbcls,
                                float* dWlt, float* dWlf, float* dWst, float* dWsf, float* dmu, float* loss_inout,
                                void* stream) {
   GCC_REQUIRE(partials && n_partials > 0 && mu && Wcls && Wlt && Wlf && Wst && Wsf && gate_ws,
               "gate_bwd: null pointer");
+  // row n_partials of the buffer receives the column sums (the caller allocates n_partials + 1 rows)
+  float* reduced = partials + (size_t)n_partials * PT_TOTAL;
+  reduce_partials_kernel<<<(PT_TOTAL + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, reduced);
+  GCC_CHECK_LAUNCH("reduce_partials");
+  partials = reduced;
+  n_partials = 1;
   gate_bwd_kernel<<<1, 352, 0, (cudaStream_t)stream>>>(partials, n_partials, mu, Wcls, Wlt, Wlf, Wst, Wsf, gate_ws,
                                                        gating_reg, l1_scale, dWcls, dbcls, dWlt, dWlf, dWst, dWsf, dmu,
                                                        loss_inout);

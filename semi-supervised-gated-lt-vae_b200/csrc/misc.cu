@@ -158,6 +158,7 @@ extern "C" int gccvae_abi_version(void) { return GCCVAE_ABI_VERSION; }
 extern "C" const char* gccvae_last_error(void) { return g_err; }
 extern "C" long long gccvae_launch_count(void) { return g_launches; }
 extern "C" void gccvae_reset_launch_count(void) { g_launches = 0; }
+extern "C" void gccvae_add_launch_count(long long n) { g_launches += n; }
 
 extern "C" int gccvae_arch_check(int device) {
   cudaDeviceProp prop;

@@ -50,21 +50,28 @@ class EngineTC(Engine):
             self.wp[name + ".sl"] = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(g), 1), dtype=BF16, device=dev)
         self.wp["enc.conv1.c4"] = torch.zeros(32 * 64, dtype=BF16, device=dev)
         self.wp["dec.conv5t.c4"] = torch.zeros(32 * 64, dtype=BF16, device=dev)
+        self._jobs = None
 
     # ---- packed weights ---------------------------------------------------------------------------------
     def pack_weights(self):
-        st = _stream()
-        lib, v = self.lib, self.store.view
-        for name in TC_ENC + TC_DEC:
-            lay = _ENC.get(name) or _DEC[name]
-            g = make_geom(lay, 1)
-            _lib.check(lib.gccvae_pack_weights_bf16(C.byref(g), ptr(v(name + ".w")), ptr(self.wp[name + ".ls"]),
-                                                    ptr(self.wp[name + ".sl"]), st), "pack " + name)
-        g = make_geom(_DEC["dec.conv5t"], 1)
-        _lib.check(lib.gccvae_pack_weights_bf16(C.byref(g), ptr(v("dec.conv5t.w")), None,
-                                                ptr(self.wp["dec.conv5t.sl"]), st), "pack dec.conv5t")
-        _lib.check(lib.gccvae_pack_c4_bf16(ptr(v("enc.conv1.w")), 32, ptr(self.wp["enc.conv1.c4"]), st), "pack conv1")
-        _lib.check(lib.gccvae_pack_c4_bf16(ptr(v("dec.conv5t.w")), 32, ptr(self.wp["dec.conv5t.c4"]), st), "pack conv5t")
+        """refresh every packed bf16 operand from the fp32 master weights: one kernel launch."""
+        if self._jobs is None:
+            v = self.store.view
+            jobs = []
+            for name in TC_ENC + TC_DEC:
+                lay = _ENC.get(name) or _DEC[name]
+                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
+                jobs.append((0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"]))
+                kind = 2 if (HS == 1 and WS == 1) else 1
+                jobs.append((kind, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"]))
+            jobs.append((1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"]))
+            jobs.append((3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"]))
+            jobs.append((3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"]))
+            arr = (_lib.PackJob * len(jobs))()
+            for i, (kind, taps, CL, CS, W, out) in enumerate(jobs):
+                arr[i] = _lib.PackJob(kind, taps, CL, CS, ptr(W), ptr(out))
+            self._jobs = arr
+        _lib.check(self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()), "pack_jobs")
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def _alloc(self, B):

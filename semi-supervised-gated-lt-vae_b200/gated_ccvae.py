@@ -145,7 +145,7 @@ class Learner:
     """gated_ccvae.py:114-311, 421-455."""
 
     def __init__(self, ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config, device=None,
-                 precision="fp32", seed=1234, init_seed=0):
+                 precision="fp32", seed=1234, init_seed=0, graphs=False):
         if tuple(ip_shape) != (64, 64, 3):
             raise ValueError("the kernels are specialised for 64x64x3 inputs (gated_ccvae.py:481)")
         self.train_config = train_config
@@ -165,6 +165,8 @@ class Learner:
         self.n_trainable = self.store.total if self.model.mu_trainable else self.store.n_without_mu
         self.optimiser = KerasAdam(self.lr, self.store, self.n_trainable)
         self.seed = int(seed)
+        self.use_graphs = bool(graphs)   # replay the whole train_step as ONE CUDA graph (Philox-noise steps only)
+        self._graphs = {}
         self.last = {}
         self._lat = {}
         self._gate_ws = torch.zeros(GATE_WS_FLOATS, dtype=torch.float32, device=self.device)
@@ -184,7 +186,7 @@ class Learner:
             e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=self.device)
             npart = self.lib.gccvae_latent_bwd_partials(B)
             lb = dict(loc=e(B, 45), scale=e(B, 45), z=e(B, 45), terms=e(6, B), logits=e(B, 18),
-                      y_i32=e(B, 18, dt=torch.int32), log_pxz=e(B), partials=e(npart, LATENT_PARTIAL_FLOATS),
+                      y_i32=e(B, 18, dt=torch.int32), log_pxz=e(B), partials=e(npart + 1, LATENT_PARTIAL_FLOATS),
                       npart=npart)
             self._lat[B] = lb
         return lb
@@ -320,10 +322,58 @@ class Learner:
 
     def train_step(self, x, y, supervised, noise=None, k=100):
         """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update."""
+        if self.use_graphs and noise is None:
+            return self._train_step_graphed(x, y, supervised, k)
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
         self._allreduce_grads()
         self.optimiser.apply_gradients()
         return self._global_loss(loss), c
+
+    # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
+    def _train_step_graphed(self, x, y, supervised, k):
+        B = int(x.shape[0])
+        key = (B, bool(supervised), int(k))
+        g = self._graphs.get(key)
+        if g is None:
+            g = self._capture(key)
+        g["x"].copy_(torch.as_tensor(x), non_blocking=True)
+        if supervised:
+            g["y"].copy_(torch.as_tensor(y), non_blocking=True)
+        g["graph"].replay()
+        self.lib.gccvae_add_launch_count(g["launches"])
+        return g["loss"], self._c
+
+    def _capture(self, key):
+        B, supervised, k = key
+        xs = torch.zeros(B, *self.ip_shape, dtype=torch.float32, device=self.device)
+        ys = torch.zeros(B, self.y_dim, dtype=torch.int64, device=self.device) if supervised else None
+
+        def body():
+            loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
+            self._allreduce_grads()
+            self.optimiser.apply_gradients()
+            return self._global_loss(loss)
+
+        # warm-up on a side stream (first-use attribute calls, buffer allocation), state restored afterwards
+        saved = (self.store.flat.clone(), self.optimiser.m.clone(), self.optimiser.v.clone(),
+                 self.optimiser.step_dev.clone())
+        side = torch.cuda.Stream(device=self.device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        n0 = self.lib.gccvae_launch_count()
+        with torch.cuda.graph(graph):
+            loss = body()
+        launches = self.lib.gccvae_launch_count() - n0
+        torch.cuda.synchronize(self.device)
+        for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
+            dst.copy_(src)
+        g = dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches)
+        self._graphs[key] = g
+        return g
 
     def classifier_accuracy(self, x, y, noise=None):
         """gated_ccvae.py:421-446."""

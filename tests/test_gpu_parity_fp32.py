@@ -397,3 +397,25 @@ def test_full_size_properties_config2():
         lrn.loss_and_grads(x[sl], y[sl], True, noise=dict(eps=eps[sl], eps_k=ek[:, sl], U1=U1, U2=U2), k=10)
         acc += lrn.store.grad * 0.5
     assert_close(acc[: lrn.n_trainable], gfull[: lrn.n_trainable], 2e-5, "shard linearity")
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_cuda_graph_replay_equals_eager(precision):
+    """the graphed train_step (Philox noise keyed by the device-side step counter) follows the eager one."""
+    cfg = dict(cfg_for("learnable"), lr=1e-3)
+    p = O.init_params(0, trained_like=True)
+    a = make_learner(cfg, p, precision=precision, seed=5)
+    b = make_learner(cfg, p, precision=precision, seed=5, graphs=True)
+    g = torch.Generator().manual_seed(1)
+    for it in range(4):
+        x = torch.rand(16, 64, 64, 3, generator=g).to(dev())
+        y = (torch.rand(16, 18, generator=g) < 0.5).long().to(dev())
+        sup = it % 2 == 0
+        la, ca = a.train_step(x, y, sup)
+        lb, cb = b.train_step(x, y, sup)
+        torch.cuda.synchronize()
+        tol = 1e-6 if precision == "fp32" else 1e-4   # bf16 path: red.global ordering is not deterministic
+        assert rel_err(cb, ca) <= tol                 # (mu is learnable here, so c follows the parameters)
+        assert abs(float(la) - float(lb)) <= tol * abs(float(la)), (it, float(la), float(lb))
+    assert a.optimiser.iterations == b.optimiser.iterations == 4
+    assert rel_err(b.store.flat, a.store.flat) < (1e-6 if precision == "fp32" else 1e-3)
