@@ -96,11 +96,14 @@ int gccvae_colsum_f32(const float* in, long long rows, int cols, float* out, voi
  * out_f32 != 0 stores the result as fp32 instead of bf16.                                           */
 size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
 /* batched form of the packing entry points below: ONE launch for all layers of a step.
- * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below) */
+ * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below);
+ * 4/5: strided copy into a zero-padded bf16 / fp32 operand (the 45-wide dense layers padded to 64 / 96) */
 typedef struct {
   int kind, taps, CL, CS;
   const float* W;
   void* out;
+  /* kinds 4 (bf16 out) / 5 (fp32 out): out[(row_off+r)*ld_out + col_off + k] = W[r*sr + k*sk], r < taps, k < CL */
+  int sr, sk, ld_out, row_off, col_off, pad_;
 } gccvae_pack_job;
 int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, void* stream);
 int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, void* Wp_ls, void* Wp_sl, void* stream);
@@ -110,7 +113,20 @@ int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const
                    const void* mask, void* L, int out_f32, void* stream);
 /* dW (fp32, Keras [kh,kw,cl,cs]) += gather(L)^T S; out[c] += column sums.  Accumulating: zero first. */
 int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream);
-int gccvae_colsum_bf16(const void* in, long long rows, int cols, float* out, void* stream);
+/* out[c] += column sums of a bf16 [rows, cols] tensor for c < n_valid (0 = all) */
+int gccvae_colsum_bf16(const void* in, long long rows, int cols, int n_valid, float* out, void* stream);
+/* dense layers (networks.py:17-18 heads, :43 fc1, :45 conv1t as [B,45]x[45,2048]) with operands zero-padded
+ * to tensor-core friendly widths:
+ *   gemm:    out[rows,N] = act(A[rows,K] Wp[N,K]^T + bias[n % bias_mod], n < bias_n) (* mask > 0)
+ *   gemm_tn: D[M,N] += A[rows,M]^T B[rows,N], scattered to 1-2 column segments of fp32 tensors */
+typedef struct {
+  int n_seg, m_valid;
+  struct { int col0, ncols, ld, pad_; float* dst; } seg[2];
+} gccvae_wg_out;
+int gccvae_gemm_bf16(long long rows, int K, int N, const void* A, const void* Wp, const float* bias, int bias_n,
+                     int bias_mod, int act, const void* mask, void* out, int out_f32, void* stream);
+int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, const void* B, const gccvae_wg_out* out,
+                        void* stream);
 /* 3-channel end layers (conv1 input, conv5t output) go through a K=64 im2col matrix
  * M64[(n,oh,ow),(kh,kw,c4)] (bf16, 128-byte rows) so that they are dense tcgen05 GEMMs too. */
 int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* stream);
@@ -159,6 +175,7 @@ typedef struct {
   uint64_t seed, offset;   /* Philox key / per-step counter base */
   const int* step_dev;     /* optional device int added to `offset` (CUDA-graph replay) */
   const float* gate_ws;    /* from gccvae_gate_fwd */
+  int ld_pre;              /* row stride (floats) of loc_pre / scale_pre; 0 = 45 */
   /* outputs */
   float* loc;    /* [B,45] */
   float* scale;  /* [B,45] */
@@ -166,6 +183,7 @@ typedef struct {
   float* terms;  /* [6,B]: kl | log_qy_zc | log_qy_x | w | log_py | coef_pxz (= -w/batch_global) */
   float* logits; /* [B,18] */
   int* y_out;    /* [B,18] int32 sampled labels (unsup) or copy of y (sup); may be NULL */
+  void* z16;     /* optional bf16 [B,64] copy of z, columns 45..63 zero (operand of the tensor-core fc1) */
 } gccvae_latent_fwd_args;
 int gccvae_latent_fwd(const gccvae_latent_fwd_args* a, void* stream);
 
@@ -186,8 +204,12 @@ typedef struct {
   const float* terms;    /* [6,B] from the forward */
   const float* log_pxz;  /* [B] */
   const float* dz;       /* [B,45] dLoss/dz from the decoder */
-  float* dloc_pre;       /* [B,45] */
+  float* dloc_pre;       /* [B,45] (may be NULL when dpre16 is given) */
   float* dscale_pre;     /* [B,45] */
+  int ld_pre, ld_dz;     /* row strides (floats) of loc_pre/scale_pre and of dz; 0 = 45 */
+  void* dpre16;          /* optional bf16 [B,96]: dloc_pre at cols 0..44, dscale_pre at 48..92, rest zero */
+  float* db_loc;         /* optional [45] += column sums of dloc_pre (bias gradient of the locs head) */
+  float* db_scale;       /* optional [45] += column sums of dscale_pre */
   float* partials;       /* [n_partials + 1, GCCVAE_LATENT_PARTIAL_FLOATS] (last row: scratch of gate_bwd) */
   int n_partials;        /* = gccvae_latent_bwd_partials(batch) */
   float* loss_out;       /* [1]: sum_b -(elbo_b)/batch_global for this rank (no L1 term) */

@@ -203,10 +203,10 @@ def encoder(p, x, return_acts: bool = False):
     h2 = _act16(F.relu(_conv(h1, _w16(p["enc.conv2.w"]), p["enc.conv2.b"], 2, 1)))
     h3 = _act16(F.relu(_conv(h2, _w16(p["enc.conv3.w"]), p["enc.conv3.b"], 2, 1)))
     h4 = _act16(F.relu(_conv(h3, _w16(p["enc.conv4.w"]), p["enc.conv4.b"], 2, 1)))
-    h5 = _grad16(F.relu(_conv(h4, _w16(p["enc.conv5.w"]), p["enc.conv5.b"], 1, 0)))
+    h5 = _act16(F.relu(_conv(h4, _w16(p["enc.conv5.w"]), p["enc.conv5.b"], 1, 0)))
     hf = h5.reshape(h5.shape[0], -1)
-    locs = F.relu(hf @ p["enc.locs.w"] + p["enc.locs.b"])
-    scale = clipped_softplus(hf @ p["enc.std.w"] + p["enc.std.b"])
+    locs = F.relu(_grad16(hf @ _w16(p["enc.locs.w"]) + p["enc.locs.b"]))
+    scale = clipped_softplus(_grad16(hf @ _w16(p["enc.std.w"]) + p["enc.std.b"]))
     if return_acts:
         return locs, scale, (h1, h2, h3, h4, h5)
     return locs, scale
@@ -214,9 +214,9 @@ def encoder(p, x, return_acts: bool = False):
 
 def decoder(p, z, return_acts: bool = False):
     """networks.py:51-59 with hidden_dim = z_dim (gated_ccvae.py:34)."""
-    g0 = F.relu(z @ p["dec.fc1.w"] + p["dec.fc1.b"])
+    g0 = _act16(F.relu(_w16(z) @ _w16(p["dec.fc1.w"]) + p["dec.fc1.b"]))
     g0r = g0.reshape(g0.shape[0], 1, 1, g0.shape[1])
-    g1 = _act16(F.relu(_convT(g0r, p["dec.conv1t.w"], p["dec.conv1t.b"], 1, 0)))
+    g1 = _act16(F.relu(_convT(g0r, _w16(p["dec.conv1t.w"]), p["dec.conv1t.b"], 1, 0)))
     g2 = _act16(F.relu(_convT(g1, _w16(p["dec.conv2t.w"]), p["dec.conv2t.b"], 2, 1)))
     g3 = _act16(F.relu(_convT(g2, _w16(p["dec.conv3t.w"]), p["dec.conv3t.b"], 2, 1)))
     g4 = _act16(F.relu(_convT(g3, _w16(p["dec.conv4t.w"]), p["dec.conv4t.b"], 2, 1)))

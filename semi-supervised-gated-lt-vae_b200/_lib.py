@@ -25,8 +25,9 @@ class LatentFwdArgs(C.Structure):
         ("batch", C.c_int), ("batch_global", C.c_int), ("supervised", C.c_int), ("K", C.c_int),
         ("loc_pre", C.c_void_p), ("scale_pre", C.c_void_p), ("y", C.c_void_p), ("eps", C.c_void_p),
         ("eps_k", C.c_void_p), ("U_y", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
-        ("step_dev", C.c_void_p), ("gate_ws", C.c_void_p), ("loc", C.c_void_p), ("scale", C.c_void_p), ("z", C.c_void_p),
-        ("terms", C.c_void_p), ("logits", C.c_void_p), ("y_out", C.c_void_p),
+        ("step_dev", C.c_void_p), ("gate_ws", C.c_void_p), ("ld_pre", C.c_int), ("loc", C.c_void_p),
+        ("scale", C.c_void_p), ("z", C.c_void_p),
+        ("terms", C.c_void_p), ("logits", C.c_void_p), ("y_out", C.c_void_p), ("z16", C.c_void_p),
     ]
 
 
@@ -37,13 +38,24 @@ class LatentBwdArgs(C.Structure):
         ("eps_k", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64), ("step_dev", C.c_void_p),
         ("gate_ws", C.c_void_p),
         ("terms", C.c_void_p), ("log_pxz", C.c_void_p), ("dz", C.c_void_p), ("dloc_pre", C.c_void_p),
-        ("dscale_pre", C.c_void_p), ("partials", C.c_void_p), ("n_partials", C.c_int), ("loss_out", C.c_void_p),
+        ("dscale_pre", C.c_void_p), ("ld_pre", C.c_int), ("ld_dz", C.c_int), ("dpre16", C.c_void_p),
+        ("db_loc", C.c_void_p), ("db_scale", C.c_void_p),
+        ("partials", C.c_void_p), ("n_partials", C.c_int), ("loss_out", C.c_void_p),
     ]
 
 
 class PackJob(C.Structure):
     _fields_ = [("kind", C.c_int), ("taps", C.c_int), ("CL", C.c_int), ("CS", C.c_int), ("W", C.c_void_p),
-                ("out", C.c_void_p)]
+                ("out", C.c_void_p), ("sr", C.c_int), ("sk", C.c_int), ("ld_out", C.c_int), ("row_off", C.c_int),
+                ("col_off", C.c_int), ("pad_", C.c_int)]
+
+
+class WgSeg(C.Structure):
+    _fields_ = [("col0", C.c_int), ("ncols", C.c_int), ("ld", C.c_int), ("pad_", C.c_int), ("dst", C.c_void_p)]
+
+
+class WgOut(C.Structure):
+    _fields_ = [("n_seg", C.c_int), ("m_valid", C.c_int), ("seg", WgSeg * 2)]
 
 
 _P, _I, _F, _LL, _SZ, _U64 = C.c_void_p, C.c_int, C.c_float, C.c_longlong, C.c_size_t, C.c_uint64
@@ -69,7 +81,9 @@ SIGNATURES = {
     "gccvae_ls_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_sl_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_wg_bf16": (_I, [_G, _P, _P, _P, _P]),
-    "gccvae_colsum_bf16": (_I, [_P, _LL, _I, _P, _P]),
+    "gccvae_colsum_bf16": (_I, [_P, _LL, _I, _I, _P, _P]),
+    "gccvae_gemm_bf16": (_I, [_LL, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
+    "gccvae_gemm_tn_bf16": (_I, [_LL, _I, _I, _P, _P, C.POINTER(WgOut), _P]),
     "gccvae_im2col_x_bf16": (_I, [_P, _I, _P, _P]),
     "gccvae_recon_im2col_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "gccvae_pack_c4_bf16": (_I, [_P, _I, _P, _P]),

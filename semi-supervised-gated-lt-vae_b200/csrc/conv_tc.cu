@@ -260,8 +260,7 @@ struct alignas(64) WgParams {
   short a_dw[16], a_dh[16];
   int N;
   int tiles_total, tiles_per_cta;
-  float* dW;
-  int m_total;
+  gccvae_wg_out out;   // destination segments (columns -> tensors); out.m_valid rows are stored
   int stages;
 };
 
@@ -360,13 +359,26 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
         const int mrow = p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m;
-        if (m < p.m_total && !(p.c4_rows && (m & 3) == 3)) {
-          float* dst = p.dW + (size_t)mrow * p.N + c0;
+        if (m < p.out.m_valid && !(p.c4_rows && (m & 3) == 3)) {
 #pragma unroll
-          for (int i = 0; i < 16; i += 4)
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst + i), "f"(__uint_as_float(r[i])),
-                         "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])), "f"(__uint_as_float(r[i + 3]))
-                         : "memory");
+          for (int sg = 0; sg < 2; ++sg) {
+            if (sg >= p.out.n_seg) break;
+            const int col0 = p.out.seg[sg].col0, ncols = p.out.seg[sg].ncols, ld = p.out.seg[sg].ld;
+            if (c0 + 16 <= col0 || c0 >= col0 + ncols) continue;
+            float* drow = p.out.seg[sg].dst + (size_t)mrow * ld - col0;   // drow[c] = element of column c
+            if ((ld & 3) == 0 && (col0 & 3) == 0 && c0 >= col0 && c0 + 16 <= col0 + ncols) {
+#pragma unroll
+              for (int i = 0; i < 16; i += 4)
+                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(drow + c0 + i),
+                             "f"(__uint_as_float(r[i])), "f"(__uint_as_float(r[i + 1])), "f"(__uint_as_float(r[i + 2])),
+                             "f"(__uint_as_float(r[i + 3]))
+                             : "memory");
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i)
+                if (c0 + i >= col0 && c0 + i < col0 + ncols) atomicAdd(drow + c0 + i, __uint_as_float(r[i]));
+            }
+          }
         }
       }
       tc_fence_before();
@@ -381,7 +393,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
 
 // bias gradient from a bf16 [rows, cols] tensor: out[c] += sum_r in[r,c]  (fp32 atomics; out pre-zeroed)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols,
-                                                          int rows_per_cta, float* __restrict__ out) {
+                                                          int rows_per_cta, int n_valid, float* __restrict__ out) {
   // thread handles column pair (2 bf16) ; cols even, cols/2 <= 128 -> 256 threads cover (cols/2) x (256/(cols/2)) rows
   const int cp = cols >> 1;
   const int tc = threadIdx.x % cp, tr = threadIdx.x / cp, nr = 256 / cp;
@@ -404,8 +416,8 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
       a0 += red[q * cp + tc][0];
       a1 += red[q * cp + tc][1];
     }
-    atomicAdd(out + 2 * tc, a0);
-    atomicAdd(out + 2 * tc + 1, a1);
+    if (2 * tc < n_valid) atomicAdd(out + 2 * tc, a0);
+    if (2 * tc + 1 < n_valid) atomicAdd(out + 2 * tc + 1, a1);
   }
 }
 
@@ -536,6 +548,18 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
   } else if (jb.kind == 2) {   // plain cast
     const long long n = (long long)taps * CL * CS;
     for (long long i = i0; i < n; i += stride) out[i] = __float2bfloat16(W[i]);
+  } else if (jb.kind == 4 || jb.kind == 5) {
+    // strided copy into a zero-padded operand: out[(row_off + r) * ld_out + col_off + k] = W[r*sr + k*sk]
+    // (kind 4: bf16 destination, kind 5: fp32 destination); taps = R, CL = K, CS unused
+    const int R = jb.taps, K = jb.CL;
+    const long long n = (long long)R * K;
+    for (long long i = i0; i < n; i += stride) {
+      const int r = (int)(i / K), k = (int)(i % K);
+      const float v = W[(size_t)r * jb.sr + (size_t)k * jb.sk];
+      const size_t o = (size_t)(jb.row_off + r) * jb.ld_out + jb.col_off + k;
+      if (jb.kind == 4) out[o] = __float2bfloat16(v);
+      else reinterpret_cast<float*>(jb.out)[o] = v;
+    }
   } else {                     // c4: out[cs][(tap, c4)], W = [16][3][CS]
     const long long n = (long long)CS * 64;
     for (long long i = i0; i < n; i += stride) {
@@ -844,11 +868,12 @@ extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int
 }
 
 // dW[kh,kw,cl,cs] (fp32, Keras layout) += wgrad; dW must be zeroed by the caller (accumulating entry).
-static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, float* dW, int c4_rows, void* stream) {
-  GCC_REQUIRE(g && L && S && dW, "wg_bf16: null pointer");
+static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, const gccvae_wg_out* out, int c4_rows,
+                        void* stream) {
+  GCC_REQUIRE(g && L && S && out && out->n_seg >= 1 && out->n_seg <= 2 && out->seg[0].dst, "wg_bf16: null pointer");
   const int CL = g->CL, CS = g->CS, taps = g->KH * g->KW;
-  GCC_REQUIRE(CL == 32 || (CL % 64 == 0 && CL <= 256), "wg_bf16: CL=%d unsupported (32, 64, 128, 256)", CL);
-  GCC_REQUIRE(CS == 32 || (CS % 64 == 0 && CS <= 256), "wg_bf16: CS=%d unsupported (32, 64, 128, 256)", CS);
+  GCC_REQUIRE(CL == 32 || CL % 64 == 0, "wg_bf16: CL=%d unsupported (32 or a multiple of 64)", CL);
+  GCC_REQUIRE(CS % 32 == 0 && CS <= 256, "wg_bf16: CS=%d unsupported (multiple of 32, <= 256)", CS);
   WgParams p;
   memset(&p, 0, sizeof(p));
   p.kcA = CL > 64 ? 64 : CL;
@@ -856,7 +881,7 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, floa
   p.blocks_per_mtile = 128 / p.kcA;
   p.taps = taps;
   p.c4_rows = c4_rows;
-  p.kcB = CS > 64 ? 64 : CS;
+  p.kcB = (CS % 64 == 0) ? 64 : 32;
   p.b_loads = CS / p.kcB;
   p.swzA = umma_swizzle_for(p.kcA * 2);
   p.swzB = umma_swizzle_for(p.kcB * 2);
@@ -874,7 +899,7 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, floa
   if ((rc = encode_act_map(&p.tmA, L, g->batch, g->HL, g->WL, CL, p.kcA, bw, bh, bn, es))) return rc;
   if ((rc = encode_act_map(&p.tmB, S, g->batch, g->HS, g->WS, CS, p.kcB, bw, bh, bn, 1))) return rc;
   p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = g->WS / bw; p.tiles_h = g->HS / bh;
-  p.N = CS; p.dW = dW; p.m_total = taps * CL;
+  p.N = CS; p.out = *out;
   const int groups = (g->batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
   const int mtiles = (taps * p.blocks_per_tap + p.blocks_per_mtile - 1) / p.blocks_per_mtile;
@@ -902,7 +927,21 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, floa
 }
 
 extern "C" int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream) {
-  return wg_bf16_impl(g, L, S, dW, 0, stream);
+  GCC_REQUIRE(g && dW, "wg_bf16: null pointer");
+  gccvae_wg_out o;
+  memset(&o, 0, sizeof(o));
+  o.n_seg = 1; o.m_valid = g->KH * g->KW * g->CL;
+  o.seg[0].col0 = 0; o.seg[0].ncols = g->CS; o.seg[0].ld = g->CS; o.seg[0].dst = dW;
+  return wg_bf16_impl(g, L, S, &o, 0, stream);
+}
+
+// D[M, N] += A^T B for row-major bf16 A [rows, M], B [rows, N] (M multiple of 64, N multiple of 32, <= 256);
+// the result is scattered to 1-2 column segments (e.g. the two [256,45] head kernels).
+extern "C" int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, const void* B, const gccvae_wg_out* out,
+                                   void* stream) {
+  GCC_REQUIRE(rows > 0 && rows < (1LL << 31), "gemm_tn: bad row count");
+  gccvae_geom g = {(int)rows, 1, 1, M, 1, 1, N, 1, 1, 1, 0};
+  return wg_bf16_impl(&g, A, B, out, 0, stream);
 }
 
 // conv1 / conv5t weight gradient from the K=64 im2col matrix X64[rows, (tap, c4)]:
@@ -910,19 +949,58 @@ extern "C" int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S
 extern "C" int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream) {
   GCC_REQUIRE(rows > 0 && rows < (1LL << 31), "wg_c4: bad row count");
   gccvae_geom g = {(int)rows, 1, 1, 64, 1, 1, CS, 1, 1, 1, 0};
-  return wg_bf16_impl(&g, X64, S, dW, 1, stream);
+  gccvae_wg_out o;
+  memset(&o, 0, sizeof(o));
+  o.n_seg = 1; o.m_valid = 64;
+  o.seg[0].col0 = 0; o.seg[0].ncols = CS; o.seg[0].ld = CS; o.seg[0].dst = dW;
+  return wg_bf16_impl(&g, X64, S, &o, 1, stream);
 }
 
 // out[c] += sum_r in[r,c] for a bf16 [rows, cols] tensor (out fp32, pre-zeroed by the caller)
-extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, float* out, void* stream) {
-  GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256, "colsum_bf16: bad args (cols=%d)", cols);
+extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int n_valid, float* out, void* stream) {
+  GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256 && (256 % (cols / 2)) == 0,
+              "colsum_bf16: bad args (cols=%d)", cols);
+  if (n_valid <= 0 || n_valid > cols) n_valid = cols;
   long long ctas = (rows + 255) / 256;
   if (ctas > 148 * 4) ctas = 148 * 4;
   const int rpc = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rpc - 1) / rpc;
-  colsum_bf16_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, cols, rpc, out);
+  colsum_bf16_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, cols, rpc, n_valid,
+                                                                  out);
   GCC_CHECK_LAUNCH("colsum_bf16");
   return GCCVAE_OK;
+}
+
+// out[rows, N] = act(A[rows, K] * Wp[N, K]^T + bias) (* mask > 0): dense layers on the tensor cores.
+// K multiple of 16/32/64, N multiple of 16; N > 256 is tiled in slabs.  bias[(n % bias_mod)] for n < bias_n.
+extern "C" int gccvae_gemm_bf16(long long rows, int K, int N, const void* A, const void* Wp, const float* bias,
+                                int bias_n, int bias_mod, int act, const void* mask, void* out, int out_f32,
+                                void* stream) {
+  GCC_REQUIRE(A && Wp && out && rows > 0 && rows < (1LL << 31), "gemm_bf16: bad args");
+  const int kc = (K % 64 == 0) ? 64 : (K % 32 == 0 ? 32 : (K % 16 == 0 ? 16 : 0));
+  GCC_REQUIRE(kc > 0, "gemm_bf16: K=%d must be a multiple of 16", K);
+  GCC_REQUIRE(N % 16 == 0, "gemm_bf16: N=%d must be a multiple of 16", N);
+  int nslab = N;
+  const int m_tiles = (int)((rows + 127) / 128);
+  if (N > 256 || (m_tiles < 74 && N > 64)) {
+    nslab = (N % 64 == 0) ? 64 : ((N % 48 == 0) ? 48 : ((N % 32 == 0) ? 32 : 16));
+    if (N > 256 && m_tiles >= 74) nslab = (N % 256 == 0) ? 256 : ((N % 128 == 0) ? 128 : nslab);
+  }
+  GCC_REQUIRE(N % nslab == 0, "gemm_bf16: cannot tile N=%d", N);
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = encode_act_map(&p.tmA, A, (int)rows, 1, 1, K, kc, 1, 1, 128, 1))) return rc;
+  if ((rc = encode_mat_map(&p.tmB, Wp, N, K, kc, nslab))) return rc;
+  p.num_taps = 1; p.chunks = K / kc; p.a_scale = 1; p.BW = 1; p.BH = 1; p.BN = 128; p.tiles_w = p.tiles_h = 1;
+  p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
+  p.N = nslab; p.n_store = N; p.n_slabs = N / nslab;
+  p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
+  p.bias_n = bias ? (bias_n > 0 ? bias_n : N) : 0;
+  p.bias_mod = bias_mod;
+  p.OH = 1; p.OW = 1; p.OC = N; p.oys = p.oxs = 1;
+  p.batch = (int)rows;
+  return launch_tapgemm(p, m_tiles, 1, (cudaStream_t)stream, "gemm_bf16");
 }
 
 extern "C" size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which) {
@@ -998,7 +1076,7 @@ extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, vo
   PackJobs pj;
   memset(&pj, 0, sizeof(pj));
   for (int i = 0; i < n_jobs; ++i) {
-    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 3, "pack_jobs: bad job %d", i);
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 5, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
   pack_jobs_kernel<<<dim3(64, n_jobs, 1), 256, 0, (cudaStream_t)stream>>>(pj);

@@ -11,6 +11,8 @@
 // 18x18 products shared by the whole batch live in shared memory (written once per step by
 // gate_fwd into `gate_ws`).  HBM traffic per image: 2x[45] heads + (fixed-noise mode only)
 // eps[45] + eps_k[K,18]; outputs 3x[45] + 6 scalars + [18] logits.
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 
 namespace gccvae {
@@ -217,6 +219,7 @@ __global__ void __launch_bounds__(WARPS * 32) latent_fwd_kernel(gccvae_latent_fw
   if (a.step_dev) a.offset += (uint64_t)(*a.step_dev);
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
   const int B = a.batch;
+  const int ldp = a.ld_pre > 0 ? a.ld_pre : Z;
   const float invBg = 1.0f / (float)a.batch_global;
   float* locc = s_locc[wid];
   float* scc = s_scc[wid];
@@ -230,9 +233,10 @@ __global__ void __launch_bounds__(WARPS * 32) latent_fwd_kernel(gccvae_latent_fw
       const int d = lane + 32 * h;
       if (d < Z) {
         float loc, sc;
-        head_act(a.loc_pre[(size_t)b * Z + d], a.scale_pre[(size_t)b * Z + d], loc, sc);
+        head_act(a.loc_pre[(size_t)b * ldp + d], a.scale_pre[(size_t)b * ldp + d], loc, sc);
         const float e = draw_eps(a.eps, a.seed, a.offset, b, d);
         const float z = fmaf(sc, e, loc);
+        if (a.z16 != nullptr) reinterpret_cast<__nv_bfloat16*>(a.z16)[(size_t)b * 64 + d] = __float2bfloat16(z);
         a.loc[(size_t)b * Z + d] = loc;
         a.scale[(size_t)b * Z + d] = sc;
         a.z[(size_t)b * Z + d] = z;
@@ -243,6 +247,8 @@ __global__ void __launch_bounds__(WARPS * 32) latent_fwd_kernel(gccvae_latent_fw
           scc[d - ZS] = sc;
           zcs[d - ZS] = z;
         }
+      } else if (d < 64 && a.z16 != nullptr) {
+        reinterpret_cast<__nv_bfloat16*>(a.z16)[(size_t)b * 64 + d] = __float2bfloat16(0.0f);
       }
     }
     __syncwarp();
@@ -350,9 +356,11 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
   if (lane < Y + 2) s.db[lane] = 0.0f;
   __syncthreads();
   const int B = a.batch;
+  const int ldp = a.ld_pre > 0 ? a.ld_pre : Z, lddz = a.ld_dz > 0 ? a.ld_dz : Z;
   const float invBg = 1.0f / (float)a.batch_global;
   const float logK = SUP ? logf((float)a.K) : 0.0f;
   float loss_acc = 0.0f;
+  float dbl[2] = {0.0f, 0.0f}, dbs[2] = {0.0f, 0.0f};  // bias-gradient partial sums of the two heads
 
   for (int b = blockIdx.x * WARPS + wid; b < B; b += gridDim.x * WARPS) {
     // --- recompute the forward quantities ---------------------------------------------------------
@@ -362,8 +370,8 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
       const int d = lane + 32 * h;
       locv[h] = scv[h] = lpre[h] = spre[h] = 0.0f;
       if (d < Z) {
-        lpre[h] = a.loc_pre[(size_t)b * Z + d];
-        spre[h] = a.scale_pre[(size_t)b * Z + d];
+        lpre[h] = a.loc_pre[(size_t)b * ldp + d];
+        spre[h] = a.scale_pre[(size_t)b * ldp + d];
         head_act(lpre[h], spre[h], locv[h], scv[h]);
         const float e = draw_eps(a.eps, a.seed, a.offset, b, d);
         s.ev[d] = e;
@@ -511,7 +519,7 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
     for (int h = 0; h < 2; ++h) {
       const int d = lane + 32 * h;
       if (d < Z) {
-        float dzt = a.dz[(size_t)b * Z + d];
+        float dzt = a.dz[(size_t)b * lddz + d];
         float dloc, dsc;
         if (d < ZS) {
           dloc = dzt + cA * locv[h];
@@ -523,11 +531,36 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
           dsc = dzt * s.ev[d] + s.dsckl[i] + s.dsx[i];
         }
         const float spv = softplus_f(spre[h]);
-        a.dloc_pre[(size_t)b * Z + d] = (lpre[h] > 0.0f) ? dloc : 0.0f;
-        a.dscale_pre[(size_t)b * Z + d] = (spv >= 1e-3f && spv <= 1e3f) ? dsc * sigmoid_f(spre[h]) : 0.0f;
+        const float gl = (lpre[h] > 0.0f) ? dloc : 0.0f;
+        const float gs = (spv >= 1e-3f && spv <= 1e3f) ? dsc * sigmoid_f(spre[h]) : 0.0f;
+        if (a.dloc_pre != nullptr) {
+          a.dloc_pre[(size_t)b * Z + d] = gl;
+          a.dscale_pre[(size_t)b * Z + d] = gs;
+        }
+        if (a.dpre16 != nullptr) {
+          __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(a.dpre16) + (size_t)b * 96;
+          row[d] = __float2bfloat16(gl);
+          row[48 + d] = __float2bfloat16(gs);
+        }
+        dbl[h] += gl;
+        dbs[h] += gs;
+      } else if (d < 48 && a.dpre16 != nullptr) {
+        __nv_bfloat16* row = reinterpret_cast<__nv_bfloat16*>(a.dpre16) + (size_t)b * 96;
+        row[d] = __float2bfloat16(0.0f);
+        row[48 + d] = __float2bfloat16(0.0f);
       }
     }
     __syncwarp();
+  }
+  if (a.db_loc != nullptr) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int d = lane + 32 * h;
+      if (d < Z) {
+        atomicAdd(a.db_loc + d, dbl[h]);
+        atomicAdd(a.db_scale + d, dbs[h]);
+      }
+    }
   }
   // --- CTA reduction of the per-warp batch sums -> one partial row per CTA ---------------------------------------
   if (lane == 0) s_loss[wid] = loss_acc;
@@ -819,9 +852,10 @@ extern "C" int gccvae_latent_bwd_partials(int batch) { return latent_grid(batch)
 extern "C" int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream) {
   GCC_REQUIRE(a, "latent_bwd: null args");
   GCC_REQUIRE(a->batch > 0 && a->batch_global >= a->batch, "latent_bwd: bad batch");
-  GCC_REQUIRE(a->loc_pre && a->scale_pre && a->y && a->gate_ws && a->terms && a->log_pxz && a->dz && a->dloc_pre &&
-                  a->dscale_pre && a->partials,
+  GCC_REQUIRE(a->loc_pre && a->scale_pre && a->y && a->gate_ws && a->terms && a->log_pxz && a->dz && a->partials,
               "latent_bwd: null pointer");
+  GCC_REQUIRE((a->dloc_pre && a->dscale_pre) || a->dpre16, "latent_bwd: no destination for the head gradients");
+  GCC_REQUIRE((a->db_loc == nullptr) == (a->db_scale == nullptr), "latent_bwd: db_loc and db_scale go together");
   GCC_REQUIRE((uintptr_t)a->eps_k % 8 == 0, "latent_bwd: eps_k must be 8-byte aligned");
   const int grid = latent_grid(a->batch);
   GCC_REQUIRE(a->n_partials == grid, "latent_bwd: n_partials must be %d", grid);

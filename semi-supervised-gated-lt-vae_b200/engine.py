@@ -118,6 +118,12 @@ class Engine:
             _lib.check(fn(C.byref(g), ptr(dout), ptr(W), None, act, ptr(mask), ptr(dx), st), lay[0] + " dgrad")
 
     # ---- step hooks shared with the tensor-core engine ------------------------------------------------
+    def latent_io(self, b):
+        """device pointers / strides through which the fused latent kernels talk to this engine."""
+        return dict(loc_pre=ptr(b["enc.locs.out"]), scale_pre=ptr(b["enc.std.out"]), ld_pre=45, z16=None,
+                    dz=ptr(b["dz"]), ld_dz=45, dloc_pre=ptr(b["enc.locs.dout"]), dscale_pre=ptr(b["enc.std.dout"]),
+                    dpre16=None, db_loc=None, db_scale=None)
+
     def zero_grads(self):
         """the fp32 kernels overwrite every gradient; nothing to clear."""
 
@@ -141,7 +147,7 @@ class Engine:
             self.layer_fwd(lay, B, h, b[lay[0] + ".out"])
         return b["enc.locs.out"].view(B, 45), b["enc.std.out"].view(B, 45)
 
-    def decoder_fwd(self, z, b):
+    def decoder_fwd(self, z, b, z16_ready=False):
         B = z.shape[0]
         h = z
         for lay in DEC_LAYERS:

@@ -5,8 +5,8 @@ losses and all gradients of parameters are fp32.  Layer -> kernel map:
 
   enc.conv1   x fp32 -> K=64 im2col matrix X64 (bf16) -> dense tcgen05 GEMM; wgrad from X64
   enc.conv2-4 tap-GEMM (16 taps, stride-2 TMA boxes); dgrad = 4-phase tap-GEMM; wgrad = MN-major GEMM
-  enc.conv5   dense tcgen05 GEMM [B,2048]x[2048,256] (fp32 output for the heads)
-  heads, dec.fc1, dec.conv1t   (45-wide, <1% of the FLOPs) fp32 CUDA-core kernels of conv_f32.cu
+  enc.conv5   dense tcgen05 GEMM [B,2048]x[2048,256]
+  heads, dec.fc1, dec.conv1t   45-wide dense layers, operands zero-padded to 64 / 96: dense tcgen05 GEMMs
   dec.conv2t-4t  4-phase tap-GEMM; dgrad = 16-tap tap-GEMM; wgrad = MN-major GEMM
   dec.conv5t  4-phase tap-GEMM, N=16 (3 real channels), float4 image output; the reconstruction
               log-likelihood kernel emits its gradient directly as the im2col matrix G64, from which
@@ -42,14 +42,23 @@ class EngineTC(Engine):
         super().__init__(store)
         dev = self.device
         lib = self.lib
+        z16 = lambda *shape: torch.zeros(*shape, dtype=BF16, device=dev)
         self.wp = {}
         for name in TC_ENC + TC_DEC + ["dec.conv5t"]:
             lay = _ENC.get(name) or _DEC[name]
             g = make_geom(lay, 1)
-            self.wp[name + ".ls"] = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(g), 0), dtype=BF16, device=dev)
-            self.wp[name + ".sl"] = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(g), 1), dtype=BF16, device=dev)
-        self.wp["enc.conv1.c4"] = torch.zeros(32 * 64, dtype=BF16, device=dev)
-        self.wp["dec.conv5t.c4"] = torch.zeros(32 * 64, dtype=BF16, device=dev)
+            self.wp[name + ".ls"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 0))
+            self.wp[name + ".sl"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 1))
+        self.wp["enc.conv1.c4"] = z16(32 * 64)
+        self.wp["dec.conv5t.c4"] = z16(32 * 64)
+        # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
+        self.wp["heads.ls"] = z16(96, 256)       # rows 0..44 = W_loc^T, 48..92 = W_std^T
+        self.wp["heads.sl"] = z16(256, 96)
+        self.wp["heads.bias"] = torch.zeros(96, dtype=torch.float32, device=dev)
+        self.wp["fc1.ls"] = z16(64, 64)
+        self.wp["fc1.sl"] = z16(64, 64)
+        self.wp["conv1t.sl"] = z16(2048, 64)
+        self.wp["conv1t.ls"] = z16(64, 2048)
         self._jobs = None
 
     # ---- packed weights ---------------------------------------------------------------------------------
@@ -58,70 +67,75 @@ class EngineTC(Engine):
         if self._jobs is None:
             v = self.store.view
             jobs = []
+            J = lambda kind, taps, CL, CS, W, out, sr=0, sk=0, ld=0, ro=0, co=0: jobs.append(
+                _lib.PackJob(kind, taps, CL, CS, ptr(W), ptr(out), sr, sk, ld, ro, co, 0))
             for name in TC_ENC + TC_DEC:
                 lay = _ENC.get(name) or _DEC[name]
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
-                jobs.append((0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"]))
-                kind = 2 if (HS == 1 and WS == 1) else 1
-                jobs.append((kind, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"]))
-            jobs.append((1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"]))
-            jobs.append((3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"]))
-            jobs.append((3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"]))
-            arr = (_lib.PackJob * len(jobs))()
-            for i, (kind, taps, CL, CS, W, out) in enumerate(jobs):
-                arr[i] = _lib.PackJob(kind, taps, CL, CS, ptr(W), ptr(out))
+                J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
+                J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
+            J(1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"])
+            J(3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"])
+            J(3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"])
+            # kind 4/5: out[(ro + r) * ld + co + k] = W[r * sr + k * sk],  r < taps(R), k < CL(K)
+            for off, nm in ((0, "enc.locs"), (48, "enc.std")):
+                J(4, 45, 256, 0, v(nm + ".w"), self.wp["heads.ls"], 1, 45, 256, off, 0)
+                J(4, 256, 45, 0, v(nm + ".w"), self.wp["heads.sl"], 45, 1, 96, 0, off)
+                J(5, 1, 45, 0, v(nm + ".b"), self.wp["heads.bias"], 0, 1, 96, 0, off)
+            J(4, 45, 45, 0, v("dec.fc1.w"), self.wp["fc1.ls"], 1, 45, 64)
+            J(4, 45, 45, 0, v("dec.fc1.w"), self.wp["fc1.sl"], 45, 1, 64)
+            J(4, 2048, 45, 0, v("dec.conv1t.w"), self.wp["conv1t.sl"], 45, 1, 64)
+            J(4, 45, 2048, 0, v("dec.conv1t.w"), self.wp["conv1t.ls"], 1, 45, 2048)
+            arr = (_lib.PackJob * len(jobs))(*jobs)
             self._jobs = arr
         _lib.check(self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()), "pack_jobs")
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def _alloc(self, B):
         dev = self.device
-        e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=dev)
+        e = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         b = {}
         b["X64"] = e(B * 1024, 64, dt=BF16)
         b["G64"] = e(B * 1024, 64, dt=BF16)
-        for name in ["enc.conv1", "enc.conv2", "enc.conv3", "enc.conv4"]:
+        for name in ["enc.conv1", "enc.conv2", "enc.conv3", "enc.conv4", "enc.conv5"]:
             oh, ow, oc = out_shape(_ENC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
             b[name + ".dout"] = e(B, oh, ow, oc, dt=BF16)
-        b["enc.conv5.out"] = e(B, 1, 1, 256)            # fp32: consumed by the fp32 heads
-        b["enc.conv5.dout"] = e(B, 1, 1, 256)
-        b["enc.conv5.dout16"] = e(B, 1, 1, 256, dt=BF16)
-        for name in ["enc.locs", "enc.std"]:
-            b[name + ".out"] = e(B, 1, 1, 45)
-            b[name + ".dout"] = e(B, 1, 1, 45)
-        b["dec.fc1.out"] = e(B, 1, 1, 45)
-        b["dec.fc1.dout"] = e(B, 1, 1, 45)
-        b["dec.conv1t.out"] = e(B, 4, 4, 128)           # fp32 (CUDA-core layer) + bf16 copy for conv2t
-        b["dec.conv1t.out16"] = e(B, 4, 4, 128, dt=BF16)
-        b["dec.conv1t.dout"] = e(B, 4, 4, 128)
-        b["dec.conv1t.dout16"] = e(B, 4, 4, 128, dt=BF16)
-        for name in TC_DEC:
+        b["pre96"] = e(B, 96)                    # heads' pre-activations: locs at cols 0..44, std at 48..92
+        b["dpre16"] = e(B, 96, dt=BF16)
+        b["z16"] = e(B, 64, dt=BF16)
+        b["dz64"] = e(B, 64)
+        b["dec.fc1.out"] = e(B, 64, dt=BF16)     # 45 real channels
+        b["dec.fc1.dout"] = e(B, 64, dt=BF16)
+        for name in ["dec.conv1t"] + TC_DEC:
             oh, ow, oc = out_shape(_DEC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
             b[name + ".dout"] = e(B, oh, ow, oc, dt=BF16)
         b["xhat4"] = e(B, 64, 64, 4)
-        b["dz"] = e(B, 45)
-        ws_bytes = 0
-        for lay in HEAD_LAYERS + DEC_LAYERS[:2]:
-            g = make_geom(lay, B)
-            ws_bytes = max(ws_bytes, self.lib.gccvae_wg_f32_workspace_bytes(C.byref(g)))
-            oh, ow, oc = out_shape(lay)
-            ws_bytes = max(ws_bytes, self.lib.gccvae_colsum_f32_workspace_bytes(B * oh * ow, oc))
-        b["ws"] = torch.empty(ws_bytes // 4 + 16, dtype=torch.float32, device=dev)
-        b["ws_bytes"] = ws_bytes
         return b
 
+    def latent_io(self, b):
+        pre, g_ = b["pre96"], self.store.g
+        return dict(loc_pre=ptr(pre), scale_pre=ptr(pre) + 48 * 4, ld_pre=96, z16=ptr(b["z16"]), dz=ptr(b["dz64"]),
+                    ld_dz=64, dloc_pre=None, dscale_pre=None, dpre16=ptr(b["dpre16"]), db_loc=ptr(g_("enc.locs.b")),
+                    db_scale=ptr(g_("enc.std.b")))
+
     # ---- helpers --------------------------------------------------------------------------------------------
-    def _cast16(self, src, dst):
-        _lib.check(self.lib.gccvae_cast_f32_to_bf16(ptr(src), src.numel(), ptr(dst), _stream()), "cast->bf16")
+    def _gemm(self, rows, K, N, A, Wp, bias, bias_n, bias_mod, act, mask, out, out_f32, what):
+        _lib.check(self.lib.gccvae_gemm_bf16(rows, K, N, ptr(A), ptr(Wp), ptr(bias), bias_n, bias_mod, act, ptr(mask),
+                                             ptr(out), out_f32, _stream()), what)
 
-    def _cast32(self, src, dst):
-        _lib.check(self.lib.gccvae_cast_bf16_to_f32(ptr(src), src.numel(), ptr(dst), _stream()), "cast->f32")
+    def _gemm_tn(self, rows, M, N, A, Bm, segs, m_valid, what):
+        o = _lib.WgOut()
+        o.n_seg, o.m_valid = len(segs), m_valid
+        for i, (col0, ncols, ld, dst) in enumerate(segs):
+            o.seg[i] = _lib.WgSeg(col0, ncols, ld, 0, ptr(dst))
+        _lib.check(self.lib.gccvae_gemm_tn_bf16(rows, M, N, ptr(A), ptr(Bm), C.byref(o), _stream()), what)
 
-    def _bias_grad16(self, dout, name):
-        rows = dout.numel() // dout.shape[-1]
-        _lib.check(self.lib.gccvae_colsum_bf16(ptr(dout), rows, dout.shape[-1], ptr(self.store.g(name + ".b")),
+    def _bias_grad16(self, dout, name, cols=None, n_valid=0):
+        cols = cols or dout.shape[-1]
+        rows = dout.numel() // cols
+        _lib.check(self.lib.gccvae_colsum_bf16(ptr(dout), rows, cols, n_valid, ptr(self.store.g(name + ".b")),
                                                _stream()), name + " bgrad")
 
     def zero_grads(self):
@@ -138,23 +152,24 @@ class EngineTC(Engine):
                                       ACT_RELU, None, ptr(b["enc.conv1.out"]), 0, st), "conv1 fwd")
         h = b["enc.conv1.out"]
         for name in TC_ENC:
-            lay = _ENC[name]
-            g = make_geom(lay, B)
-            f32 = 1 if name == "enc.conv5" else 0
+            g = make_geom(_ENC[name], B)
             _lib.check(lib.gccvae_ls_bf16(C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU,
-                                          None, ptr(b[name + ".out"]), f32, st), name + " fwd")
+                                          None, ptr(b[name + ".out"]), 0, st), name + " fwd")
             h = b[name + ".out"]
-        for lay in HEAD_LAYERS:
-            self.layer_fwd(lay, B, h, b[lay[0] + ".out"])
-        return b["enc.locs.out"].view(B, 45), b["enc.std.out"].view(B, 45)
+        self._gemm(B, 256, 96, h, self.wp["heads.ls"], self.wp["heads.bias"], 96, 0, ACT_NONE, None, b["pre96"], 1,
+                   "heads fwd")
+        return b["pre96"][:, 0:45], b["pre96"][:, 48:93]
 
-    def decoder_fwd(self, z, b):
+    def decoder_fwd(self, z, b, z16_ready=False):
         B = z.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
-        self.layer_fwd(DEC_LAYERS[0], B, z, b["dec.fc1.out"])
-        self.layer_fwd(DEC_LAYERS[1], B, b["dec.fc1.out"], b["dec.conv1t.out"])
-        self._cast16(b["dec.conv1t.out"], b["dec.conv1t.out16"])
-        h = b["dec.conv1t.out16"]
+        if not z16_ready:          # standalone Decoder(z) call; inside the step the latent kernel writes z16
+            b["z16"][:, :45].copy_(z)
+        self._gemm(B, 64, 64, b["z16"], self.wp["fc1.ls"], v("dec.fc1.b"), 45, 0, ACT_RELU, None, b["dec.fc1.out"], 0,
+                   "fc1 fwd")
+        self._gemm(B, 64, 2048, b["dec.fc1.out"], self.wp["conv1t.sl"], v("dec.conv1t.b"), 2048, 128, ACT_RELU, None,
+                   b["dec.conv1t.out"], 0, "conv1t fwd")
+        h = b["dec.conv1t.out"]
         for name in TC_DEC:
             g = make_geom(_DEC[name], B)
             _lib.check(lib.gccvae_sl_bf16(C.byref(g), ptr(h), ptr(self.wp[name + ".sl"]), ptr(v(name + ".b")), ACT_RELU,
@@ -163,7 +178,7 @@ class EngineTC(Engine):
         g = make_geom(_DEC["dec.conv5t"], B)
         _lib.check(lib.gccvae_sl_bf16(C.byref(g), ptr(h), ptr(self.wp["dec.conv5t.sl"]), ptr(v("dec.conv5t.b")),
                                       ACT_SIGMOID, None, ptr(b["xhat4"]), 2, st), "conv5t fwd")
-        return b["xhat4"]
+        return b["xhat4"][..., :3]
 
     def recon(self, x, b, coef, log_pxz, backward):
         B = x.shape[0]
@@ -177,7 +192,6 @@ class EngineTC(Engine):
     def decoder_bwd(self, z, b, want_dz=True):
         B = z.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
-        ws, wsb = b["ws"], b["ws_bytes"]
         # conv5t from the im2col'd logit gradient
         g4 = b["dec.conv4t.out"]
         _lib.check(lib.gccvae_wg_c4_bf16(B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), st), "conv5t wgrad")
@@ -187,35 +201,36 @@ class EngineTC(Engine):
         prev_of = {"dec.conv4t": "dec.conv3t", "dec.conv3t": "dec.conv2t", "dec.conv2t": "dec.conv1t"}
         for name in reversed(TC_DEC):
             geom = make_geom(_DEC[name], B)
-            dout = b[name + ".dout"]
-            pn = prev_of[name]
-            xin = b[pn + ".out16"] if pn == "dec.conv1t" else b[pn + ".out"]
-            dxin = b[pn + ".dout16"] if pn == "dec.conv1t" else b[pn + ".dout"]
+            dout, pn = b[name + ".dout"], prev_of[name]
+            xin, dxin = b[pn + ".out"], b[pn + ".dout"]
             _lib.check(lib.gccvae_wg_bf16(C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), st), name + " wgrad")
             self._bias_grad16(dout, name)
             _lib.check(lib.gccvae_ls_bf16(C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin),
                                           ptr(dxin), 0, st), name + " dgrad")
-        self._cast32(b["dec.conv1t.dout16"], b["dec.conv1t.dout"])
-        # conv1t and fc1 on the fp32 CUDA-core path
-        self.layer_bwd(DEC_LAYERS[1], B, b["dec.fc1.out"], b["dec.conv1t.dout"], b["dec.fc1.dout"], b["dec.fc1.out"],
-                       ws, wsb)
-        self.layer_bwd(DEC_LAYERS[0], B, z, b["dec.fc1.dout"], b["dz"] if want_dz else None, None, ws, wsb)
-        return b["dz"]
+        # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
+        dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
+        self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048, "conv1t wgrad")
+        self._bias_grad16(dg1, "dec.conv1t", cols=128)
+        self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "conv1t dgrad")
+        self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "fc1 wgrad")
+        self._bias_grad16(dg0, "dec.fc1", cols=64, n_valid=45)
+        if want_dz:
+            self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "fc1 dgrad")
+        return b["dz64"][:, :45]
 
     def encoder_bwd(self, x, b):
         B = x.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
-        ws, wsb = b["ws"], b["ws_bytes"]
-        h5, dh5 = b["enc.conv5.out"], b["enc.conv5.dout"]
-        self.layer_bwd(HEAD_LAYERS[0], B, h5, b["enc.locs.dout"], dh5, None, ws, wsb)
-        self.layer_bwd(HEAD_LAYERS[1], B, h5, b["enc.std.dout"], dh5, h5, ws, wsb, accumulate=True)
-        self._cast16(dh5, b["enc.conv5.dout16"])
+        h5, dh5, dpre = b["enc.conv5.out"], b["enc.conv5.dout"], b["dpre16"]
+        # heads: weight gradients of both [256,45] kernels in one GEMM; bias gradients come from the latent kernel
+        self._gemm_tn(B, 256, 96, h5, dpre, [(0, 45, 45, g_("enc.locs.w")), (48, 45, 45, g_("enc.std.w"))], 256,
+                      "heads wgrad")
+        self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "heads dgrad")
         prev_of = {"enc.conv5": "enc.conv4", "enc.conv4": "enc.conv3", "enc.conv3": "enc.conv2",
                    "enc.conv2": "enc.conv1"}
         for name in reversed(TC_ENC):
             geom = make_geom(_ENC[name], B)
-            dout = b["enc.conv5.dout16"] if name == "enc.conv5" else b[name + ".dout"]
-            pn = prev_of[name]
+            dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
             _lib.check(lib.gccvae_wg_bf16(C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), st), name + " wgrad")
             self._bias_grad16(dout, name)

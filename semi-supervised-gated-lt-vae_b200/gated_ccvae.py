@@ -234,7 +234,9 @@ class Learner:
     def _latent_fwd(self, B, lb, b, y, n, supervised, K):
         a = LatentFwdArgs()
         a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
-        a.loc_pre, a.scale_pre = ptr(b["enc.locs.out"]), ptr(b["enc.std.out"])
+        io = self.engine.latent_io(b)
+        a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
+        a.z16 = io["z16"]
         a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
         a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
         a.step_dev = ptr(self.optimiser.step_dev)
@@ -246,12 +248,15 @@ class Learner:
     def _latent_bwd(self, B, lb, b, n, supervised, K):
         a = LatentBwdArgs()
         a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
-        a.loc_pre, a.scale_pre = ptr(b["enc.locs.out"]), ptr(b["enc.std.out"])
+        io = self.engine.latent_io(b)
+        a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
         a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
         a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
         a.step_dev = ptr(self.optimiser.step_dev)
-        a.gate_ws, a.terms, a.log_pxz, a.dz = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"]), ptr(b["dz"])
-        a.dloc_pre, a.dscale_pre = ptr(b["enc.locs.dout"]), ptr(b["enc.std.dout"])
+        a.gate_ws, a.terms, a.log_pxz = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"])
+        a.dz, a.ld_dz = io["dz"], io["ld_dz"]
+        a.dloc_pre, a.dscale_pre, a.dpre16 = io["dloc_pre"], io["dscale_pre"], io["dpre16"]
+        a.db_loc, a.db_scale = io["db_loc"], io["db_scale"]
         a.partials, a.n_partials, a.loss_out = ptr(lb["partials"]), lb["npart"], None
         _lib.check(self.lib.gccvae_latent_bwd(C.byref(a), _stream()), "latent_bwd")
 
@@ -267,7 +272,7 @@ class Learner:
         self._gate(n)
         self.engine.encoder_fwd(x, b)
         self._latent_fwd(B, lb, b, y, n, supervised, k)
-        self.engine.decoder_fwd(lb["z"], b)
+        self.engine.decoder_fwd(lb["z"], b, z16_ready=True)
         xhat = self.engine.recon(x, b, lb["terms"][5], lb["log_pxz"], backward)
         if backward:
             self.engine.decoder_bwd(lb["z"], b)

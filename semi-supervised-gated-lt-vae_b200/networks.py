@@ -62,6 +62,7 @@ class Encoder(_Net):
         B = x.shape[0]
         b = self.engine.bufs(B)
         loc_pre, scale_pre = self.engine.encoder_fwd(x, b)
+        loc_pre, scale_pre = loc_pre.contiguous(), scale_pre.contiguous()
         loc, scale = torch.empty_like(loc_pre), torch.empty_like(scale_pre)
         _lib.check(self.lib.gccvae_head_act_f32(ptr(loc_pre), ptr(scale_pre), loc.numel(), ptr(loc), ptr(scale),
                                                 _stream()), "head_act")

@@ -170,7 +170,7 @@ def test_tc_wgrad(name, batch):
     dW = torch.zeros(k, k, CL, CS, device=d)
     L.check(lib.gccvae_wg_bf16(C.byref(geom), L.ptr(Ld), L.ptr(Sd), L.ptr(dW), _stream()))
     db = torch.zeros(CS, device=d)
-    L.check(lib.gccvae_colsum_bf16(L.ptr(Sd), batch * HS * WS, CS, L.ptr(db), _stream()))
+    L.check(lib.gccvae_colsum_bf16(L.ptr(Sd), batch * HS * WS, CS, 0, L.ptr(db), _stream()))
     torch.cuda.synchronize()
     Wd = torch.zeros(k, k, CL, CS, dtype=torch.float64, requires_grad=True)
     (O._conv(bf(Lt).double(), Wd, None, s, p) * bf(St).double()).sum().backward()
