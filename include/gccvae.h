@@ -136,6 +136,10 @@ int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
 int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
 int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream);
 int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream);
+/* debug aid: while set (device buffer of 32*8 int64), block 0 of every tap-GEMM launch records clock64()
+ * at its pipeline events: [item][0 slot free,1 TMA issued,2 TMEM free,3 operands landed,4 accum ready,
+ * 5 accum read,6 stored]. */
+void gccvae_debug_set_timeline(long long* dev_buf);
 /* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
 int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                        int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream);

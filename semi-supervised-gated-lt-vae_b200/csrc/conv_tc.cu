@@ -49,7 +49,14 @@ struct alignas(64) TapGemmParams {
   int phases;
   int total_items;  // tiles * n_slabs * phases, spread contiguously over the persistent CTAs
   int bias_n;       // number of valid bias entries (channels >= bias_n get no bias)
+  long long* timeline;  // debug: block 0 records clock64() at pipeline events [item][8] (NULL = off)
 };
+
+#define TL(item_local, slot)                                                              \
+  do {                                                                                    \
+    if (p.timeline != nullptr && blockIdx.x == 0 && (item_local) < 32)                    \
+      p.timeline[(item_local) * 8 + (slot)] = clock64();                                  \
+  } while (0)
 
 constexpr int TG_THREADS = 192;
 
@@ -110,11 +117,13 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
         for (int it = 0; it < k_iters; ++it) {
           const int t = it / p.chunks, c = it % p.chunks;
           mbar_wait(&empty[stage], ph ^ 1);
+          if (it == 0) TL(item - item_beg, 0);
           mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
           tma_load_4d(sA + stage * a_stride, &p.tmA, &full[stage], c * p.KC, p.a_scale * w0 + p.a_dw[phase_id][t],
                       p.a_scale * h0 + p.a_dh[phase_id][t], n0);
           tma_load_2d(sB + stage * b_stride, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC,
                       p.b_row0[phase_id] + slab * p.N);
+          if (it == k_iters - 1) TL(item - item_beg, 1);
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
@@ -129,10 +138,12 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const int li = item - item_beg, as = li & 1;
       mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
       tc_fence_after();
+      if (lane == 0) TL(li, 2);
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
       for (int it = 0; it < k_iters; ++it) {
         mbar_wait(&full[stage], ph);
         tc_fence_after();
+        if (lane == 0 && it == k_iters - 1) TL(li, 3);
         if (elect_one()) {
           const uint32_t a0 = smem_u32(sA + stage * a_stride), b0 = smem_u32(sB + stage * b_stride);
           for (int kk = 0; kk < p.KC / 16; ++kk) {
@@ -175,24 +186,50 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       }
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
       tc_fence_after();
+      if (threadIdx.x == 64) TL(li, 4);
+      // bias index of this slab's first channel: host guarantees bias_mod % N == 0 or bias_mod >= n_store,
+      // so no per-element modulo is needed
+      const int bias_base = slab0 % p.bias_mod;
       for (int c0 = 0; c0 < p.N; c0 += 16) {
+        const int cg = slab0 + c0;  // global output channel of this chunk
+        // issue the bias loads first so that their latency overlaps the TMEM load
+        float bv[16];
+        const bool full_bias = p.bias != nullptr && cg + 16 <= p.bias_n;
+        if (full_bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = __ldg(bp + i);
+            bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w;
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            bv[i] = (p.bias != nullptr && cg + i < p.bias_n) ? __ldg(p.bias + bias_base + c0 + i) : 0.0f;
+        }
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)c0, r);
         tmem_ld_wait();
         if (c0 + 16 >= p.N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
           tc_fence_before();
           if (lane == 0) mbar_arrive(&tempty[as]);
+          if (threadIdx.x == 64) TL(li, 5);
         }
-        const int cg = slab0 + c0;  // global output channel of this chunk
         if (!valid || cg >= p.n_store) continue;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          float f = __uint_as_float(r[i]);
-          if (p.bias != nullptr && cg + i < p.bias_n) f += __ldg(p.bias + (cg + i) % p.bias_mod);
-          if (p.act == GCCVAE_ACT_RELU) f = fmaxf(f, 0.0f);
-          else if (p.act == GCCVAE_ACT_SIGMOID) f = sigmoid_f(f);
-          v[i] = f;
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
+        if (p.act == GCCVAE_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        } else if (p.act == GCCVAE_ACT_SIGMOID) {
+          if (p.out_f32 == 2) {   // 3-channel image: only the real channels
+#pragma unroll
+            for (int i = 0; i < 3; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));
+          }
         }
         const size_t o = opix * p.OC + cg;
         if (use_mask) {
@@ -234,6 +271,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
                               pack_bf16x2(v[14], v[15]));
         }
       }
+      if (threadIdx.x == 64) TL(li, 6);
     }
     tc_fence_before();
   }
@@ -725,7 +763,10 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
   return 0;
 }
 
+static long long* g_timeline = nullptr;
+
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
+  p.timeline = g_timeline;
   const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
   // up to 4 persistent CTAs per SM (their epilogues overlap); each gets a ring of >= 3 stages.
   // TMEM: two accumulator stages per CTA, 512 columns per SM.
@@ -747,8 +788,11 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   }
   GCC_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory", name, smem);
   if (p.n_slabs < 1) p.n_slabs = 1;
-  if (p.bias_mod < 1) p.bias_mod = 1 << 30;
+  if (p.bias_mod < 1 || p.bias == nullptr) p.bias_mod = 1 << 30;
   if (p.bias_n < 1) p.bias_n = p.n_store;
+  GCC_REQUIRE(p.bias_mod >= p.n_store || p.bias_mod % p.N == 0, "%s: bias_mod %d incompatible with N slab %d", name,
+              p.bias_mod, p.N);
+  GCC_REQUIRE(p.bias == nullptr || ((uintptr_t)p.bias % 16) == 0, "%s: bias must be 16-byte aligned", name);
   p.phases = phases;
   p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
   int ctas = p.total_items < 148 * per_sm ? p.total_items : 148 * per_sm;
@@ -854,6 +898,8 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
   const int groups = (g->batch + p.BN - 1) / p.BN;
   return launch_tapgemm(p, groups, phases, (cudaStream_t)stream, "sl_bf16");
 }
+
+extern "C" void gccvae_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
 
 extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                                   int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream) {
