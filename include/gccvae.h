@@ -140,6 +140,8 @@ int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* strea
  * at its pipeline events: [item][0 slot free,1 TMA issued,2 TMEM free,3 operands landed,4 accum ready,
  * 5 accum read,6 stored]. */
 void gccvae_debug_set_timeline(long long* dev_buf);
+/* debug aid: force gccvae_sl_bf16 onto the generic 16-load tap-GEMM instead of the halo kernel */
+void gccvae_debug_disable_halo(int off);
 /* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
 int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                        int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream);

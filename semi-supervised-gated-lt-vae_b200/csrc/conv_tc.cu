@@ -283,6 +283,223 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------------
+// S -> L "halo" kernel (Conv2DTranspose forward / Conv2D dgrad for 16x16 and 32x32 S planes).
+// The generic tap-GEMM above reads every input tile 16 times from L2 (4 output-parity phases x 4 taps)
+// and is L2-bandwidth bound.  Here one CTA computes ALL FOUR phases of a tile of BH full-width rows:
+//   * the input rows h0-1 .. h0+BH (one halo row above and below) are loaded ONCE per column shift
+//     dw in {-1,0,+1} (3 TMA boxes, zero-filled outside the image);
+//   * the row shift dh in {-1,0,+1} of a tap is a descriptor start-address offset of BW rows (a multiple
+//     of the swizzle pattern), so the 16 (phase, tap) MMAs all read those three buffers;
+//   * the 16 weight blocks [N x C] stay resident in shared memory for the whole (persistent) kernel;
+//   * 4 phases x 2 stages of fp32 accumulators live in TMEM; 8 epilogue warps drain them.
+// L2->SM traffic per tile: 3*(BH+2)/BH tile-equivalents instead of 16.
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) SlHaloParams {
+  CUtensorMap tmA, tmB;
+  int C, BW, BH, tiles_h;
+  int N, n_store, swz;
+  void* out;
+  const void* mask;
+  const float* bias;
+  int bias_n, act, out_f32;
+  int OH, OW, OC, batch, total_tiles, stages;
+};
+constexpr int HALO_THREADS = 320;
+
+__global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_constant__ SlHaloParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  const int rowb = p.C * 2;                       // bytes per pixel row (64 or 128)
+  const int avb = (p.BH + 2) * p.BW * rowb;       // one column-shift variant
+  const int a_stage = 3 * avb;
+  const int bblk = p.N * rowb;                    // one (phase, tap) weight block
+  uint8_t* sB = smem;
+  uint8_t* sA = smem + ((16 * bblk + 1023) & ~1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * a_stage);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_beg = blockIdx.x * per_cta;
+  const int tile_end = min(tile_beg + per_cta, p.total_tiles);
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < p.N) acc_cols <<= 1;
+  const uint32_t tmem_cols = acc_cols * 8;        // 4 phases x 2 stages
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 8);
+    }
+    mbar_init(bfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
+  for (int i = threadIdx.x; i < 256; i += HALO_THREADS)
+    s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.0f;
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (elect_one() && tile_beg < tile_end) {
+      mbar_expect_tx(bfull, (uint32_t)(16 * bblk));
+      for (int blk = 0; blk < 16; ++blk)   // blk = phase*4 + tap; packed weights: [phase][N rows][tap*C + c]
+        tma_load_2d(sB + blk * bblk, &p.tmB, bfull, (blk & 3) * p.C, (blk >> 2) * p.N);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
+        mbar_wait(&empty[stage], ph ^ 1);
+        mbar_expect_tx(&full[stage], (uint32_t)a_stage);
+        for (int v = 0; v < 3; ++v)
+          tma_load_4d(sA + stage * a_stage + v * avb, &p.tmA, &full[stage], 0, v - 1, h0 - 1, n);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
+    const uint32_t sbo = 8u * (uint32_t)rowb;
+    int stage = 0;
+    uint32_t ph = 0;
+    if (tile_beg < tile_end) mbar_wait(bfull, 0);
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      const int li = tile - tile_beg, as = li & 1;
+      mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+      mbar_wait(&full[stage], ph);
+      tc_fence_after();
+      if (elect_one()) {
+        const uint32_t a0 = smem_u32(sA + stage * a_stage), b0 = smem_u32(sB);
+        for (int phase = 0; phase < 4; ++phase) {
+          const int php = phase >> 1, pwp = phase & 1;
+          const uint32_t tacc = tmem_base + (uint32_t)(as * 4 + phase) * acc_cols;
+          for (int tap = 0; tap < 4; ++tap) {
+            const int dh = php - (tap >> 1), dw = pwp - (tap & 1);
+            const uint32_t aaddr = a0 + (uint32_t)((dw + 1) * avb + (dh + 1) * p.BW * rowb);
+            const uint32_t baddr = b0 + (uint32_t)((phase * 4 + tap) * bblk);
+            for (int kk = 0; kk < p.C / 16; ++kk)
+              umma_bf16(tacc, smem_desc(aaddr + kk * 32, 16, sbo, (uint32_t)p.swz),
+                        smem_desc(baddr + kk * 32, 16, sbo, (uint32_t)p.swz), idesc, (tap > 0 || kk > 0) ? 1u : 0u);
+          }
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[as]);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; ph ^= 1; }
+    }
+  } else {
+    // ===== epilogue: 8 warps; warp pair (q, q+4) shares TMEM lane quadrant q, each takes 2 phases =====
+    const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const int m = q * 32 + lane;
+    const int dy = m / p.BW, dx = m % p.BW;
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      const int li = tile - tile_beg, as = li & 1;
+      const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
+      const int y = h0 + dy;
+      size_t opix[2];
+      uint4 mpre[2][4];
+      const bool use_mask = p.mask != nullptr;
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int phase = half * 2 + j;
+        opix[j] = ((size_t)n * p.OH + (size_t)(2 * y + (phase >> 1))) * p.OW + (2 * dx + (phase & 1));
+        if (use_mask) {   // first 32 channels of the ReLU mask, fetched before the accumulator is ready
+          const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix[j] * p.OC);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (i * 8 < p.n_store) mpre[j][i] = __ldg(mk + i);
+        }
+      }
+      mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int phase = half * 2 + j;
+        const uint32_t tacc = tmem_base + (uint32_t)(as * 4 + phase) * acc_cols + ((uint32_t)(q * 32) << 16);
+        for (int c0 = 0; c0 < p.N; c0 += 16) {
+          uint32_t r[16];
+          tmem_ld16(tacc + (uint32_t)c0, r);
+          tmem_ld_wait();
+          if (j == 1 && c0 + 16 >= p.N) {  // this warp has read both of its accumulators
+            tc_fence_before();
+            if (lane == 0) mbar_arrive(&tempty[as]);
+          }
+          if (c0 >= p.n_store) continue;
+          float v[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + s_bias[c0 + i];
+          if (p.act == GCCVAE_ACT_RELU) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+          } else if (p.act == GCCVAE_ACT_SIGMOID) {
+            if (p.out_f32 == 2) {
+#pragma unroll
+              for (int i = 0; i < 3; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));
+            } else {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __fdividef(1.0f, 1.0f + __expf(-v[i]));
+            }
+          }
+          const size_t o = opix[j] * p.OC + c0;
+          if (use_mask) {
+            uint4 m0, m1;
+            if (c0 == 0) { m0 = mpre[j][0]; m1 = mpre[j][1]; }
+            else if (c0 == 16) { m0 = mpre[j][2]; m1 = mpre[j][3]; }
+            else {
+              const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
+              m0 = __ldg(mk);
+              m1 = __ldg(mk + 1);
+            }
+            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+              if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
+              if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+            }
+          }
+          if (p.out_f32 == 2) {
+            if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix[j]] = make_float4(v[0], v[1], v[2], 0.0f);
+          } else if (p.out_f32) {
+            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          } else {
+            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
+            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                                pack_bf16x2(v[6], v[7]));
+            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                                pack_bf16x2(v[14], v[15]));
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // weight-gradient kernel: dW[(tap,cl), cs] += sum_pix gather(L)[pix,(tap,cl)] * S[pix, cs]
 // The reduction axis of this GEMM is the PIXEL axis, so both operands are MN-major: a TMA box
 // [128 pixels x channels] is, as it lands, the canonical MN-major swizzled layout (channels
@@ -764,6 +981,7 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
 }
 
 static long long* g_timeline = nullptr;
+static bool g_disable_halo = false;
 
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
   p.timeline = g_timeline;
@@ -875,6 +1093,47 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
     GCC_REQUIRE(pick_tile(g->HS, g->WS, &bw, &bh, &bn) == 0, "sl_bf16: cannot tile %dx%d", g->HS, g->WS);
     const int rows_pad = (g->CL + 15) / 16 * 16;
     GCC_REQUIRE(rows_pad <= 256, "sl_bf16: CL too large");
+    GCC_REQUIRE(g->CL % 16 == 0 || (g->CL == 3 && out_f32 == 2 && mask == nullptr),
+                "sl_bf16: CL=%d must be a multiple of 16 (or 3 with the float4 image output)", g->CL);
+    // full-width row tiles (bn == 1, bw == WS), 64/128-byte pixels, N <= 64: the halo kernel applies
+    if (bn == 1 && bw == g->WS && (g->CS == 32 || g->CS == 64) && rows_pad <= 64 && !g_disable_halo) {
+      SlHaloParams hp;
+      memset(&hp, 0, sizeof(hp));
+      EncodeTiledFn enc = get_encode();
+      GCC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+      {
+        cuuint64_t dims[4] = {(cuuint64_t)g->CS, (cuuint64_t)g->WS, (cuuint64_t)g->HS, (cuuint64_t)g->batch};
+        cuuint64_t strides[3] = {(cuuint64_t)g->CS * 2, (cuuint64_t)g->WS * g->CS * 2,
+                                 (cuuint64_t)g->HS * g->WS * g->CS * 2};
+        cuuint32_t box[4] = {(cuuint32_t)g->CS, (cuuint32_t)bw, (cuuint32_t)(bh + 2), 1};
+        cuuint32_t estr[4] = {1, 1, 1, 1};
+        CUresult r = enc(&hp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S), dims, strides, box, estr,
+                         CU_TENSOR_MAP_INTERLEAVE_NONE, tma_swizzle_for(g->CS * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        GCC_REQUIRE(r == CUDA_SUCCESS, "sl_bf16(halo): cuTensorMapEncodeTiled failed: %d", (int)r);
+      }
+      if ((rc = encode_mat_map(&hp.tmB, Wp_sl, 4LL * rows_pad, 4LL * g->CS, g->CS, rows_pad))) return rc;
+      hp.C = g->CS; hp.BW = bw; hp.BH = bh; hp.tiles_h = g->HS / bh;
+      hp.N = rows_pad; hp.n_store = g->CL; hp.swz = umma_swizzle_for(g->CS * 2);
+      hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act; hp.out_f32 = out_f32;
+      hp.OH = g->HL; hp.OW = g->WL; hp.OC = g->CL; hp.batch = g->batch;
+      hp.total_tiles = g->batch * hp.tiles_h;
+      const int rowb = g->CS * 2, a_stage = 3 * (bh + 2) * bw * rowb, b_bytes = (16 * rows_pad * rowb + 1023) & ~1023;
+      int stages = (196 * 1024 - b_bytes - 4096) / a_stage;
+      if (stages > 5) stages = 5;
+      GCC_REQUIRE(stages >= 2, "sl_bf16(halo): shared memory");
+      hp.stages = stages;
+      const size_t smem = (size_t)b_bytes + (size_t)stages * a_stage + 1024 + 2048;
+      static bool attr_set = false;
+      if (!attr_set) {
+        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        attr_set = true;
+      }
+      const int ctas = hp.total_tiles < 148 ? hp.total_tiles : 148;
+      sl_halo_kernel<<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
+      GCC_CHECK_LAUNCH("sl_bf16(halo)");
+      return GCCVAE_OK;
+    }
     phases = 4;
     if ((rc = encode_act_map(&p.tmA, S, g->batch, g->HS, g->WS, g->CS, kc, bw, bh, bn, 1))) return rc;
     p.num_taps = 4; p.chunks = g->CS / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
@@ -889,8 +1148,6 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
     if ((rc = encode_mat_map(&p.tmB, Wp_sl, 4LL * rows_pad, 4LL * g->CS, kc, rows_pad))) return rc;
     p.N = rows_pad; p.n_store = g->CL;
     p.OH = g->HL; p.OW = g->WL; p.OC = g->CL; p.oys = p.oxs = 2;
-    GCC_REQUIRE(g->CL % 16 == 0 || (g->CL == 3 && out_f32 == 2 && mask == nullptr),
-                "sl_bf16: CL=%d must be a multiple of 16 (or 3 with the float4 image output)", g->CL);
   }
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
   p.out = L; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
@@ -900,6 +1157,7 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
 }
 
 extern "C" void gccvae_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
+extern "C" void gccvae_debug_disable_halo(int off) { g_disable_halo = off != 0; }
 
 extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                                   int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream) {
