@@ -231,9 +231,19 @@ def run_ours(args, rank, world, local_rank):
     d2h = 4
 
     # ---- per-kernel timing for the roofline of the dominant kernel ---------------------------------------------
-    roof = None
+    roof, top = None, None
     if hasattr(lrn.engine, "profile_step"):
-        roof = lrn.engine.profile_step(lrn, dev_x[0], dev_y[0])
+        # same process, right after the timed region: every op of 3 eager steps bracketed by CUDA events on the
+        # launching stream; the dominant op = largest total device time per step
+        prof = lrn.engine.profile_step(lrn, dev_x[0], dev_y[0], steps=3)
+        tot = sum(ms * n for ms, n, _ in prof.values())
+        order = sorted(prof.items(), key=lambda kv: -kv[1][0] * kv[1][1])
+        name, (ms, n, nbytes) = order[0]
+        roof = {"bound": "hbm", "kernel": name, "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
+                "bytes_per_launch": nbytes, "ms_per_launch": ms, "launches_per_step": n,
+                "share_of_profiled_step": ms * n / tot, "traffic": None}
+        top = [{"op": k, "ms": round(v[0], 4), "per_step": v[1], "GB/s": round(v[2] / (v[0] * 1e-3) / 1e9, 1)}
+               for k, v in order[:8]]
 
     if rank != 0:
         if world > 1:
@@ -265,6 +275,7 @@ def run_ours(args, rank, world, local_rank):
         roof["peak"], roof["peak_source"] = pk, src
         roof["frac"] = roof["achieved"] / pk
         line["roofline"] = roof
+        line["top_ops"] = top
     if not args.no_cpu_baseline:
         rate, ms = cpu_oracle_rate(args.ref_batch, args.cpu_baseline_steps, 1)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",

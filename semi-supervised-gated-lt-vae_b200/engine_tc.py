@@ -60,6 +60,7 @@ class EngineTC(Engine):
         self.wp["conv1t.sl"] = z16(2048, 64)
         self.wp["conv1t.ls"] = z16(64, 2048)
         self._jobs = None
+        self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
 
     # ---- packed weights ---------------------------------------------------------------------------------
     def pack_weights(self):
@@ -88,7 +89,7 @@ class EngineTC(Engine):
             J(4, 45, 2048, 0, v("dec.conv1t.w"), self.wp["conv1t.ls"], 1, 45, 2048)
             arr = (_lib.PackJob * len(jobs))(*jobs)
             self._jobs = arr
-        _lib.check(self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()), "pack_jobs")
+        self._run("pack_weights", (), lambda: self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()))
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def _alloc(self, B):
@@ -121,22 +122,36 @@ class EngineTC(Engine):
                     db_scale=ptr(g_("enc.std.b")))
 
     # ---- helpers --------------------------------------------------------------------------------------------
+    def _run(self, what, tensors, rc_fn):
+        """issue one C-ABI call; with self.prof set, bracket it with CUDA events on the launching stream and
+        record (duration, bytes of the tensors it reads/writes = its algorithmic HBM traffic)."""
+        if self.prof is None:
+            _lib.check(rc_fn(), what)
+            return
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        _lib.check(rc_fn(), what)
+        e1.record()
+        nbytes = sum(t.numel() * t.element_size() for t in tensors if t is not None)
+        self.prof.append((what, e0, e1, nbytes))
+
     def _gemm(self, rows, K, N, A, Wp, bias, bias_n, bias_mod, act, mask, out, out_f32, what):
-        _lib.check(self.lib.gccvae_gemm_bf16(rows, K, N, ptr(A), ptr(Wp), ptr(bias), bias_n, bias_mod, act, ptr(mask),
-                                             ptr(out), out_f32, _stream()), what)
+        self._run(what, (A, Wp, mask, out), lambda: self.lib.gccvae_gemm_bf16(
+            rows, K, N, ptr(A), ptr(Wp), ptr(bias), bias_n, bias_mod, act, ptr(mask), ptr(out), out_f32, _stream()))
 
     def _gemm_tn(self, rows, M, N, A, Bm, segs, m_valid, what):
         o = _lib.WgOut()
         o.n_seg, o.m_valid = len(segs), m_valid
         for i, (col0, ncols, ld, dst) in enumerate(segs):
             o.seg[i] = _lib.WgSeg(col0, ncols, ld, 0, ptr(dst))
-        _lib.check(self.lib.gccvae_gemm_tn_bf16(rows, M, N, ptr(A), ptr(Bm), C.byref(o), _stream()), what)
+        self._run(what, (A, Bm) + tuple(sg[3] for sg in segs), lambda: self.lib.gccvae_gemm_tn_bf16(
+            rows, M, N, ptr(A), ptr(Bm), C.byref(o), _stream()))
 
     def _bias_grad16(self, dout, name, cols=None, n_valid=0):
         cols = cols or dout.shape[-1]
         rows = dout.numel() // cols
-        _lib.check(self.lib.gccvae_colsum_bf16(ptr(dout), rows, cols, n_valid, ptr(self.store.g(name + ".b")),
-                                               _stream()), name + " bgrad")
+        self._run(name + " bgrad", (dout,), lambda: self.lib.gccvae_colsum_bf16(
+            ptr(dout), rows, cols, n_valid, ptr(self.store.g(name + ".b")), _stream()))
 
     def zero_grads(self):
         self.store.grad.zero_()   # the tensor-core wgrad / bias-grad kernels accumulate (split-K red.global)
@@ -146,18 +161,22 @@ class EngineTC(Engine):
         B = x.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
         self.pack_weights()
-        _lib.check(lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st), "im2col_x")
+        self._run("im2col_x", (x, b["X64"]), lambda: lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st))
         g = _dense64_geom(B * 1024, 32)
-        _lib.check(lib.gccvae_ls_bf16(C.byref(g), ptr(b["X64"]), ptr(self.wp["enc.conv1.c4"]), ptr(v("enc.conv1.b")),
-                                      ACT_RELU, None, ptr(b["enc.conv1.out"]), 0, st), "conv1 fwd")
+        g1 = g
+        self._run("enc.conv1 fwd", (b["X64"], b["enc.conv1.out"]), lambda: lib.gccvae_ls_bf16(
+            C.byref(g1), ptr(b["X64"]), ptr(self.wp["enc.conv1.c4"]), ptr(v("enc.conv1.b")), ACT_RELU, None,
+            ptr(b["enc.conv1.out"]), 0, st))
         h = b["enc.conv1.out"]
         for name in TC_ENC:
             g = make_geom(_ENC[name], B)
-            _lib.check(lib.gccvae_ls_bf16(C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU,
-                                          None, ptr(b[name + ".out"]), 0, st), name + " fwd")
+            self._run(name + " fwd", (h, self.wp[name + ".ls"], b[name + ".out"]),
+                      lambda g=g, h=h, name=name: lib.gccvae_ls_bf16(
+                          C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU, None,
+                          ptr(b[name + ".out"]), 0, st))
             h = b[name + ".out"]
         self._gemm(B, 256, 96, h, self.wp["heads.ls"], self.wp["heads.bias"], 96, 0, ACT_NONE, None, b["pre96"], 1,
-                   "heads fwd")
+                   "enc.heads fwd")
         return b["pre96"][:, 0:45], b["pre96"][:, 48:93]
 
     def decoder_fwd(self, z, b, z16_ready=False):
@@ -166,26 +185,30 @@ class EngineTC(Engine):
         if not z16_ready:          # standalone Decoder(z) call; inside the step the latent kernel writes z16
             b["z16"][:, :45].copy_(z)
         self._gemm(B, 64, 64, b["z16"], self.wp["fc1.ls"], v("dec.fc1.b"), 45, 0, ACT_RELU, None, b["dec.fc1.out"], 0,
-                   "fc1 fwd")
+                   "dec.fc1 fwd")
         self._gemm(B, 64, 2048, b["dec.fc1.out"], self.wp["conv1t.sl"], v("dec.conv1t.b"), 2048, 128, ACT_RELU, None,
-                   b["dec.conv1t.out"], 0, "conv1t fwd")
+                   b["dec.conv1t.out"], 0, "dec.conv1t fwd")
         h = b["dec.conv1t.out"]
         for name in TC_DEC:
             g = make_geom(_DEC[name], B)
-            _lib.check(lib.gccvae_sl_bf16(C.byref(g), ptr(h), ptr(self.wp[name + ".sl"]), ptr(v(name + ".b")), ACT_RELU,
-                                          None, ptr(b[name + ".out"]), 0, st), name + " fwd")
+            self._run(name + " fwd", (h, self.wp[name + ".sl"], b[name + ".out"]),
+                      lambda g=g, h=h, name=name: lib.gccvae_sl_bf16(
+                          C.byref(g), ptr(h), ptr(self.wp[name + ".sl"]), ptr(v(name + ".b")), ACT_RELU, None,
+                          ptr(b[name + ".out"]), 0, st))
             h = b[name + ".out"]
         g = make_geom(_DEC["dec.conv5t"], B)
-        _lib.check(lib.gccvae_sl_bf16(C.byref(g), ptr(h), ptr(self.wp["dec.conv5t.sl"]), ptr(v("dec.conv5t.b")),
-                                      ACT_SIGMOID, None, ptr(b["xhat4"]), 2, st), "conv5t fwd")
+        self._run("dec.conv5t fwd", (h, b["xhat4"]), lambda: lib.gccvae_sl_bf16(
+            C.byref(g), ptr(h), ptr(self.wp["dec.conv5t.sl"]), ptr(v("dec.conv5t.b")), ACT_SIGMOID, None,
+            ptr(b["xhat4"]), 2, st))
         return b["xhat4"][..., :3]
 
     def recon(self, x, b, coef, log_pxz, backward):
         B = x.shape[0]
-        _lib.check(self.lib.gccvae_recon_im2col_bf16(
-            ptr(x), ptr(b["xhat4"]), B, ptr(coef) if backward else None, ptr(log_pxz),
-            ptr(b["G64"]) if backward else None, ptr(self.store.g("dec.conv5t.b")) if backward else None, _stream()),
-            "recon_im2col")
+        self._run("recon_im2col", (x, b["xhat4"], b["G64"] if backward else None),
+                  lambda: self.lib.gccvae_recon_im2col_bf16(
+                      ptr(x), ptr(b["xhat4"]), B, ptr(coef) if backward else None, ptr(log_pxz),
+                      ptr(b["G64"]) if backward else None, ptr(self.store.g("dec.conv5t.b")) if backward else None,
+                      _stream()))
         return b["xhat4"][..., :3]
 
     # ---- backward -----------------------------------------------------------------------------------------------
@@ -194,28 +217,31 @@ class EngineTC(Engine):
         lib, st, g_ = self.lib, _stream(), self.store.g
         # conv5t from the im2col'd logit gradient
         g4 = b["dec.conv4t.out"]
-        _lib.check(lib.gccvae_wg_c4_bf16(B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), st), "conv5t wgrad")
+        self._run("dec.conv5t wgrad", (b["G64"], g4), lambda: lib.gccvae_wg_c4_bf16(
+            B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), st))
         g = _dense64_geom(B * 1024, 32)
-        _lib.check(lib.gccvae_ls_bf16(C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
-                                      ptr(b["dec.conv4t.dout"]), 0, st), "conv5t dgrad")
+        self._run("dec.conv5t dgrad", (b["G64"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_ls_bf16(
+            C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
+            ptr(b["dec.conv4t.dout"]), 0, st))
         prev_of = {"dec.conv4t": "dec.conv3t", "dec.conv3t": "dec.conv2t", "dec.conv2t": "dec.conv1t"}
         for name in reversed(TC_DEC):
             geom = make_geom(_DEC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            _lib.check(lib.gccvae_wg_bf16(C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), st), name + " wgrad")
+            self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
+                C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), st))
             self._bias_grad16(dout, name)
-            _lib.check(lib.gccvae_ls_bf16(C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin),
-                                          ptr(dxin), 0, st), name + " dgrad")
+            self._run(name + " dgrad", (dout, self.wp[name + ".ls"], xin, dxin), lambda: lib.gccvae_ls_bf16(
+                C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
-        self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048, "conv1t wgrad")
+        self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048, "dec.conv1t wgrad")
         self._bias_grad16(dg1, "dec.conv1t", cols=128)
-        self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "conv1t dgrad")
-        self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "fc1 wgrad")
+        self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "dec.conv1t dgrad")
+        self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "dec.fc1 wgrad")
         self._bias_grad16(dg0, "dec.fc1", cols=64, n_valid=45)
         if want_dz:
-            self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "fc1 dgrad")
+            self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "dec.fc1 dgrad")
         return b["dz64"][:, :45]
 
     def encoder_bwd(self, x, b):
@@ -224,18 +250,41 @@ class EngineTC(Engine):
         h5, dh5, dpre = b["enc.conv5.out"], b["enc.conv5.dout"], b["dpre16"]
         # heads: weight gradients of both [256,45] kernels in one GEMM; bias gradients come from the latent kernel
         self._gemm_tn(B, 256, 96, h5, dpre, [(0, 45, 45, g_("enc.locs.w")), (48, 45, 45, g_("enc.std.w"))], 256,
-                      "heads wgrad")
-        self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "heads dgrad")
+                      "enc.heads wgrad")
+        self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "enc.heads dgrad")
         prev_of = {"enc.conv5": "enc.conv4", "enc.conv4": "enc.conv3", "enc.conv3": "enc.conv2",
                    "enc.conv2": "enc.conv1"}
         for name in reversed(TC_ENC):
             geom = make_geom(_ENC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            _lib.check(lib.gccvae_wg_bf16(C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), st), name + " wgrad")
+            self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
+                C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), st))
             self._bias_grad16(dout, name)
-            _lib.check(lib.gccvae_sl_bf16(C.byref(geom), ptr(dout), ptr(self.wp[name + ".sl"]), None, ACT_NONE, ptr(xin),
-                                          ptr(dxin), 0, st), name + " dgrad")
+            self._run(name + " dgrad", (dout, self.wp[name + ".sl"], xin, dxin), lambda: lib.gccvae_sl_bf16(
+                C.byref(geom), ptr(dout), ptr(self.wp[name + ".sl"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
         dh1 = b["enc.conv1.dout"]
-        _lib.check(lib.gccvae_wg_c4_bf16(B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), st), "conv1 wgrad")
+        self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
+            B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), st))
         self._bias_grad16(dh1, "enc.conv1")
+
+    # ---- per-op device timing (bench.py roofline) -------------------------------------------------------------
+    def profile_step(self, learner, x, y, steps=3):
+        """Run `steps` eager supervised+unsupervised train_steps with every tensor-core / data-movement op
+        bracketed by CUDA events; returns {op: (mean ms per launch, launches per step, algorithmic bytes)}."""
+        graphs, learner.use_graphs = learner.use_graphs, False
+        agg = {}
+        try:
+            for _ in range(steps):
+                self.prof = []
+                learner.train_step(x, y, True)
+                learner.train_step(x, None, False)
+                torch.cuda.synchronize(self.device)
+                for what, e0, e1, nbytes in self.prof:
+                    a = agg.setdefault(what, [0.0, 0, nbytes])
+                    a[0] += e0.elapsed_time(e1)
+                    a[1] += 1
+        finally:
+            self.prof = None
+            learner.use_graphs = graphs
+        return {k: (v[0] / v[1], v[1] / steps, v[2]) for k, v in agg.items()}
