@@ -27,7 +27,7 @@ import os
 import numpy as np
 import torch
 
-from . import _lib
+from . import _lib, dp
 from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, LatentBwdArgs, LatentFwdArgs, ptr
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
@@ -174,10 +174,8 @@ class Learner:
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
         self._acc = torch.zeros(1, dtype=torch.float32, device=self.device)
         # data parallel
-        import torch.distributed as dist
-        self._dist = dist if (dist.is_available() and dist.is_initialized()) else None
-        self.world = self._dist.get_world_size() if self._dist else 1
-        self.rank = self._dist.get_rank() if self._dist else 0
+        self._dist = dp.dist_or_none()
+        self.world, self.rank = dp.world_and_rank(self._dist)
 
     # ---- buffers of the latent stage -------------------------------------------------------------------
     def _latent_bufs(self, B):
@@ -226,19 +224,19 @@ class Learner:
         v = self.store.view
         T = float(self.gating_sampler_temp if temperature is None else temperature)
         _lib.check(self.lib.gccvae_gate_fwd(ptr(self.store.view("mu")), ptr(c_in), ptr(n["U1"]), ptr(n["U2"]),
-                                            self.seed, 0, ptr(self.optimiser.step_dev), T, ptr(v("cls.w")),
+                                            dp.gate_seed(self.seed), 0, ptr(self.optimiser.step_dev), T, ptr(v("cls.w")),
                                             ptr(v("cls.b")), ptr(v("prior.loc_true")), ptr(v("prior.loc_false")),
                                             ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
                                             ptr(self._gate_ws), ptr(self._c), _stream()), "gate_fwd")
 
     def _latent_fwd(self, B, lb, b, y, n, supervised, K):
         a = LatentFwdArgs()
-        a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
+        a.batch, a.batch_global, a.supervised, a.K = B, dp.batch_global(B, self.world), int(supervised), K
         io = self.engine.latent_io(b)
         a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
         a.z16 = io["z16"]
         a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
-        a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
+        a.seed, a.offset = dp.data_seed(self.seed, self.rank), 0
         a.step_dev = ptr(self.optimiser.step_dev)
         a.gate_ws = ptr(self._gate_ws)
         a.loc, a.scale, a.z, a.terms, a.logits, a.y_out = (ptr(lb["loc"]), ptr(lb["scale"]), ptr(lb["z"]),
@@ -247,11 +245,11 @@ class Learner:
 
     def _latent_bwd(self, B, lb, b, n, supervised, K):
         a = LatentBwdArgs()
-        a.batch, a.batch_global, a.supervised, a.K = B, B * self.world, int(supervised), K
+        a.batch, a.batch_global, a.supervised, a.K = B, dp.batch_global(B, self.world), int(supervised), K
         io = self.engine.latent_io(b)
         a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
         a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
-        a.seed, a.offset = self.seed + 7919 * (self.rank + 1), 0
+        a.seed, a.offset = dp.data_seed(self.seed, self.rank), 0
         a.step_dev = ptr(self.optimiser.step_dev)
         a.gate_ws, a.terms, a.log_pxz = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"])
         a.dz, a.ld_dz = io["dz"], io["ld_dz"]
@@ -281,15 +279,16 @@ class Learner:
             _lib.check(self.lib.gccvae_gate_bwd(
                 ptr(lb["partials"]), lb["npart"], ptr(v("mu")), ptr(v("cls.w")), ptr(v("prior.loc_true")),
                 ptr(v("prior.loc_false")), ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
-                ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), 1.0 / self.world,
+                ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), dp.l1_scale(self.world),
                 ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
                 ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
                 ptr(self._loss), st), "gate_bwd")
             self.engine.encoder_bwd(x, b)
         else:
-            _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B, B * self.world,
-                                                     int(supervised), ptr(v_mu(self)) if learnable else None,
-                                                     float(self.train_config.get("gating_reg", 0.0)) / self.world,
+            _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B,
+                                                     dp.batch_global(B, self.world), int(supervised),
+                                                     ptr(v_mu(self)) if learnable else None,
+                                                     float(self.train_config.get("gating_reg", 0.0)) * dp.l1_scale(self.world),
                                                      ptr(self._loss), st), "elbo_loss")
         t = lb["terms"]
         self.last = dict(post_locs=lb["loc"], post_scales=lb["scale"], z=lb["z"], logits=lb["logits"], kl=t[0],
@@ -414,14 +413,10 @@ class Learner:
 
     # ---- data parallel ---------------------------------------------------------------------------------------------------
     def _allreduce_grads(self):
-        if self._dist is not None and self.world > 1:
-            self._dist.all_reduce(self.store.grad[: self.n_trainable], op=self._dist.ReduceOp.SUM)
+        dp.allreduce_sum_(self._dist, self.store.grad, self.n_trainable)
 
     def _global_loss(self, loss):
-        if self._dist is not None and self.world > 1:
-            loss = loss.clone()
-            self._dist.all_reduce(loss, op=self._dist.ReduceOp.SUM)
-        return loss
+        return dp.global_scalar(self._dist, loss)
 
 
 def v_mu(learner):
