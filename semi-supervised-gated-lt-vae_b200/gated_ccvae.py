@@ -282,7 +282,7 @@ class Learner:
                 ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), dp.l1_scale(self.world),
                 ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
                 ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
-                ptr(self._loss), st), "gate_bwd")
+                ptr(self.store.loss_slot), st), "gate_bwd")
             self.engine.encoder_bwd(x, b)
         else:
             _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B,
@@ -294,7 +294,7 @@ class Learner:
         self.last = dict(post_locs=lb["loc"], post_scales=lb["scale"], z=lb["z"], logits=lb["logits"], kl=t[0],
                          log_qy_zc=t[1], log_qy_x=t[2], w=t[3], log_py=t[4], log_pxz=lb["log_pxz"], recon=xhat,
                          y=lb["y_i32"], c=self._c, supervised=supervised)
-        return self._loss[0], self._c
+        return (self.store.loss_slot[0] if backward else self._loss[0]), self._c
 
     # ---- reference API ---------------------------------------------------------------------------------------------
     def sup_loss(self, x, y, noise=None, k=100):
@@ -321,8 +321,8 @@ class Learner:
     def loss_and_grads(self, x, y, supervised, noise=None, k=100):
         """forward + backward without the optimiser: (loss, c), gradients in self.store.grad."""
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
-        self._allreduce_grads()
-        return self._global_loss(loss).clone(), c.clone()
+        self._allreduce_grads()      # the loss rides in the tail slot of the gradient buffer
+        return loss.clone(), c.clone()
 
     def train_step(self, x, y, supervised, noise=None, k=100):
         """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update."""
@@ -331,7 +331,7 @@ class Learner:
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
         self._allreduce_grads()
         self.optimiser.apply_gradients()
-        return self._global_loss(loss), c
+        return loss, c
 
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
     def _train_step_graphed(self, x, y, supervised, k):
@@ -345,6 +345,9 @@ class Learner:
             g["y"].copy_(torch.as_tensor(y), non_blocking=True)
         g["graph"].replay()
         self.lib.gccvae_add_launch_count(g["launches"])
+        if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
+            self._allreduce_grads()
+            self.optimiser.apply_gradients()
         return g["loss"], self._c
 
     def _capture(self, key):
@@ -354,9 +357,9 @@ class Learner:
 
         def body():
             loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
-            self._allreduce_grads()
-            self.optimiser.apply_gradients()
-            return self._global_loss(loss)
+            if self.world == 1:
+                self.optimiser.apply_gradients()
+            return loss
 
         # warm-up on a side stream (first-use attribute calls, buffer allocation), state restored afterwards
         saved = (self.store.flat.clone(), self.optimiser.m.clone(), self.optimiser.v.clone(),
@@ -413,7 +416,7 @@ class Learner:
 
     # ---- data parallel ---------------------------------------------------------------------------------------------------
     def _allreduce_grads(self):
-        dp.allreduce_sum_(self._dist, self.store.grad, self.n_trainable)
+        dp.allreduce_sum_(self._dist, self.store.grad_full, self.store.total + 1)
 
     def _global_loss(self, loss):
         return dp.global_scalar(self._dist, loss)

@@ -50,7 +50,11 @@ class ParamStore:
         self.total = off
         self.device = torch.device(device)
         self.flat = torch.zeros(self.total, dtype=torch.float32, device=self.device)
-        self.grad = torch.zeros_like(self.flat)
+        # gradient buffer + 4 trailing floats: slot [total] carries this rank's share of the loss so that the
+        # data-parallel step needs ONE all-reduce for gradients and loss together
+        self.grad_full = torch.zeros(self.total + 4, dtype=torch.float32, device=self.device)
+        self.grad = self.grad_full[: self.total]
+        self.loss_slot = self.grad_full[self.total: self.total + 1]
         # mu sits last so that "all but mu" is one contiguous prefix (frozen-mu modes)
         self.n_without_mu = self.offsets["mu"][0]
 
