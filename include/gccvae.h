@@ -111,6 +111,10 @@ int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const
                    const void* mask, void* S, int out_f32, void* stream);
 int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const float* bias, int act,
                    const void* mask, void* L, int out_f32, void* stream);
+/* Arms the NEXT gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_gemm_bf16 call of this thread: it additionally does
+ * colsum[c % mod] += sum over rows of the values it stores, for channels c < n (mod <= 0: no wrap).  This is the
+ * bias gradient of the layer whose pre-activation gradient the dgrad produces, fused into its epilogue. */
+void gccvae_next_launch_colsum(float* colsum, int n, int mod);
 /* dW (fp32, Keras [kh,kw,cl,cs]) += gather(L)^T S; out[c] += column sums.  Accumulating: zero first. */
 int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream);
 /* out[c] += column sums of a bf16 [rows, cols] tensor for c < n_valid (0 = all) */

@@ -50,6 +50,8 @@ struct alignas(64) TapGemmParams {
   int total_items;  // tiles * n_slabs * phases, spread contiguously over the persistent CTAs
   int bias_n;       // number of valid bias entries (channels >= bias_n get no bias)
   long long* timeline;  // debug: block 0 records clock64() at pipeline events [item][8] (NULL = off)
+  float* colsum;        // optional: += column sums of the stored tile (bias gradient of the producer layer)
+  int colsum_n, colsum_mod;
 };
 
 #define TL(item_local, slot)                                                              \
@@ -60,6 +62,41 @@ struct alignas(64) TapGemmParams {
 
 constexpr int TG_THREADS = 192;
 
+// Column sums of a [32 lanes x 16 columns] register tile: recursive halving (16 shuffles) leaves the sum of
+// column `col` in every lane; lanes with an even id add it to the CTA's shared-memory accumulator.
+__device__ __forceinline__ void warp_colsum16(const float (&v)[16], float* s_col, int idx_base, int n_valid_cols,
+                                              int lane) {
+  float w8[8], w4[4], w2[2], w1;
+  const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const float send = b4 ? v[i] : v[i + 8];
+    const float keep = b4 ? v[i + 8] : v[i];
+    w8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const float send = b3 ? w8[i] : w8[i + 4];
+    const float keep = b3 ? w8[i + 4] : w8[i];
+    w4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+  }
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const float send = b2 ? w4[i] : w4[i + 2];
+    const float keep = b2 ? w4[i + 2] : w4[i];
+    w2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+  }
+  {
+    const float send = b1 ? w2[0] : w2[1];
+    const float keep = b1 ? w2[1] : w2[0];
+    w1 = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+  }
+  w1 += __shfl_xor_sync(0xffffffffu, w1, 1);
+  const int col = (b4 ? 8 : 0) + (b3 ? 4 : 0) + (b2 ? 2 : 0) + (b1 ? 1 : 0);
+  if ((lane & 1) == 0 && col < n_valid_cols) atomicAdd(s_col + idx_base + col, w1);
+}
+
+template <bool COLSUM>
 __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -73,8 +110,11 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   uint64_t* tfull = empty + p.stages;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty = tfull + 2;         // [2] accumulator stage drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  float* s_col = reinterpret_cast<float*>(tmem_slot + 4);   // [256] per-CTA column sums (bias gradient)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (COLSUM)
+    for (int i = threadIdx.x; i < 256; i += TG_THREADS) s_col[i] = 0.0f;
   // persistent: this CTA owns a contiguous range of work items; item = (tile, slab, phase), phase fastest,
   // so the 4 output-parity phases that re-read one input tile run back to back on the same SM.
   const int per_cta = (p.total_items + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -163,6 +203,16 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int dx = m % p.BW, dy = (m / p.BW) % p.BH, dn = m / (p.BW * p.BH);
+    // bias-gradient column sums: with a single N slab of <= 64 columns every thread keeps running sums of its own
+    // row in registers across all items and the cross-lane reduction happens once, after the loop
+    float cacc[COLSUM ? 4 : 1][16];
+    if (COLSUM) {
+#pragma unroll
+      for (int a = 0; a < (COLSUM ? 4 : 1); ++a)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cacc[a][i] = 0.0f;
+    }
+    const bool reg_colsum = COLSUM && p.n_slabs == 1 && p.N <= 64;
     for (int item = item_beg; item < item_end; ++item) {
       const int li = item - item_beg, as = li & 1;
       const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
@@ -215,7 +265,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (lane == 0) mbar_arrive(&tempty[as]);
           if (threadIdx.x == 64) TL(li, 5);
         }
-        if (!valid || cg >= p.n_store) continue;
+        if ((!valid && !COLSUM) || cg >= p.n_store) continue;
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
@@ -256,6 +306,35 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
             if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
           }
         }
+        if constexpr (COLSUM) {
+          if (!valid) {
+#pragma unroll
+            for (int i = 0; i < 16; ++i) v[i] = 0.0f;
+          }
+          if (reg_colsum) {
+            switch (c0 >> 4) {   // static indexing keeps cacc[][] in registers
+              case 0:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[0][i] += v[i];
+                break;
+              case 1:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[1][i] += v[i];
+                break;
+              case 2:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[2][i] += v[i];
+                break;
+              default:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[3][i] += v[i];
+                break;
+            }
+          } else {
+            warp_colsum16(v, s_col, cg % p.colsum_mod, p.colsum_n - cg, lane);
+          }
+          if (!valid) continue;
+        }
         if (p.out_f32 == 2) {
           // 3-channel image padded to 4 (decoder output): one float4 per pixel, pad channel = 0
           if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix] = make_float4(v[0], v[1], v[2], 0.0f);
@@ -273,9 +352,20 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       }
       if (threadIdx.x == 64) TL(li, 6);
     }
+    if constexpr (COLSUM) if (reg_colsum) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a * 16 < p.N && a * 16 < p.colsum_n)
+          warp_colsum16(cacc[a], s_col, (a * 16) % p.colsum_mod, p.colsum_n - a * 16, lane);
+    }
     tc_fence_before();
   }
   __syncthreads();
+  if (COLSUM) {
+    const int ncol = p.colsum_mod < p.colsum_n ? p.colsum_mod : p.colsum_n;
+    for (int i = threadIdx.x; i < ncol; i += TG_THREADS)
+      if (s_col[i] != 0.0f) atomicAdd(p.colsum + i, s_col[i]);
+  }
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -303,9 +393,12 @@ struct alignas(64) SlHaloParams {
   const float* bias;
   int bias_n, act, out_f32;
   int OH, OW, OC, batch, total_tiles, stages;
+  float* colsum;
+  int colsum_n;
 };
 constexpr int HALO_THREADS = 320;
 
+template <bool COLSUM>
 __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_constant__ SlHaloParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -323,6 +416,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   uint64_t* bfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256]
+  float* s_col = s_bias + 256;                                // [256] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
@@ -347,8 +441,10 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
     fence_mbar_init();
   }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
-  for (int i = threadIdx.x; i < 256; i += HALO_THREADS)
+  for (int i = threadIdx.x; i < 256; i += HALO_THREADS) {
     s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.0f;
+    s_col[i] = 0.0f;
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -408,6 +504,13 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
     const int m = q * 32 + lane;
     const int dy = m / p.BW, dx = m % p.BW;
+    float cacc[COLSUM ? 4 : 1][16];   // running column sums of this thread's rows (bias gradient)
+    if (COLSUM) {
+#pragma unroll
+      for (int a = 0; a < (COLSUM ? 4 : 1); ++a)
+#pragma unroll
+        for (int i = 0; i < 16; ++i) cacc[a][i] = 0.0f;
+    }
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int li = tile - tile_beg, as = li & 1;
       const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
@@ -474,6 +577,26 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
               if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
             }
           }
+          if constexpr (COLSUM) {
+            switch (c0 >> 4) {
+              case 0:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[0][i] += v[i];
+                break;
+              case 1:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[1][i] += v[i];
+                break;
+              case 2:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[2][i] += v[i];
+                break;
+              default:
+#pragma unroll
+                for (int i = 0; i < 16; ++i) cacc[3][i] += v[i];
+                break;
+            }
+          }
           if (p.out_f32 == 2) {
             if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix[j]] = make_float4(v[0], v[1], v[2], 0.0f);
           } else if (p.out_f32) {
@@ -490,9 +613,17 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
         }
       }
     }
+    if constexpr (COLSUM) {
+#pragma unroll
+      for (int a = 0; a < 4; ++a)
+        if (a * 16 < p.N && a * 16 < p.colsum_n) warp_colsum16(cacc[a], s_col, a * 16, p.colsum_n - a * 16, lane);
+    }
     tc_fence_before();
   }
   __syncthreads();
+  if (COLSUM)
+    for (int i = threadIdx.x; i < p.colsum_n; i += HALO_THREADS)
+      if (s_col[i] != 0.0f) atomicAdd(p.colsum + i, s_col[i]);
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, tmem_cols);
@@ -980,11 +1111,20 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
   return 0;
 }
 
+static thread_local float* g_colsum = nullptr;
+static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
 static long long* g_timeline = nullptr;
 static bool g_disable_halo = false;
 
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
   p.timeline = g_timeline;
+  p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_mod = g_colsum_mod > 0 ? g_colsum_mod : (1 << 30);
+  g_colsum = nullptr;
+  if (p.colsum) {
+    GCC_REQUIRE(p.colsum_n > 0 && (p.colsum_mod >= p.colsum_n ? p.colsum_n : p.colsum_mod) <= 256 &&
+                    (p.colsum_mod >= (1 << 29) || p.colsum_mod % 16 == 0),
+                "%s: unsupported column-sum shape (n=%d mod=%d)", name, p.colsum_n, p.colsum_mod);
+  }
   const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
   // up to 4 persistent CTAs per SM (their epilogues overlap); each gets a ring of >= 3 stages.
   // TMEM: two accumulator stages per CTA, 512 columns per SM.
@@ -993,15 +1133,16 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   int per_sm = 512 / (2 * (int)acc_cols);
   if (per_sm > 4) per_sm = 4;
   if (per_sm < 1) per_sm = 1;
-  while (per_sm > 1 && (200 * 1024 / per_sm) < 3 * (a_stride + b_stride) + 2048) --per_sm;
-  int stages = ((200 * 1024 / per_sm) - 2048) / (a_stride + b_stride);
+  while (per_sm > 1 && (200 * 1024 / per_sm) < 3 * (a_stride + b_stride) + 3072) --per_sm;
+  int stages = ((200 * 1024 / per_sm) - 3072) / (a_stride + b_stride);
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * (a_stride + b_stride) + 1024 + 256;
+  const size_t smem = (size_t)stages * (a_stride + b_stride) + 1024 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
   GCC_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory", name, smem);
@@ -1015,7 +1156,8 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
   int ctas = p.total_items < 148 * per_sm ? p.total_items : 148 * per_sm;
   dim3 grid(ctas, 1, 1);
-  tapgemm_kernel<<<grid, TG_THREADS, smem, st>>>(p);
+  if (p.colsum != nullptr) tapgemm_kernel<true><<<grid, TG_THREADS, smem, st>>>(p);
+  else tapgemm_kernel<false><<<grid, TG_THREADS, smem, st>>>(p);
   GCC_CHECK_LAUNCH(name);
   return GCCVAE_OK;
 }
@@ -1118,19 +1260,24 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
       hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act; hp.out_f32 = out_f32;
       hp.OH = g->HL; hp.OW = g->WL; hp.OC = g->CL; hp.batch = g->batch;
       hp.total_tiles = g->batch * hp.tiles_h;
+      hp.colsum = g_colsum; hp.colsum_n = g_colsum_n;
+      g_colsum = nullptr;
+      GCC_REQUIRE(hp.colsum == nullptr || (hp.colsum_n > 0 && hp.colsum_n <= 256), "sl_bf16(halo): colsum_n");
       const int rowb = g->CS * 2, a_stage = 3 * (bh + 2) * bw * rowb, b_bytes = (16 * rows_pad * rowb + 1023) & ~1023;
-      int stages = (196 * 1024 - b_bytes - 4096) / a_stage;
+      int stages = (196 * 1024 - b_bytes - 5120) / a_stage;
       if (stages > 5) stages = 5;
       GCC_REQUIRE(stages >= 2, "sl_bf16(halo): shared memory");
       hp.stages = stages;
-      const size_t smem = (size_t)b_bytes + (size_t)stages * a_stage + 1024 + 2048;
+      const size_t smem = (size_t)b_bytes + (size_t)stages * a_stage + 1024 + 3072;
       static bool attr_set = false;
       if (!attr_set) {
-        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
         attr_set = true;
       }
       const int ctas = hp.total_tiles < 148 ? hp.total_tiles : 148;
-      sl_halo_kernel<<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
+      if (hp.colsum != nullptr) sl_halo_kernel<true><<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
+      else sl_halo_kernel<false><<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
       GCC_CHECK_LAUNCH("sl_bf16(halo)");
       return GCCVAE_OK;
     }
@@ -1156,6 +1303,12 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
   return launch_tapgemm(p, groups, phases, (cudaStream_t)stream, "sl_bf16");
 }
 
+// The NEXT gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_gemm_bf16 launch on this thread also accumulates the column
+// sums of what it stores into colsum[(channel % mod)] for channel < n: the bias gradient of the layer whose
+// pre-activation gradient that dgrad produces, fused into the epilogue (no extra pass over the tensor).
+extern "C" void gccvae_next_launch_colsum(float* colsum, int n, int mod) {
+  g_colsum = colsum; g_colsum_n = n; g_colsum_mod = mod;
+}
 extern "C" void gccvae_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
 extern "C" void gccvae_debug_disable_halo(int off) { g_disable_halo = off != 0; }
 
