@@ -167,6 +167,7 @@ class Learner:
         self.seed = int(seed)
         self.use_graphs = bool(graphs)   # replay the whole train_step as ONE CUDA graph (Philox-noise steps only)
         self._graphs = {}
+        self._copy_stream = None
         self.last = {}
         self._lat = {}
         self._gate_ws = torch.zeros(GATE_WS_FLOATS, dtype=torch.float32, device=self.device)
@@ -340,15 +341,48 @@ class Learner:
         g = self._graphs.get(key)
         if g is None:
             g = self._capture(key)
-        g["x"].copy_(torch.as_tensor(x), non_blocking=True)
-        if supervised:
-            g["y"].copy_(torch.as_tensor(y), non_blocking=True)
+        x = torch.as_tensor(x)
+        if x.device.type == "cpu":
+            self._stage_host_inputs(g, x, y if supervised else None)
+        else:
+            g["x"].copy_(x, non_blocking=True)
+            if supervised:
+                g["y"].copy_(torch.as_tensor(y), non_blocking=True)
         g["graph"].replay()
         self.lib.gccvae_add_launch_count(g["launches"])
         if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
             self._allreduce_grads()
             self.optimiser.apply_gradients()
         return g["loss"], self._c
+
+    def _stage_host_inputs(self, g, x, y):
+        """Host batches: the H2D copy runs on a dedicated copy stream into one of two staging buffers, so that the
+        copy of batch n+1 overlaps the compute of batch n (the host never blocks); the main stream then moves the
+        staged batch into the graph's static input with a device-to-device copy."""
+        main = torch.cuda.current_stream()
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        if "stage" not in g:
+            g["stage"] = [dict(x=torch.empty_like(g["x"]), y=None if g["y"] is None else torch.empty_like(g["y"]),
+                               free=None) for _ in range(2)]
+            g["turn"] = 0
+        st = g["stage"][g["turn"]]
+        g["turn"] ^= 1
+        cs = self._copy_stream
+        if st["free"] is not None:
+            cs.wait_event(st["free"])            # the previous consumer of this staging buffer has finished
+        with torch.cuda.stream(cs):
+            st["x"].copy_(x, non_blocking=True)
+            if y is not None:
+                st["y"].copy_(torch.as_tensor(y), non_blocking=True)
+            ready = torch.cuda.Event()
+            ready.record(cs)
+        main.wait_event(ready)
+        g["x"].copy_(st["x"], non_blocking=True)
+        if y is not None:
+            g["y"].copy_(st["y"], non_blocking=True)
+        st["free"] = torch.cuda.Event()
+        st["free"].record(main)
 
     def _capture(self, key):
         B, supervised, k = key

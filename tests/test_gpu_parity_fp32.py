@@ -419,3 +419,20 @@ def test_cuda_graph_replay_equals_eager(precision):
         assert abs(float(la) - float(lb)) <= tol * abs(float(la)), (it, float(la), float(lb))
     assert a.optimiser.iterations == b.optimiser.iterations == 4
     assert rel_err(b.store.flat, a.store.flat) < (1e-6 if precision == "fp32" else 1e-3)
+
+
+def test_graphed_step_accepts_pinned_host_batches():
+    """host (pinned) batches go through the double-buffered copy-stream staging and give the same result."""
+    cfg = dict(cfg_for("inferred"), lr=1e-3)
+    p = O.init_params(0, trained_like=True)
+    a = make_learner(cfg, p, precision="bf16", seed=9, graphs=True)
+    b = make_learner(cfg, p, precision="bf16", seed=9, graphs=True)
+    g = torch.Generator().manual_seed(2)
+    for it in range(5):
+        x = torch.rand(16, 64, 64, 3, generator=g).pin_memory()
+        y = (torch.rand(16, 18, generator=g) < 0.5).long().pin_memory()
+        la, _ = a.train_step(x, y, it % 2 == 0)
+        lb, _ = b.train_step(x.to(dev()), y.to(dev()), it % 2 == 0)
+        torch.cuda.synchronize()
+        assert abs(float(la) - float(lb)) <= 1e-4 * abs(float(lb)), (it, float(la), float(lb))
+    assert rel_err(a.store.flat, b.store.flat) < 1e-3
