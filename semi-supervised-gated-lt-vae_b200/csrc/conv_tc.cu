@@ -15,6 +15,7 @@
 // (TMEM -> registers -> bias/activation/mask -> bf16 -> global).  Persistent: one CTA per SM walks a
 // contiguous range of (tile, N-slab, phase) work items; the accumulator is double-buffered in TMEM so
 // the epilogue of item i overlaps the TMA/MMA main loop of item i+1.
+#include <stdlib.h>
 #include <string.h>
 
 #include <mutex>
@@ -113,6 +114,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   float* s_col = reinterpret_cast<float*>(tmem_slot + 4);   // [256] per-CTA column sums (bias gradient)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   if (COLSUM)
     for (int i = threadIdx.x; i < 256; i += TG_THREADS) s_col[i] = 0.0f;
   // persistent: this CTA owns a contiguous range of work items; item = (tile, slab, phase), phase fastest,
@@ -143,6 +145,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are needed from here on
 
   const int k_iters = p.num_taps * p.chunks;
   if (warp == 0) {
@@ -419,6 +422,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   float* s_col = s_bias + 256;                                // [256] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_beg = blockIdx.x * per_cta;
   const int tile_end = min(tile_beg + per_cta, p.total_tiles);
@@ -442,13 +446,14 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   }
   if (warp == 2) tmem_alloc(tmem_slot, tmem_cols);
   for (int i = threadIdx.x; i < 256; i += HALO_THREADS) {
-    s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.0f;
+    s_bias[i] = (p.bias != nullptr && i < p.bias_n) ? p.bias[i] : 0.0f;   // parameters: not written by the predecessor
     s_col[i] = 0.0f;
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (warp == 0) {
     // ===== TMA producer =====
@@ -664,6 +669,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
   const int mtile = blockIdx.y;
   const int tile_beg = blockIdx.x * p.tiles_per_cta;
   int tile_end = tile_beg + p.tiles_per_cta;
@@ -687,6 +693,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
 
   if (n_tiles > 0) {
     const int tiles_per_group = p.tiles_w * p.tiles_h;
@@ -780,6 +787,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
 // bias gradient from a bf16 [rows, cols] tensor: out[c] += sum_r in[r,c]  (fp32 atomics; out pre-zeroed)
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols,
                                                           int rows_per_cta, int n_valid, float* __restrict__ out) {
+  pdl_launch_dependents();
   // thread handles column pair (2 bf16) ; cols even, cols/2 <= 128 -> 256 threads cover (cols/2) x (256/(cols/2)) rows
   const int cp = cols >> 1;
   const int tc = threadIdx.x % cp, tr = threadIdx.x / cp, nr = 256 / cp;
@@ -816,6 +824,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) im2col_x_kernel(const float* __restrict__ x, long long total,
                                                        uint2* __restrict__ out) {
+  pdl_launch_dependents();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int t = (int)(i & 15);
     const long long row = i >> 4;
@@ -841,6 +850,7 @@ __global__ void __launch_bounds__(256) recon_im2col_kernel(const float* __restri
                                                            const float* __restrict__ coef,
                                                            float* __restrict__ log_pxz, uint2* __restrict__ G,
                                                            float* __restrict__ db) {
+  pdl_launch_dependents();
   __shared__ uint2 sD[10][66];   // [input row - (2*oh0-1)][input col + 1], zero border
   __shared__ float red[8][4];
   const int n = blockIdx.x >> 3, oh0 = (blockIdx.x & 7) * 4;
@@ -908,6 +918,7 @@ struct PackJobs {
   gccvae_pack_job j[32];
 };
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
+  pdl_launch_dependents();
   const gccvae_pack_job& jb = jobs.j[blockIdx.y];
   const float* __restrict__ W = jb.W;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(jb.out);
@@ -1111,6 +1122,31 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
   return 0;
 }
 
+static bool g_pdl = true;   // programmatic dependent launch for the tensor-core kernels (GCCVAE_PDL=0 disables)
+
+template <class Params>
+static cudaError_t launch_pdl(void (*kernel)(const Params), dim3 grid, int threads, size_t smem, cudaStream_t st,
+                              const Params& p) {
+  static bool env_read = false;
+  if (!env_read) {
+    const char* e = getenv("GCCVAE_PDL");
+    if (e && e[0] == '0') g_pdl = false;
+    env_read = true;
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid;
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = g_pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, p);
+}
+
 static thread_local float* g_colsum = nullptr;
 static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
 static long long* g_timeline = nullptr;
@@ -1156,8 +1192,8 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
   int ctas = p.total_items < 148 * per_sm ? p.total_items : 148 * per_sm;
   dim3 grid(ctas, 1, 1);
-  if (p.colsum != nullptr) tapgemm_kernel<true><<<grid, TG_THREADS, smem, st>>>(p);
-  else tapgemm_kernel<false><<<grid, TG_THREADS, smem, st>>>(p);
+  if (p.colsum != nullptr) GCC_CUDA(launch_pdl(tapgemm_kernel<true>, grid, TG_THREADS, smem, st, p));
+  else GCC_CUDA(launch_pdl(tapgemm_kernel<false>, grid, TG_THREADS, smem, st, p));
   GCC_CHECK_LAUNCH(name);
   return GCCVAE_OK;
 }
@@ -1276,8 +1312,10 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
         attr_set = true;
       }
       const int ctas = hp.total_tiles < 148 ? hp.total_tiles : 148;
-      if (hp.colsum != nullptr) sl_halo_kernel<true><<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
-      else sl_halo_kernel<false><<<ctas, HALO_THREADS, smem, (cudaStream_t)stream>>>(hp);
+      if (hp.colsum != nullptr)
+        GCC_CUDA(launch_pdl(sl_halo_kernel<true>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
+      else
+        GCC_CUDA(launch_pdl(sl_halo_kernel<false>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
       GCC_CHECK_LAUNCH("sl_bf16(halo)");
       return GCCVAE_OK;
     }
@@ -1378,7 +1416,7 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, cons
     attr_set = true;
   }
   dim3 grid(splits, mtiles, 1);
-  wgrad_kernel<<<grid, TG_THREADS, smem, (cudaStream_t)stream>>>(p);
+  GCC_CUDA(launch_pdl(wgrad_kernel, grid, TG_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("wg_bf16");
   return GCCVAE_OK;
 }

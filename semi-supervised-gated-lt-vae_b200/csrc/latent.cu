@@ -14,6 +14,7 @@
 #include <cuda_bf16.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gccvae {
 
@@ -44,6 +45,7 @@ __global__ void __launch_bounds__(352) gate_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ Wlf, const float* __restrict__ Wst,
                                                        const float* __restrict__ Wsf, float* __restrict__ ws,
                                                        float* __restrict__ c_out) {
+  gccvae::tc::pdl_launch_dependents();
   const int p = threadIdx.x;
   if (p < 32) ws[GW_B + p] = (p < Y) ? bcls[p] : 0.0f;
   if (p >= NP) return;
@@ -212,6 +214,7 @@ __device__ __forceinline__ float kl_dim(float lq, float sq, float lp, float sp) 
 // ---------------------------------------------------------------------------------------------
 template <bool SUP>
 __global__ void __launch_bounds__(WARPS * 32) latent_fwd_kernel(gccvae_latent_fwd_args a) {
+  gccvae::tc::pdl_launch_dependents();
   __shared__ __align__(16) GateSmem g;
   __shared__ float s_locc[WARPS][ZC], s_scc[WARPS][ZC], s_zc[WARPS][ZC];
   load_gate_smem(g, a.gate_ws);
@@ -344,6 +347,7 @@ struct BwdWarpSmem {
 
 template <bool SUP>
 __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bwd_args a) {
+  gccvae::tc::pdl_launch_dependents();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateSmem& g = *reinterpret_cast<GateSmem*>(smem_raw);
   BwdWarpSmem* wsm_all = reinterpret_cast<BwdWarpSmem*>(smem_raw + ((sizeof(GateSmem) + 15) / 16) * 16);
@@ -591,6 +595,7 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
 // column-wise sum of the per-CTA partial rows -> one row (4 independent accumulators per thread)
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
                                                               float* __restrict__ out) {
+  gccvae::tc::pdl_launch_dependents();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= PT_TOTAL) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -617,6 +622,7 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dWlt, float* __restrict__ dWlf,
                                                        float* __restrict__ dWst, float* __restrict__ dWsf,
                                                        float* __restrict__ dmu, float* __restrict__ loss_inout) {
+  gccvae::tc::pdl_launch_dependents();
   __shared__ float s_dc[NP];
   __shared__ float s_red[352 / 32];
   const int p = threadIdx.x;

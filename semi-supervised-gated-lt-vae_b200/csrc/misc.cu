@@ -3,6 +3,7 @@
 #include <stdarg.h>
 
 #include "common.cuh"
+#include "tc_common.cuh"
 
 namespace gccvae {
 
@@ -59,12 +60,14 @@ __global__ void __launch_bounds__(256) recon_kernel(const float4* __restrict__ x
 
 // Keras 2.8 Adam.  `step_dev` (optional) holds t on the device so that a captured CUDA graph of the
 // whole step can be replayed: bump_kernel increments it before every update.
-__global__ void bump_kernel(int* p) { *p += 1; }
+__global__ void bump_kernel(int* p) {  gccvae::tc::pdl_launch_dependents();
+ *p += 1; }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float lr, float b1, float b2, float eps, int step,
                                                    const int* __restrict__ step_dev) {
+  gccvae::tc::pdl_launch_dependents();
   const int t = step_dev ? *step_dev : step;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {

@@ -134,6 +134,12 @@ __host__ __device__ __forceinline__ uint32_t instr_desc_bf16(int M, int N, int a
   return d;
 }
 
+// Programmatic dependent launch: a kernel launched with the programmatic-stream-serialization attribute may
+// start (run its prologue: barrier init, TMEM allocation, descriptor prefetch) while its predecessor drains;
+// pdl_wait() blocks until the predecessor grid has completed and its writes are visible.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
