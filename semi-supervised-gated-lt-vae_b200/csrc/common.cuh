@@ -79,6 +79,32 @@ __host__ __device__ __forceinline__ float u32_to_unit_open0(uint32_t x) {
 }
 
 #ifdef __CUDACC__
+// Launch with the programmatic-stream-serialization attribute (programmatic dependent launch).  EVERY kernel
+// launched through this helper must execute griddepcontrol.wait before it touches global memory.
+// Measured on B200: PDL pays for the tensor-core kernels (long prologues: 2.30 -> 2.10 ms per step) but NOT for
+// the prologue-less auxiliary kernels routed through this helper (2.10 -> 2.17 ms: their early-scheduled CTAs only
+// occupy SM slots), so for them the attribute is off unless GCCVAE_PDL_AUX=1.
+bool pdl_enabled();
+template <class... KArgs, class... Args>
+static inline cudaError_t launch_pdl_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                                       Args... args) {
+  cudaLaunchConfig_t cfg;
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+__device__ __forceinline__ void pdl_prologue() {   // let the successor start, then wait for the predecessor
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+
 // four N(0,1) from one Philox block (Box-Muller on two pairs)
 __device__ __forceinline__ void philox_normal4(uint64_t seed, uint64_t offset, uint32_t stream, uint64_t index,
                                                float (&n)[4]) {

@@ -788,6 +788,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
 __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols,
                                                           int rows_per_cta, int n_valid, float* __restrict__ out) {
   pdl_launch_dependents();
+  pdl_wait();
   // thread handles column pair (2 bf16) ; cols even, cols/2 <= 128 -> 256 threads cover (cols/2) x (256/(cols/2)) rows
   const int cp = cols >> 1;
   const int tc = threadIdx.x % cp, tr = threadIdx.x / cp, nr = 256 / cp;
@@ -825,6 +826,7 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
 __global__ void __launch_bounds__(256) im2col_x_kernel(const float* __restrict__ x, long long total,
                                                        uint2* __restrict__ out) {
   pdl_launch_dependents();
+  pdl_wait();
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
     const int t = (int)(i & 15);
     const long long row = i >> 4;
@@ -851,6 +853,7 @@ __global__ void __launch_bounds__(256) recon_im2col_kernel(const float* __restri
                                                            float* __restrict__ log_pxz, uint2* __restrict__ G,
                                                            float* __restrict__ db) {
   pdl_launch_dependents();
+  pdl_wait();
   __shared__ uint2 sD[10][66];   // [input row - (2*oh0-1)][input col + 1], zero border
   __shared__ float red[8][4];
   const int n = blockIdx.x >> 3, oh0 = (blockIdx.x & 7) * 4;
@@ -919,6 +922,7 @@ struct PackJobs {
 };
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
   pdl_launch_dependents();
+  pdl_wait();
   const gccvae_pack_job& jb = jobs.j[blockIdx.y];
   const float* __restrict__ W = jb.W;
   __nv_bfloat16* __restrict__ out = reinterpret_cast<__nv_bfloat16*>(jb.out);
@@ -1460,8 +1464,8 @@ extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int 
   if (ctas > 148 * 4) ctas = 148 * 4;
   const int rpc = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rpc - 1) / rpc;
-  colsum_bf16_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)in, rows, cols, rpc, n_valid,
-                                                                  out);
+  GCC_CUDA(launch_pdl_k(colsum_bf16_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
+                        (const __nv_bfloat16*)in, rows, cols, rpc, n_valid, out));
   GCC_CHECK_LAUNCH("colsum_bf16");
   return GCCVAE_OK;
 }
@@ -1540,7 +1544,7 @@ extern "C" int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* 
   const long long total = (long long)batch * 1024 * 16;
   long long ctas = (total + 255) / 256;
   if (ctas > 148 * 16) ctas = 148 * 16;
-  im2col_x_kernel<<<(int)ctas, 256, 0, (cudaStream_t)stream>>>(x, total, (uint2*)X64);
+  GCC_CUDA(launch_pdl_k(im2col_x_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, x, total, (uint2*)X64));
   GCC_CHECK_LAUNCH("im2col_x");
   return GCCVAE_OK;
 }
@@ -1554,7 +1558,8 @@ extern "C" int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int 
   cudaStream_t st = (cudaStream_t)stream;
   fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
   GCC_CHECK_LAUNCH("recon_fill");
-  recon_im2col_kernel<<<batch * 8, 256, 0, st>>>(x, (const float4*)xhat4, coef, log_pxz, (uint2*)G64, db);
+  GCC_CUDA(launch_pdl_k(recon_im2col_kernel, dim3(batch * 8), dim3(256), 0, st, x, (const float4*)xhat4, coef, log_pxz,
+                        (uint2*)G64, db));
   GCC_CHECK_LAUNCH("recon_im2col");
   return GCCVAE_OK;
 }
@@ -1574,7 +1579,7 @@ extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, vo
     GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 5, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
-  pack_jobs_kernel<<<dim3(64, n_jobs, 1), 256, 0, (cudaStream_t)stream>>>(pj);
+  GCC_CUDA(launch_pdl_k(pack_jobs_kernel, dim3(64, n_jobs, 1), dim3(256), 0, (cudaStream_t)stream, pj));
   GCC_CHECK_LAUNCH("pack_jobs");
   return GCCVAE_OK;
 }

@@ -45,7 +45,7 @@ __global__ void __launch_bounds__(352) gate_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ Wlf, const float* __restrict__ Wst,
                                                        const float* __restrict__ Wsf, float* __restrict__ ws,
                                                        float* __restrict__ c_out) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   const int p = threadIdx.x;
   if (p < 32) ws[GW_B + p] = (p < Y) ? bcls[p] : 0.0f;
   if (p >= NP) return;
@@ -214,7 +214,7 @@ __device__ __forceinline__ float kl_dim(float lq, float sq, float lp, float sp) 
 // ---------------------------------------------------------------------------------------------
 template <bool SUP>
 __global__ void __launch_bounds__(WARPS * 32) latent_fwd_kernel(gccvae_latent_fwd_args a) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   __shared__ __align__(16) GateSmem g;
   __shared__ float s_locc[WARPS][ZC], s_scc[WARPS][ZC], s_zc[WARPS][ZC];
   load_gate_smem(g, a.gate_ws);
@@ -347,7 +347,7 @@ struct BwdWarpSmem {
 
 template <bool SUP>
 __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bwd_args a) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   extern __shared__ __align__(16) unsigned char smem_raw[];
   GateSmem& g = *reinterpret_cast<GateSmem*>(smem_raw);
   BwdWarpSmem* wsm_all = reinterpret_cast<BwdWarpSmem*>(smem_raw + ((sizeof(GateSmem) + 15) / 16) * 16);
@@ -595,7 +595,7 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
 // column-wise sum of the per-CTA partial rows -> one row (4 independent accumulators per thread)
 __global__ void __launch_bounds__(128) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
                                                               float* __restrict__ out) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   const int c = blockIdx.x * 128 + threadIdx.x;
   if (c >= PT_TOTAL) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
@@ -622,7 +622,7 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
                                                        float* __restrict__ dWlt, float* __restrict__ dWlf,
                                                        float* __restrict__ dWst, float* __restrict__ dWsf,
                                                        float* __restrict__ dmu, float* __restrict__ loss_inout) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   __shared__ float s_dc[NP];
   __shared__ float s_red[352 / 32];
   const int p = threadIdx.x;
@@ -822,8 +822,8 @@ extern "C" int gccvae_gate_fwd(const float* mu, const float* c_in, const float* 
   GCC_REQUIRE((mu || c_in) && Wcls && bcls && Wlt && Wlf && Wst && Wsf && gate_ws, "gate_fwd: null pointer");
   GCC_REQUIRE((U1 == nullptr) == (U2 == nullptr), "gate_fwd: U1 and U2 must both be given or both be NULL");
   GCC_REQUIRE(temperature > 0.0f, "gate_fwd: temperature must be > 0");
-  gate_fwd_kernel<<<1, 352, 0, (cudaStream_t)stream>>>(mu, c_in, U1, U2, seed, offset, step_dev, temperature, Wcls, bcls, Wlt, Wlf,
-                                                       Wst, Wsf, gate_ws, c_out);
+  GCC_CUDA(launch_pdl_k(gate_fwd_kernel, dim3(1), dim3(352), 0, (cudaStream_t)stream, mu, c_in, U1, U2, seed, offset,
+                        step_dev, temperature, Wcls, bcls, Wlt, Wlf, Wst, Wsf, gate_ws, c_out));
   GCC_CHECK_LAUNCH("gate_fwd");
   return GCCVAE_OK;
 }
@@ -846,9 +846,9 @@ extern "C" int gccvae_latent_fwd(const gccvae_latent_fwd_args* a, void* stream) 
   GCC_REQUIRE((uintptr_t)a->eps_k % 8 == 0, "latent_fwd: eps_k must be 8-byte aligned");
   const int grid = latent_grid(a->batch);
   if (a->supervised)
-    latent_fwd_kernel<true><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(*a);
+    GCC_CUDA(launch_pdl_k(latent_fwd_kernel<true>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, *a));
   else
-    latent_fwd_kernel<false><<<grid, WARPS * 32, 0, (cudaStream_t)stream>>>(*a);
+    GCC_CUDA(launch_pdl_k(latent_fwd_kernel<false>, dim3(grid), dim3(WARPS * 32), 0, (cudaStream_t)stream, *a));
   GCC_CHECK_LAUNCH("latent_fwd");
   return GCCVAE_OK;
 }
@@ -872,13 +872,13 @@ extern "C" int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream) 
       GCC_CUDA(cudaFuncSetAttribute(latent_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done[1] = true;
     }
-    latent_bwd_kernel<true><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(*a);
+    GCC_CUDA(launch_pdl_k(latent_bwd_kernel<true>, dim3(grid), dim3(WARPS * 32), smem, (cudaStream_t)stream, *a));
   } else {
     if (!attr_done[0]) {
       GCC_CUDA(cudaFuncSetAttribute(latent_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
       attr_done[0] = true;
     }
-    latent_bwd_kernel<false><<<grid, WARPS * 32, smem, (cudaStream_t)stream>>>(*a);
+    GCC_CUDA(launch_pdl_k(latent_bwd_kernel<false>, dim3(grid), dim3(WARPS * 32), smem, (cudaStream_t)stream, *a));
   }
   GCC_CHECK_LAUNCH("latent_bwd");
   return GCCVAE_OK;
@@ -893,13 +893,15 @@ extern "C" int gccvae_gate_bwd(float* partials, int n_partials, const float* mu,
               "gate_bwd: null pointer");
   // row n_partials of the buffer receives the column sums (the caller allocates n_partials + 1 rows)
   float* reduced = partials + (size_t)n_partials * PT_TOTAL;
-  reduce_partials_kernel<<<(PT_TOTAL + 127) / 128, 128, 0, (cudaStream_t)stream>>>(partials, n_partials, reduced);
+  GCC_CUDA(launch_pdl_k(reduce_partials_kernel, dim3((PT_TOTAL + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
+                        (const float*)partials, n_partials, reduced));
   GCC_CHECK_LAUNCH("reduce_partials");
   partials = reduced;
   n_partials = 1;
-  gate_bwd_kernel<<<1, 352, 0, (cudaStream_t)stream>>>(partials, n_partials, mu, Wcls, Wlt, Wlf, Wst, Wsf, gate_ws,
+  GCC_CUDA(launch_pdl_k(gate_bwd_kernel, dim3(1), dim3(352), 0, (cudaStream_t)stream, (const float*)partials, n_partials,
+                        mu, Wcls, Wlt, Wlf, Wst, Wsf, gate_ws,
                                                        gating_reg, l1_scale, dWcls, dbcls, dWlt, dWlf, dWst, dWsf, dmu,
-                                                       loss_inout);
+                                                       loss_inout));
   GCC_CHECK_LAUNCH("gate_bwd");
   return GCCVAE_OK;
 }

@@ -1,6 +1,7 @@
 // Reconstruction log-likelihood (+ its gradient), Keras-semantics Adam, column sums, and the
 // library's status plumbing.
 #include <stdarg.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -17,6 +18,14 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 void count_launch(int n) { g_launches += n; }
+bool pdl_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("GCCVAE_PDL_AUX");
+    v = (e && e[0] == '1') ? 1 : 0;
+  }
+  return v == 1;
+}
 
 // ---------------------------------------------------------------------------------------------
 // utils.py:101-105: log p(x|z) = sum_{h,w,c} Laplace(xhat,1).log_prob(x) = -|x-xhat|_1 - n ln2.
@@ -60,14 +69,15 @@ __global__ void __launch_bounds__(256) recon_kernel(const float4* __restrict__ x
 
 // Keras 2.8 Adam.  `step_dev` (optional) holds t on the device so that a captured CUDA graph of the
 // whole step can be replayed: bump_kernel increments it before every update.
-__global__ void bump_kernel(int* p) {  gccvae::tc::pdl_launch_dependents();
+__global__ void bump_kernel(int* p) {
+  pdl_prologue();
  *p += 1; }
 
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g,
                                                    float* __restrict__ m, float* __restrict__ v, long long n,
                                                    float lr, float b1, float b2, float eps, int step,
                                                    const int* __restrict__ step_dev) {
-  gccvae::tc::pdl_launch_dependents();
+  pdl_prologue();
   const int t = step_dev ? *step_dev : step;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
   for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n; i += (long long)gridDim.x * 256) {
@@ -202,11 +212,11 @@ extern "C" int gccvae_adam_f32(float* param, const float* grad, float* m, float*
   long long blocks = (n + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   if (step_dev) {
-    bump_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(step_dev);
+    GCC_CUDA(launch_pdl_k(bump_kernel, dim3(1), dim3(1), 0, (cudaStream_t)stream, step_dev));
     GCC_CHECK_LAUNCH("adam_bump");
   }
-  adam_kernel<<<(int)blocks, 256, 0, (cudaStream_t)stream>>>(param, grad, m, v, n, lr, beta1, beta2, eps, step,
-                                                             step_dev);
+  GCC_CUDA(launch_pdl_k(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, n, lr,
+                        beta1, beta2, eps, step, (const int*)step_dev));
   GCC_CHECK_LAUNCH("adam");
   return GCCVAE_OK;
 }
