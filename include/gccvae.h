@@ -97,7 +97,8 @@ int gccvae_colsum_f32(const float* in, long long rows, int cols, float* out, voi
 size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
 /* batched form of the packing entry points below: ONE launch for all layers of a step.
  * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below);
- * 4/5: strided copy into a zero-padded bf16 / fp32 operand (the 45-wide dense layers padded to 64 / 96) */
+ * 4/5: strided copy into a zero-padded bf16 / fp32 operand (the 45-wide dense layers padded to 64 / 96);
+ * 6: "sl9" packing of the halo kernel */
 typedef struct {
   int kind, taps, CL, CS;
   const float* W;
@@ -138,14 +139,20 @@ int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, cons
                              void* G64, float* db, void* stream);
 int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
 int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
+/* S -> L "halo" kernel for 16x16 / 32x32 S planes with 32 or 64 channels and C_L <= 64: all four output-parity
+ * phases per CTA from three column-shifted halo boxes (3.6x less L2 traffic than gccvae_sl_bf16), one MMA per
+ * shifted view with N = 4*C_L.  Weights packed "sl9" = [9 views][4 phases][C_L padded to 16][C_S]
+ * (gccvae_pack_jobs_bf16 kind 6; gccvae_packed_weight_elems(g, 2) elements). */
+int gccvae_sl_halo_supported(const gccvae_geom* g);
+int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl9, const float* bias, int act,
+                        const void* mask, void* L, int out_f32, void* stream);
 int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream);
 int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream);
 /* debug aid: while set (device buffer of 32*8 int64), block 0 of every tap-GEMM launch records clock64()
  * at its pipeline events: [item][0 slot free,1 TMA issued,2 TMEM free,3 operands landed,4 accum ready,
  * 5 accum read,6 stored]. */
 void gccvae_debug_set_timeline(long long* dev_buf);
-/* debug aid: force gccvae_sl_bf16 onto the generic 16-load tap-GEMM instead of the halo kernel */
-void gccvae_debug_disable_halo(int off);
+
 /* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
 int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                        int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream);

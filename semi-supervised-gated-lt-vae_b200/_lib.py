@@ -88,11 +88,12 @@ SIGNATURES = {
     "gccvae_recon_im2col_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
     "gccvae_pack_c4_bf16": (_I, [_P, _I, _P, _P]),
     "gccvae_wg_c4_bf16": (_I, [_LL, _P, _P, _I, _P, _P]),
+    "gccvae_sl_halo_supported": (_I, [_G]),
+    "gccvae_sl_halo_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
     "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
     "gccvae_next_launch_colsum": (None, [_P, _I, _I]),
     "gccvae_debug_set_timeline": (None, [_P]),
-    "gccvae_debug_disable_halo": (None, [_I]),
     "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),
     "gccvae_gate_fwd": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),

@@ -409,9 +409,9 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   const int rowb = p.C * 2;                       // bytes per pixel row (64 or 128)
   const int avb = (p.BH + 2) * p.BW * rowb;       // one column-shift variant
   const int a_stage = 3 * avb;
-  const int bblk = p.N * rowb;                    // one (phase, tap) weight block
+  const int bblk = 4 * p.N * rowb;                // one view's weight block: [4 phases x N rows][C]
   uint8_t* sB = smem;
-  uint8_t* sA = smem + ((16 * bblk + 1023) & ~1023);
+  uint8_t* sA = smem + ((9 * bblk + 1023) & ~1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * a_stage);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;
@@ -426,9 +426,8 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
   const int tile_beg = blockIdx.x * per_cta;
   const int tile_end = min(tile_beg + per_cta, p.total_tiles);
-  uint32_t acc_cols = 32;
-  while ((int)acc_cols < p.N) acc_cols <<= 1;
-  const uint32_t tmem_cols = acc_cols * 8;        // 4 phases x 2 stages
+  uint32_t tmem_cols = 32;                        // 2 stages x 4 phases x N columns, power of two
+  while ((int)tmem_cols < 8 * p.N) tmem_cols <<= 1;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&p.tmA);
@@ -458,9 +457,9 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   if (warp == 0) {
     // ===== TMA producer =====
     if (elect_one() && tile_beg < tile_end) {
-      mbar_expect_tx(bfull, (uint32_t)(16 * bblk));
-      for (int blk = 0; blk < 16; ++blk)   // blk = phase*4 + tap; packed weights: [phase][N rows][tap*C + c]
-        tma_load_2d(sB + blk * bblk, &p.tmB, bfull, (blk & 3) * p.C, (blk >> 2) * p.N);
+      mbar_expect_tx(bfull, (uint32_t)(9 * bblk));
+      for (int view = 0; view < 9; ++view)   // packed weights "sl9": [view][phase][N rows][C]
+        tma_load_2d(sB + view * bblk, &p.tmB, bfull, 0, view * 4 * p.N);
       int stage = 0;
       uint32_t ph = 0;
       for (int tile = tile_beg; tile < tile_end; ++tile) {
@@ -474,7 +473,11 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
+    // One MMA covers all four output-parity phases: N = 4*N_phase, the B block of a view holds each phase's
+    // weights for the tap that reads this view (zeros where a phase does not use it).  9 views x C/16 MMAs
+    // instead of 16 (phase,tap) x C/16: the MMA pipe is bound by re-reading the 128-row A operand from shared
+    // memory, so fewer, wider instructions are ~1.8x faster.
+    const uint32_t idesc = instr_desc_bf16(128, 4 * p.N, 0, 0);
     const uint32_t sbo = 8u * (uint32_t)rowb;
     int stage = 0;
     uint32_t ph = 0;
@@ -486,17 +489,14 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
       tc_fence_after();
       if (elect_one()) {
         const uint32_t a0 = smem_u32(sA + stage * a_stage), b0 = smem_u32(sB);
-        for (int phase = 0; phase < 4; ++phase) {
-          const int php = phase >> 1, pwp = phase & 1;
-          const uint32_t tacc = tmem_base + (uint32_t)(as * 4 + phase) * acc_cols;
-          for (int tap = 0; tap < 4; ++tap) {
-            const int dh = php - (tap >> 1), dw = pwp - (tap & 1);
-            const uint32_t aaddr = a0 + (uint32_t)((dw + 1) * avb + (dh + 1) * p.BW * rowb);
-            const uint32_t baddr = b0 + (uint32_t)((phase * 4 + tap) * bblk);
-            for (int kk = 0; kk < p.C / 16; ++kk)
-              umma_bf16(tacc, smem_desc(aaddr + kk * 32, 16, sbo, (uint32_t)p.swz),
-                        smem_desc(baddr + kk * 32, 16, sbo, (uint32_t)p.swz), idesc, (tap > 0 || kk > 0) ? 1u : 0u);
-          }
+        const uint32_t tacc = tmem_base + (uint32_t)as * 4u * (uint32_t)p.N;
+        for (int view = 0; view < 9; ++view) {
+          const int dh = view / 3 - 1, dw = view % 3 - 1;
+          const uint32_t aaddr = a0 + (uint32_t)((dw + 1) * avb + (dh + 1) * p.BW * rowb);
+          const uint32_t baddr = b0 + (uint32_t)(view * bblk);
+          for (int kk = 0; kk < p.C / 16; ++kk)
+            umma_bf16(tacc, smem_desc(aaddr + kk * 32, 16, sbo, (uint32_t)p.swz),
+                      smem_desc(baddr + kk * 32, 16, sbo, (uint32_t)p.swz), idesc, (view > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
@@ -539,7 +539,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int phase = half * 2 + j;
-        const uint32_t tacc = tmem_base + (uint32_t)(as * 4 + phase) * acc_cols + ((uint32_t)(q * 32) << 16);
+        const uint32_t tacc = tmem_base + (uint32_t)(as * 4 + phase) * (uint32_t)p.N + ((uint32_t)(q * 32) << 16);
         for (int c0 = 0; c0 < p.N; c0 += 16) {
           uint32_t r[16];
           tmem_ld16(tacc + (uint32_t)c0, r);
@@ -949,6 +949,22 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
   } else if (jb.kind == 2) {   // plain cast
     const long long n = (long long)taps * CL * CS;
     for (long long i = i0; i < n; i += stride) out[i] = __float2bfloat16(W[i]);
+  } else if (jb.kind == 6) {   // "sl9" (halo kernel): out[view][phase][cl (padded)][cs]; view = (dh+1)*3 + (dw+1)
+    const int rows_pad = (CL + 15) / 16 * 16;
+    const long long n = 9LL * 4 * rows_pad * CS;
+    for (long long i = i0; i < n; i += stride) {
+      const int cs = (int)(i % CS);
+      const int cl = (int)((i / CS) % rows_pad);
+      const int phase = (int)((i / ((long long)CS * rows_pad)) % 4), view = (int)(i / ((long long)CS * rows_pad * 4));
+      const int dh = view / 3 - 1, dw = view % 3 - 1, ph = phase >> 1, pw = phase & 1;
+      const int th = ph - dh, tw = pw - dw;   // the tap of this phase that reads input shifted by (dh, dw)
+      float v = 0.0f;
+      if (cl < CL && th >= 0 && th <= 1 && tw >= 0 && tw <= 1) {
+        const int kh = ((ph + 1) & 1) + 2 * th, kw = ((pw + 1) & 1) + 2 * tw;
+        v = W[((size_t)(kh * 4 + kw) * CL + cl) * CS + cs];
+      }
+      out[i] = __float2bfloat16(v);
+    }
   } else if (jb.kind == 4 || jb.kind == 5) {
     // strided copy into a zero-padded operand: out[(row_off + r) * ld_out + col_off + k] = W[r*sr + k*sk]
     // (kind 4: bf16 destination, kind 5: fp32 destination); taps = R, CL = K, CS unused
@@ -1154,7 +1170,6 @@ static cudaError_t launch_pdl(void (*kernel)(const Params), dim3 grid, int threa
 static thread_local float* g_colsum = nullptr;
 static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
 static long long* g_timeline = nullptr;
-static bool g_disable_halo = false;
 
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
   p.timeline = g_timeline;
@@ -1277,52 +1292,6 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
     GCC_REQUIRE(rows_pad <= 256, "sl_bf16: CL too large");
     GCC_REQUIRE(g->CL % 16 == 0 || (g->CL == 3 && out_f32 == 2 && mask == nullptr),
                 "sl_bf16: CL=%d must be a multiple of 16 (or 3 with the float4 image output)", g->CL);
-    // full-width row tiles (bn == 1, bw == WS), 64/128-byte pixels, N <= 64: the halo kernel applies
-    if (bn == 1 && bw == g->WS && (g->CS == 32 || g->CS == 64) && rows_pad <= 64 && !g_disable_halo) {
-      SlHaloParams hp;
-      memset(&hp, 0, sizeof(hp));
-      EncodeTiledFn enc = get_encode();
-      GCC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
-      {
-        cuuint64_t dims[4] = {(cuuint64_t)g->CS, (cuuint64_t)g->WS, (cuuint64_t)g->HS, (cuuint64_t)g->batch};
-        cuuint64_t strides[3] = {(cuuint64_t)g->CS * 2, (cuuint64_t)g->WS * g->CS * 2,
-                                 (cuuint64_t)g->HS * g->WS * g->CS * 2};
-        cuuint32_t box[4] = {(cuuint32_t)g->CS, (cuuint32_t)bw, (cuuint32_t)(bh + 2), 1};
-        cuuint32_t estr[4] = {1, 1, 1, 1};
-        CUresult r = enc(&hp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S), dims, strides, box, estr,
-                         CU_TENSOR_MAP_INTERLEAVE_NONE, tma_swizzle_for(g->CS * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-        GCC_REQUIRE(r == CUDA_SUCCESS, "sl_bf16(halo): cuTensorMapEncodeTiled failed: %d", (int)r);
-      }
-      if ((rc = encode_mat_map(&hp.tmB, Wp_sl, 4LL * rows_pad, 4LL * g->CS, g->CS, rows_pad))) return rc;
-      hp.C = g->CS; hp.BW = bw; hp.BH = bh; hp.tiles_h = g->HS / bh;
-      hp.N = rows_pad; hp.n_store = g->CL; hp.swz = umma_swizzle_for(g->CS * 2);
-      hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act; hp.out_f32 = out_f32;
-      hp.OH = g->HL; hp.OW = g->WL; hp.OC = g->CL; hp.batch = g->batch;
-      hp.total_tiles = g->batch * hp.tiles_h;
-      hp.colsum = g_colsum; hp.colsum_n = g_colsum_n;
-      g_colsum = nullptr;
-      GCC_REQUIRE(hp.colsum == nullptr || (hp.colsum_n > 0 && hp.colsum_n <= 256), "sl_bf16(halo): colsum_n");
-      const int rowb = g->CS * 2, a_stage = 3 * (bh + 2) * bw * rowb, b_bytes = (16 * rows_pad * rowb + 1023) & ~1023;
-      int stages = (196 * 1024 - b_bytes - 5120) / a_stage;
-      if (stages > 5) stages = 5;
-      GCC_REQUIRE(stages >= 2, "sl_bf16(halo): shared memory");
-      hp.stages = stages;
-      const size_t smem = (size_t)b_bytes + (size_t)stages * a_stage + 1024 + 3072;
-      static bool attr_set = false;
-      if (!attr_set) {
-        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-        attr_set = true;
-      }
-      const int ctas = hp.total_tiles < 148 ? hp.total_tiles : 148;
-      if (hp.colsum != nullptr)
-        GCC_CUDA(launch_pdl(sl_halo_kernel<true>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
-      else
-        GCC_CUDA(launch_pdl(sl_halo_kernel<false>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
-      GCC_CHECK_LAUNCH("sl_bf16(halo)");
-      return GCCVAE_OK;
-    }
     phases = 4;
     if ((rc = encode_act_map(&p.tmA, S, g->batch, g->HS, g->WS, g->CS, kc, bw, bh, bn, 1))) return rc;
     p.num_taps = 4; p.chunks = g->CS / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
@@ -1352,7 +1321,6 @@ extern "C" void gccvae_next_launch_colsum(float* colsum, int n, int mod) {
   g_colsum = colsum; g_colsum_n = n; g_colsum_mod = mod;
 }
 extern "C" void gccvae_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
-extern "C" void gccvae_debug_disable_halo(int off) { g_disable_halo = off != 0; }
 
 extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
                                   int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream) {
@@ -1502,9 +1470,74 @@ extern "C" int gccvae_gemm_bf16(long long rows, int K, int N, const void* A, con
   return launch_tapgemm(p, m_tiles, 1, (cudaStream_t)stream, "gemm_bf16");
 }
 
+static bool halo_supported(const gccvae_geom* g, int* bw_out, int* bh_out) {
+  if (!(g->KH == 4 && g->KW == 4 && g->stride == 2 && g->pad == 1)) return false;
+  int bw, bh, bn;
+  if (pick_tile(g->HS, g->WS, &bw, &bh, &bn) != 0) return false;
+  const int rows_pad = (g->CL + 15) / 16 * 16;
+  if (!(bn == 1 && bw == g->WS && (g->CS == 32 || g->CS == 64) && rows_pad <= 64)) return false;
+  if (bw_out) { *bw_out = bw; *bh_out = bh; }
+  return true;
+}
+extern "C" int gccvae_sl_halo_supported(const gccvae_geom* g) { return g && halo_supported(g, nullptr, nullptr) ? 1 : 0; }
+
+// S -> L through the halo kernel (weights packed "sl9", gccvae_pack_jobs_bf16 kind 6).
+extern "C" int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl9, const float* bias, int act,
+                                   const void* mask, void* L, int out_f32, void* stream) {
+  GCC_REQUIRE(g && S && Wp_sl9 && L, "sl_halo: null pointer");
+  int bw = 0, bh = 0, rc;
+  GCC_REQUIRE(halo_supported(g, &bw, &bh), "sl_halo: geometry not supported (use gccvae_sl_bf16)");
+  const int rows_pad = (g->CL + 15) / 16 * 16;
+  GCC_REQUIRE(g->CL % 16 == 0 || (g->CL == 3 && out_f32 == 2 && mask == nullptr),
+              "sl_halo: CL=%d must be a multiple of 16 (or 3 with the float4 image output)", g->CL);
+  SlHaloParams hp;
+  memset(&hp, 0, sizeof(hp));
+  EncodeTiledFn enc = get_encode();
+  GCC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  {
+    cuuint64_t dims[4] = {(cuuint64_t)g->CS, (cuuint64_t)g->WS, (cuuint64_t)g->HS, (cuuint64_t)g->batch};
+    cuuint64_t strides[3] = {(cuuint64_t)g->CS * 2, (cuuint64_t)g->WS * g->CS * 2, (cuuint64_t)g->HS * g->WS * g->CS * 2};
+    cuuint32_t box[4] = {(cuuint32_t)g->CS, (cuuint32_t)bw, (cuuint32_t)(bh + 2), 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&hp.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(S), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, tma_swizzle_for(g->CS * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GCC_REQUIRE(r == CUDA_SUCCESS, "sl_halo: cuTensorMapEncodeTiled failed: %d", (int)r);
+  }
+  if ((rc = encode_mat_map(&hp.tmB, Wp_sl9, 9LL * 4 * rows_pad, g->CS, g->CS, 4 * rows_pad))) return rc;
+  hp.C = g->CS; hp.BW = bw; hp.BH = bh; hp.tiles_h = g->HS / bh;
+  hp.N = rows_pad; hp.n_store = g->CL; hp.swz = umma_swizzle_for(g->CS * 2);
+  hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act; hp.out_f32 = out_f32;
+  hp.OH = g->HL; hp.OW = g->WL; hp.OC = g->CL; hp.batch = g->batch;
+  hp.total_tiles = g->batch * hp.tiles_h;
+  hp.colsum = g_colsum; hp.colsum_n = g_colsum_n;
+  g_colsum = nullptr;
+  GCC_REQUIRE(hp.colsum == nullptr || (hp.colsum_n > 0 && hp.colsum_n <= 256), "sl_halo: colsum_n");
+  const int rowb = g->CS * 2, a_stage = 3 * (bh + 2) * bw * rowb, b_bytes = (9 * 4 * rows_pad * rowb + 1023) & ~1023;
+  int stages = (196 * 1024 - b_bytes - 5120) / a_stage;
+  if (stages > 5) stages = 5;
+  GCC_REQUIRE(stages >= 2, "sl_halo: shared memory");
+  hp.stages = stages;
+  const size_t smem = (size_t)b_bytes + (size_t)stages * a_stage + 1024 + 3072;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(sl_halo_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  const int ctas = hp.total_tiles < 148 ? hp.total_tiles : 148;
+  if (hp.colsum != nullptr)
+    GCC_CUDA(launch_pdl(sl_halo_kernel<true>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
+  else
+    GCC_CUDA(launch_pdl(sl_halo_kernel<false>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
+  GCC_CHECK_LAUNCH("sl_halo_bf16");
+  return GCCVAE_OK;
+}
+
 extern "C" size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which) {
   if (!g) return 0;
   const int taps = g->KH * g->KW;
+  if (which == 2) return (size_t)9 * 4 * ((g->CL + 15) / 16 * 16) * g->CS;                 // sl9 (halo kernel)
   if (which == 0) return (size_t)((g->CS + 15) / 16 * 16) * taps * g->CL;                 // ls
   if (g->HS == 1 && g->WS == 1) return (size_t)taps * g->CL * g->CS;                        // sl dense
   return (size_t)4 * ((g->CL + 15) / 16 * 16) * 4 * g->CS;                                  // sl phases
@@ -1576,7 +1609,7 @@ extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, vo
   PackJobs pj;
   memset(&pj, 0, sizeof(pj));
   for (int i = 0; i < n_jobs; ++i) {
-    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 5, "pack_jobs: bad job %d", i);
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 6, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
   GCC_CUDA(launch_pdl_k(pack_jobs_kernel, dim3(64, n_jobs, 1), dim3(256), 0, (cudaStream_t)stream, pj));

@@ -49,6 +49,13 @@ class EngineTC(Engine):
             g = make_geom(lay, 1)
             self.wp[name + ".ls"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 0))
             self.wp[name + ".sl"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 1))
+        # layers whose S->L direction runs on the halo kernel get the "sl9" packing as well
+        self.halo = {}
+        for name in TC_ENC + TC_DEC + ["dec.conv5t"]:
+            g = make_geom(_ENC.get(name) or _DEC[name], 1)
+            if lib.gccvae_sl_halo_supported(C.byref(g)):
+                self.halo[name] = True
+                self.wp[name + ".sl9"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 2))
         self.wp["enc.conv1.c4"] = z16(32 * 64)
         self.wp["dec.conv5t.c4"] = z16(32 * 64)
         # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
@@ -84,6 +91,9 @@ class EngineTC(Engine):
                 J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
                 J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
             J(1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"])
+            for name in self.halo:
+                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+                J(6, 16, CL, CS, v(name + ".w"), self.wp[name + ".sl9"])
             J(3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"])
             J(3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"])
             # kind 4/5: out[(ro + r) * ld + co + k] = W[r * sr + k * sk],  r < taps(R), k < CL(K)
@@ -144,6 +154,18 @@ class EngineTC(Engine):
         e1.record()
         nbytes = sum(t.numel() * t.element_size() for t in tensors if t is not None)
         self.prof.append((what, e0, e1, nbytes))
+
+    def _sl(self, name, geom, S, bias, act, mask, L, out_f32, what):
+        """S -> L of layer `name` (convT forward / conv dgrad): halo kernel where the geometry allows it."""
+        st = _stream()
+        if name in self.halo:
+            W = self.wp[name + ".sl9"]
+            self._run(what, (S, mask, L), lambda: self.lib.gccvae_sl_halo_bf16(
+                C.byref(geom), ptr(S), ptr(W), ptr(bias), act, ptr(mask), ptr(L), out_f32, st))
+        else:
+            W = self.wp[name + ".sl"]
+            self._run(what, (S, W, mask, L), lambda: self.lib.gccvae_sl_bf16(
+                C.byref(geom), ptr(S), ptr(W), ptr(bias), act, ptr(mask), ptr(L), out_f32, st))
 
     def _gemm(self, rows, K, N, A, Wp, bias, bias_n, bias_mod, act, mask, out, out_f32, what):
         self._run(what, (A, Wp, mask, out), lambda: self.lib.gccvae_gemm_bf16(
@@ -229,15 +251,10 @@ class EngineTC(Engine):
         h = b["dec.conv1t.out"]
         for name in TC_DEC:
             g = make_geom(_DEC[name], B)
-            self._run(name + " fwd", (h, self.wp[name + ".sl"], b[name + ".out"]),
-                      lambda g=g, h=h, name=name: lib.gccvae_sl_bf16(
-                          C.byref(g), ptr(h), ptr(self.wp[name + ".sl"]), ptr(v(name + ".b")), ACT_RELU, None,
-                          ptr(b[name + ".out"]), 0, st))
+            self._sl(name, g, h, v(name + ".b"), ACT_RELU, None, b[name + ".out"], 0, name + " fwd")
             h = b[name + ".out"]
         g = make_geom(_DEC["dec.conv5t"], B)
-        self._run("dec.conv5t fwd", (h, b["xhat4"]), lambda: lib.gccvae_sl_bf16(
-            C.byref(g), ptr(h), ptr(self.wp["dec.conv5t.sl"]), ptr(v("dec.conv5t.b")), ACT_SIGMOID, None,
-            ptr(b["xhat4"]), 2, st))
+        self._sl("dec.conv5t", g, h, v("dec.conv5t.b"), ACT_SIGMOID, None, b["xhat4"], 2, "dec.conv5t fwd")
         return b["xhat4"][..., :3]
 
     def recon(self, x, b, coef, log_pxz, backward):
@@ -306,8 +323,7 @@ class EngineTC(Engine):
                 self._arm_bias_grad(pn, 2048, 128)       # dh4 is [B,(kh,kw,128)]: channel = column % 128
             else:
                 self._arm_bias_grad(pn, xin.shape[-1])
-            self._run(name + " dgrad", (dout, self.wp[name + ".sl"], xin, dxin), lambda: lib.gccvae_sl_bf16(
-                C.byref(geom), ptr(dout), ptr(self.wp[name + ".sl"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
+            self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad")
         dh1 = b["enc.conv1.dout"]
         self._side(lambda: self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
             B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream())))

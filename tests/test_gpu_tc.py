@@ -109,6 +109,18 @@ def _run_tc(direction, geom_t, batch, act, use_mask, use_bias=True):
     got = out.float().cpu().double()
     assert torch.isfinite(got).all(), "output has NaN/unwritten elements"
     err = float((got - want).abs().max() / want.abs().max())
+    if direction == "SL" and lib.gccvae_sl_halo_supported(C.byref(geom)):
+        # the same layer through the halo kernel ("sl9" packing, one wide MMA per shifted view)
+        w9 = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(geom), 2), dtype=torch.bfloat16, device=d)
+        job = (L.PackJob * 1)(L.PackJob(6, 16, CL, CS, L.ptr(Wd), L.ptr(w9), 0, 0, 0, 0, 0, 0))
+        L.check(lib.gccvae_pack_jobs_bf16(job, 1, _stream()))
+        out2 = torch.full(want.shape, float("nan"), dtype=torch.bfloat16, device=d)
+        L.check(lib.gccvae_sl_halo_bf16(C.byref(geom), L.ptr(Xd), L.ptr(w9), L.ptr(bd), act, L.ptr(md), L.ptr(out2), 0,
+                                        _stream()))
+        torch.cuda.synchronize()
+        got2 = out2.float().cpu().double()
+        assert torch.isfinite(got2).all(), "halo output has NaN/unwritten elements"
+        err = max(err, float((got2 - want).abs().max() / want.abs().max()))
     return err
 
 
@@ -226,6 +238,15 @@ def test_tc_end_layers_conv1_and_conv5t():
     xh4 = torch.full((B, 64, 64, 4), float("nan"), device=d)
     L.check(lib.gccvae_sl_bf16(C.byref(geom), L.ptr(g4d), L.ptr(wsl), L.ptr(b5d), L.ACT_SIGMOID, None, L.ptr(xh4), 2, st))
     torch.cuda.synchronize()
+    generic = xh4.clone()
+    assert lib.gccvae_sl_halo_supported(C.byref(geom))
+    w9 = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(geom), 2), dtype=torch.bfloat16, device=d)
+    job = (L.PackJob * 1)(L.PackJob(6, 16, 3, 32, L.ptr(W5d), L.ptr(w9), 0, 0, 0, 0, 0, 0))
+    L.check(lib.gccvae_pack_jobs_bf16(job, 1, st))
+    xh4.fill_(float("nan"))
+    L.check(lib.gccvae_sl_halo_bf16(C.byref(geom), L.ptr(g4d), L.ptr(w9), L.ptr(b5d), L.ACT_SIGMOID, None, L.ptr(xh4), 2, st))
+    torch.cuda.synchronize()
+    assert float((xh4 - generic).abs().max()) < 1e-5, "halo kernel and generic tap-GEMM disagree on conv5t"
     want_logit = O._convT(bf(g4).double(), bf(W5).double(), b5.double(), 2, 1)
     want_xh = torch.sigmoid(want_logit)
     got_xh = xh4.cpu()[..., :3].double()
