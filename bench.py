@@ -244,6 +244,11 @@ def run_ours(args, rank, world, local_rank):
         roof = {"bound": "hbm", "kernel": name, "achieved": nbytes / (ms * 1e-3) / 1e9, "unit": "GB/s",
                 "bytes_per_launch": nbytes, "ms_per_launch": ms, "launches_per_step": n,
                 "share_of_profiled_step": ms * n / tot, "traffic": None}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+            roof["traffic"] = traffic.get(name)
+        except Exception:
+            pass
         top = [{"op": k, "ms": round(v[0], 4), "per_step": v[1], "GB/s": round(v[2] / (v[0] * 1e-3) / 1e9, 1)}
                for k, v in order[:8]]
 

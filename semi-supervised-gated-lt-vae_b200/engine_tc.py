@@ -334,6 +334,7 @@ class EngineTC(Engine):
         """Run `steps` eager supervised+unsupervised train_steps with every tensor-core / data-movement op
         bracketed by CUDA events; returns {op: (mean ms per launch, launches per step, algorithmic bytes)}."""
         graphs, learner.use_graphs = learner.use_graphs, False
+        side, self.side = self.side, None     # serial issue: per-op times are not inflated by stream overlap
         agg = {}
         try:
             for _ in range(steps):
@@ -347,5 +348,6 @@ class EngineTC(Engine):
                     a[1] += 1
         finally:
             self.prof = None
+            self.side = side
             learner.use_graphs = graphs
         return {k: (v[0] / v[1], v[1] / steps, v[2]) for k, v in agg.items()}
