@@ -33,7 +33,7 @@ import torch
 
 METRIC = "training images/sec (sup+unsup ELBO step)"
 UNIT = "images/s"
-WORKLOAD = "Gated CCVAE fixed-inferred gating (gating_matrix_0.2), 64x64x3, 18 attrs, K=100, batch {} per GPU"
+WORKLOAD = "Gated CCVAE {gate} gating (gating_matrix_{frac}), 64x64x3, 18 attrs, K=100, batch {b} per GPU"
 
 
 def parse():
@@ -48,22 +48,28 @@ def parse():
     ap.add_argument("--cpu-baseline-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    # the other BASELINE.json configs (parity / study cases, not the headline line)
+    ap.add_argument("--gate", default="inferred", choices=["one-one", "inferred", "learnable"])
+    ap.add_argument("--frac", default="0.2", help="which data/gating_matrix_<frac>.npy initialises mu")
+    ap.add_argument("--unsup-per-sup", type=int, default=1, help="unsupervised train_steps per supervised one")
     return ap.parse_args()
 
 
-def train_cfg():
-    mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.2.npy"))
-    return dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4,
-                gating_init_temp=0.3, batch_size=1024, init_temp=0.1)
+def train_cfg(gate="inferred", frac="0.2"):
+    mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_{}.npy".format(frac)))
+    base = dict(mu_init=mu, gating_reg=0.2, lr=1e-4, batch_size=1024, init_temp=0.1)
+    if gate == "learnable":
+        return dict(base, gate_type="learnable", gate_subtype=None, gating_init_temp=1.0)
+    return dict(base, gate_type="fixed", gate_subtype=gate, gating_init_temp=0.3)
 
 
 # ---------------------------------------------------------------------------------------------------
 # CPU arm: the oracle in the reference's literal structure (two encoder passes, python K loop)
 # ---------------------------------------------------------------------------------------------------
-def cpu_oracle_rate(batch, steps, warmup):
+def cpu_oracle_rate(batch, steps, warmup, gate="inferred", frac="0.2"):
     import gccvae_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
-    cfg = train_cfg()
+    cfg = train_cfg(gate, frac)
     p = O.init_params(0)
     mu, _ = O.initialise_mu(cfg)
     opt = O.KerasAdam(cfg["lr"])
@@ -84,7 +90,7 @@ def cpu_oracle_rate(batch, steps, warmup):
 def run_reference(args, rank):
     if rank != 0:
         return
-    rate, ms = cpu_oracle_rate(args.ref_batch, max(1, args.steps), max(1, args.warmup))
+    rate, ms = cpu_oracle_rate(args.ref_batch, max(1, args.steps), max(1, args.warmup), args.gate, args.frac)
     cores = os.cpu_count() or 1
     sample = "oracle (PyTorch-CPU restatement of the TF reference), sup+unsup step on batch {} per step".format(
         args.ref_batch)
@@ -92,7 +98,8 @@ def run_reference(args, rank):
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(args.batch), "reference_sample_batch": args.ref_batch},
+        "config": {"workload": WORKLOAD.format(gate=args.gate, frac=args.frac, b=args.batch),
+                   "reference_sample_batch": args.ref_batch},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -163,7 +170,9 @@ def run_ours(args, rank, world, local_rank):
         precision = "bf16" if os.path.exists(os.path.join(ROOT, "semi-supervised-gated-lt-vae_b200",
                                                            "engine_tc.py")) else "fp32"
     B = args.batch
-    cfg = train_cfg()
+    cfg = train_cfg(args.gate, args.frac)
+    U = max(0, args.unsup_per_sup)
+    imgs_per_step = (1 + U) * B
     lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234,
                     graphs=not args.no_graph)
 
@@ -178,8 +187,10 @@ def run_ours(args, rank, world, local_rank):
 
     def step_resident(i):
         j = i % NBUF
-        lrn.train_step(dev_x[j], dev_y[j], True)
-        return lrn.train_step(dev_x[(j + 1) % NBUF], None, False)
+        out = lrn.train_step(dev_x[j], dev_y[j], True)
+        for u in range(U):
+            out = lrn.train_step(dev_x[(j + 1 + u) % NBUF], None, False)
+        return out
 
     def barrier():
         torch.cuda.synchronize()
@@ -212,7 +223,7 @@ def run_ours(args, rank, world, local_rank):
     ms_total, launches = timed(step_resident, args.steps, max(3, args.warmup))
     clocks = sampler.stop() if rank == 0 else None
     ms_step = ms_total / args.steps
-    value = 2 * B * world / (ms_step / 1e3)
+    value = imgs_per_step * world / (ms_step / 1e3)
 
     # ---- e2e: host buffers in, loss out, every step --------------------------------------------------------
     loss_host = torch.zeros(args.steps + 8).pin_memory()
@@ -222,14 +233,15 @@ def run_ours(args, rank, world, local_rank):
         # read of the step's loss into pinned memory (asynchronous; completed inside the timed region by the
         # closing synchronize, so the host never stalls the pipeline)
         j = i % NBUF
-        lrn.train_step(host_x[j], host_y[j], True)
-        loss, _ = lrn.train_step(host_x[(j + 1) % NBUF], None, False)
+        loss, _ = lrn.train_step(host_x[j], host_y[j], True)
+        for u in range(U):
+            loss, _ = lrn.train_step(host_x[(j + 1 + u) % NBUF], None, False)
         loss_host[i % loss_host.numel()].copy_(loss, non_blocking=True)
 
     ms_e2e, _ = timed(step_e2e, args.steps, 3)
     ms_e2e_step = ms_e2e / args.steps
-    e2e_value = 2 * B * world / (ms_e2e_step / 1e3)
-    h2d = 2 * B * 64 * 64 * 3 * 4 + B * 18 * 8
+    e2e_value = imgs_per_step * world / (ms_e2e_step / 1e3)
+    h2d = (1 + U) * B * 64 * 64 * 3 * 4 + B * 18 * 8
     d2h = 4
 
     # ---- per-kernel timing for the roofline of the dominant kernel ---------------------------------------------
@@ -265,8 +277,9 @@ def run_ours(args, rank, world, local_rank):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(3, args.warmup), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "bf16" if precision == "bf16" else "f32", "data": "synthetic",
-        "config": {"workload": WORKLOAD.format(B), "step": "1 supervised + 1 unsupervised train_step "
-                   "(fwd+bwd+allreduce+Adam)", "precision": precision, "noise": "in-kernel Philox4x32-10",
+        "config": {"workload": WORKLOAD.format(gate=args.gate, frac=args.frac, b=B),
+                   "step": "1 supervised + {} unsupervised train_step(s) (fwd+bwd+allreduce+Adam)".format(U),
+                   "precision": precision, "noise": "in-kernel Philox4x32-10",
                    "l2": "ring of 4 input batches (201 MB) + ~1 GB of activations per step exceed the 126 MB L2",
                    "parallelism": "dp{}".format(world)},
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -284,7 +297,7 @@ def run_ours(args, rank, world, local_rank):
         line["roofline"] = roof
         line["top_ops"] = top
     if not args.no_cpu_baseline:
-        rate, ms = cpu_oracle_rate(args.ref_batch, args.cpu_baseline_steps, 1)
+        rate, ms = cpu_oracle_rate(args.ref_batch, args.cpu_baseline_steps, 1, args.gate, args.frac)
         line["cpu_baseline"] = {"value": rate, "unit": UNIT, "cores": os.cpu_count() or 1, "kind": "port",
                                 "sample": "oracle sup+unsup step, batch {}, {} timed steps ({:.0f} ms each)".format(
                                     args.ref_batch, args.cpu_baseline_steps, ms)}
