@@ -114,7 +114,10 @@ int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const
                    const void* mask, void* L, int out_f32, void* stream);
 /* Arms the NEXT gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_gemm_bf16 call of this thread: it additionally does
  * colsum[c % mod] += sum over rows of the values it stores, for channels c < n (mod <= 0: no wrap).  This is the
- * bias gradient of the layer whose pre-activation gradient the dgrad produces, fused into its epilogue. */
+ * bias gradient of the layer whose pre-activation gradient the dgrad produces, fused into its epilogue.
+ * With mod = -1 / -2 it arms the next gccvae_wg_bf16 / gccvae_wg_c4_bf16 / gccvae_gemm_tn_bf16 instead: the
+ * column sums of its S operand (-1: Conv2D / Dense, dout = S) or of the own-pixel taps of its L operand
+ * (-2: Conv2DTranspose, dout = L) are accumulated by the otherwise idle epilogue warps during the main loop. */
 void gccvae_next_launch_colsum(float* colsum, int n, int mod);
 /* dW (fp32, Keras [kh,kw,cl,cs]) += gather(L)^T S; out[c] += column sums.  Accumulating: zero first. */
 int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream);

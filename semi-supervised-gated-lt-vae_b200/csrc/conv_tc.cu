@@ -653,6 +653,10 @@ struct alignas(64) WgParams {
   int tiles_total, tiles_per_cta;
   gccvae_wg_out out;   // destination segments (columns -> tensors); out.m_valid rows are stored
   int stages;
+  // bias gradient fused into the main loop (the four epilogue warps are idle there): column sums of the
+  // S operand (side 1: Conv2D / Dense, dout = S) or of the L operand's own-pixel taps (side 2: Conv2DTranspose)
+  float* colsum;
+  int colsum_side, colsum_n;
 };
 
 __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
@@ -667,10 +671,24 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
   uint64_t* empty = full + p.stages;
   uint64_t* tmem_full = empty + p.stages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+  float* s_red = reinterpret_cast<float*>(tmem_slot + 4);   // [4 slabs][64 channels] column-sum staging
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
   const int mtile = blockIdx.y;
+  // which smem slabs of this CTA feed the fused bias gradient (bit s = slab s)
+  uint32_t cs_mask = 0;
+  if (p.colsum != nullptr) {
+    if (p.colsum_side == 1) {
+      if (mtile == 0) cs_mask = (1u << p.b_loads) - 1u;
+    } else {
+      for (int bl = 0; bl < p.blocks_per_mtile; ++bl) {
+        const int t = (mtile * p.blocks_per_mtile + bl) / p.blocks_per_tap;
+        const int kh = t >> 2, kw = t & 3;   // k4/s2/p1: taps (1..2, 1..2) visit every L pixel exactly once
+        if (t < p.taps && (kh == 1 || kh == 2) && (kw == 1 || kw == 2)) cs_mask |= 1u << bl;
+      }
+    }
+  }
   const int tile_beg = blockIdx.x * p.tiles_per_cta;
   int tile_end = tile_beg + p.tiles_per_cta;
   if (tile_end > p.tiles_total) tile_end = p.tiles_total;
@@ -683,7 +701,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], cs_mask ? 5 : 1);   // MMA commit (+ the four column-sum warps)
     }
     mbar_init(tmem_full, 1);
     fence_mbar_init();
@@ -743,6 +761,56 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     } else {
+      if (cs_mask) {
+        // ---- fused bias gradient: column sums of the staged operand tiles, straight from shared memory ----
+        const bool sideS = p.colsum_side == 1;
+        const int kc = sideS ? p.kcB : p.kcA, rowb = kc * 2, slab = sideS ? b_slab : a_slab;
+        const uint32_t swmask = (rowb >= 128) ? 7u : ((rowb >= 64) ? 3u : 1u);
+        const int t = threadIdx.x - 64, pairs = kc >> 1, tpp = 128 / pairs;
+        const int pair = t % pairs, rg = t / pairs;
+        float acc[4][2];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) acc[i][0] = acc[i][1] = 0.0f;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < n_tiles; ++it) {
+          mbar_wait(&full[stage], ph);
+          const uint8_t* tile0 = (sideS ? sB + stage * b_bytes : sA + stage * a_bytes);
+#pragma unroll
+          for (int sl = 0; sl < 4; ++sl) {
+            if (!((cs_mask >> sl) & 1u)) continue;
+            const uint8_t* sbase = tile0 + sl * slab;
+            float a0 = 0.0f, a1 = 0.0f;
+            for (int r = rg; r < 128; r += tpp) {
+              uint32_t off = (uint32_t)(r * rowb + pair * 4);
+              off ^= ((off >> 7) & swmask) << 4;
+              const __nv_bfloat162 v = *reinterpret_cast<const __nv_bfloat162*>(sbase + off);
+              a0 += __low2float(v);
+              a1 += __high2float(v);
+            }
+            acc[sl][0] += a0;
+            acc[sl][1] += a1;
+          }
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
+        for (int i = t; i < 256; i += 128) s_red[i] = 0.0f;
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl)
+          if ((cs_mask >> sl) & 1u) {
+            atomicAdd(&s_red[sl * 64 + pair * 2], acc[sl][0]);
+            atomicAdd(&s_red[sl * 64 + pair * 2 + 1], acc[sl][1]);
+          }
+        asm volatile("bar.sync 1, 128;" ::: "memory");
+        for (int i = t; i < 256; i += 128) {
+          const int sl = i >> 6, c = i & 63;
+          if (!((cs_mask >> sl) & 1u) || c >= kc) continue;
+          const int ch = sideS ? sl * kc + c : ((mtile * p.blocks_per_mtile + sl) % p.blocks_per_tap) * kc + c;
+          if (ch < p.colsum_n && s_red[i] != 0.0f) atomicAdd(p.colsum + ch, s_red[i]);
+        }
+      }
       const int q = warp & 3;
       const int m = mtile * 128 + q * 32 + lane;
       mbar_wait(tmem_full, 0);
@@ -1046,6 +1114,9 @@ __global__ void cast_f32_kernel(const __nv_bfloat16* __restrict__ in, long long 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
+static thread_local float* g_colsum = nullptr;
+static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                   CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -1167,8 +1238,6 @@ static cudaError_t launch_pdl(void (*kernel)(const Params), dim3 grid, int threa
   return cudaLaunchKernelEx(&cfg, kernel, p);
 }
 
-static thread_local float* g_colsum = nullptr;
-static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
 static long long* g_timeline = nullptr;
 
 static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t st, const char* name) {
@@ -1367,6 +1436,13 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, cons
   if ((rc = encode_act_map(&p.tmB, S, g->batch, g->HS, g->WS, CS, p.kcB, bw, bh, bn, 1))) return rc;
   p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = g->WS / bw; p.tiles_h = g->HS / bh;
   p.N = CS; p.out = *out;
+  if (g_colsum != nullptr && g_colsum_mod < 0) {   // armed by gccvae_next_launch_colsum(ptr, n, -1 | -2)
+    p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_side = -g_colsum_mod;
+    g_colsum = nullptr;
+    GCC_REQUIRE(p.colsum_side == 1 || (p.colsum_side == 2 && !dense && !c4_rows),
+                "wg_bf16: fused bias gradient side %d unsupported here", p.colsum_side);
+    GCC_REQUIRE(p.colsum_n > 0 && p.colsum_n <= (p.colsum_side == 1 ? CS : CL), "wg_bf16: colsum_n");
+  }
   const int groups = (g->batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
   const int mtiles = (taps * p.blocks_per_tap + p.blocks_per_mtile - 1) / p.blocks_per_mtile;
@@ -1376,12 +1452,12 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, cons
   p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
-  int stages = (190 * 1024) / stage_bytes;
+  int stages = (188 * 1024) / stage_bytes;
   if (stages > 4) stages = 4;
   if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));

@@ -68,13 +68,14 @@ class EngineTC(Engine):
         self.wp["conv1t.ls"] = z16(64, 2048)
         self._jobs = None
         import os
-        # fusing the bias-gradient column sums into the dgrad epilogues costs more (registers -> occupancy) than the
-        # separate bandwidth-bound pass saves: measured 2.57 ms vs 2.37 ms per step on B200, so it is off by default
-        self.fused_bias_grad = os.environ.get("GCCVAE_FUSED_BIAS", "0") != "0"
+        # bias gradients: a separate column-sum pass per layer by default.  Both fused variants were measured slower
+        # on B200: in the dgrad epilogue (registers -> occupancy: 2.57 vs 2.37 ms per step) and in the wgrad main loop
+        # (GCCVAE_BIAS_IN_WGRAD=1: stage release waits for the sums: 2.11 vs 2.09 ms).
         # weight gradients are off the critical path (only Adam needs them): they run on a side stream, concurrently
         # with the dgrad chain; under CUDA-graph capture this becomes a parallel branch of the graph
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("GCCVAE_SIDE_STREAM", "1") != "0" else None
-        self._pending_bias = None
+        self.bias_in_wgrad = os.environ.get("GCCVAE_BIAS_IN_WGRAD", "0") != "0"
+        self._deferred_bias = []
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
 
     # ---- packed weights ---------------------------------------------------------------------------------
@@ -145,8 +146,6 @@ class EngineTC(Engine):
         record (duration, bytes of the tensors it reads/writes = its algorithmic HBM traffic)."""
         if self.prof is None:
             _lib.check(rc_fn(), what)
-            if self._pending_bias is not None and what.endswith("dgrad"):
-                self._flush_bias_grad(tensors[-1])
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -185,33 +184,37 @@ class EngineTC(Engine):
         self._run(name + " bgrad", (dout,), lambda: self.lib.gccvae_colsum_bf16(
             ptr(dout), rows, cols, n_valid, ptr(self.store.g(name + ".b")), _stream()))
 
-    def _side(self, fn):
-        """run fn (weight-gradient launches) on the side stream, after everything issued so far on the main one."""
-        if self.side is None:
+    def _flush_deferred_bias(self):
+        for dout, name, n in self._deferred_bias:
+            cols = dout.shape[-1]
+            self._bias_grad16(dout, name, cols=cols, n_valid=n if n < cols else 0)
+        self._deferred_bias = []
+
+    def _side(self, fn, small=False):
+        """run fn (weight-gradient launches) on the side stream, after everything issued so far on the main one.
+        (`small=True` keeps a launch on the main stream; measured slower for every candidate, so it is unused.)"""
+        if self.side is None or small:
             fn()
+            self._flush_deferred_bias()
             return
         self.side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(self.side):
             fn()
+        self._flush_deferred_bias()      # (main stream) column-sum passes requested by fn's _arm_wgrad_bias
 
     def join_side(self):
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
 
-    def _arm_bias_grad(self, name, n, mod=0):
-        """the next dgrad launch also accumulates the bias gradient of layer `name` in its epilogue."""
-        if self.fused_bias_grad:
-            self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, mod)
-        else:
-            self._pending_bias = (name, n, mod)
-
-    def _flush_bias_grad(self, dx):
-        """un-fused variant (GCCVAE_FUSED_BIAS=0): a separate column-sum pass over the dgrad output."""
-        if self._pending_bias is not None:
-            name, n, mod = self._pending_bias
-            self._pending_bias = None
-            cols = mod if mod else dx.shape[-1]
-            self._bias_grad16(dx, name, cols=cols, n_valid=n if n < cols else 0)
+    def _arm_wgrad_bias(self, name, n, side, dout=None):
+        """bias gradient of `name`.  Default: a separate bandwidth-bound column-sum pass over dout on the main
+        stream.  GCCVAE_BIAS_IN_WGRAD=1: the next wgrad launch produces it from its staged operand tiles (side 1:
+        S operand, 2: L operand) with its idle epilogue warps - one pass less over dout, but measured 1 % slower
+        end to end on B200 (the stage release waits for the column sums), so it is off by default."""
+        if self.bias_in_wgrad:
+            self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, -side)
+        elif dout is not None:
+            self._deferred_bias.append((dout, name, n))
 
     def zero_grads(self):
         self.store.grad.zero_()   # the tensor-core wgrad / bias-grad kernels accumulate (split-K red.global)
@@ -275,7 +278,6 @@ class EngineTC(Engine):
         self._side(lambda: self._run("dec.conv5t wgrad", (b["G64"], g4), lambda: lib.gccvae_wg_c4_bf16(
             B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
         g = _dense64_geom(B * 1024, 32)
-        self._arm_bias_grad("dec.conv4t", 32)
         self._run("dec.conv5t dgrad", (b["G64"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_ls_bf16(
             C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
             ptr(b["dec.conv4t.dout"]), 0, st))
@@ -284,18 +286,23 @@ class EngineTC(Engine):
             geom = make_geom(_DEC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            self._side(lambda: self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
-                C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), _stream())))
-            self._arm_bias_grad(pn, xin.shape[-1])
+            def wg(name=name, geom=geom, dout=dout, xin=xin):
+                self._arm_wgrad_bias(name, dout.shape[-1], 2, dout)   # dout is the L operand of a transposed conv
+                self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
+                    C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), _stream()))
+            self._side(wg)
             self._run(name + " dgrad", (dout, self.wp[name + ".ls"], xin, dxin), lambda: lib.gccvae_ls_bf16(
                 C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
                                          "dec.conv1t wgrad"))
-        self._arm_bias_grad("dec.fc1", 45)
+        self._bias_grad16(dg1, "dec.conv1t", cols=128)
         self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "dec.conv1t dgrad")
-        self._side(lambda: self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "dec.fc1 wgrad"))
+        def wg_fc1():
+            self._arm_wgrad_bias("dec.fc1", 45, 1, dg0)
+            self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "dec.fc1 wgrad")
+        self._side(wg_fc1)
         if want_dz:
             self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "dec.fc1 dgrad")
         return b["dz64"][:, :45]
@@ -308,7 +315,6 @@ class EngineTC(Engine):
         self._side(lambda: self._gemm_tn(B, 256, 96, h5, dpre,
                                          [(0, 45, 45, g_("enc.locs.w")), (48, 45, 45, g_("enc.std.w"))], 256,
                                          "enc.heads wgrad"))
-        self._arm_bias_grad("enc.conv5", 256)
         self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "enc.heads dgrad")
         prev_of = {"enc.conv5": "enc.conv4", "enc.conv4": "enc.conv3", "enc.conv3": "enc.conv2",
                    "enc.conv2": "enc.conv1"}
@@ -316,17 +322,18 @@ class EngineTC(Engine):
             geom = make_geom(_ENC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            self._side(lambda: self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
-                C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream())))
-            # dxin = gradient of the previous layer's pre-activation: its column sums are that layer's bias grad
-            if name == "enc.conv5":
-                self._arm_bias_grad(pn, 2048, 128)       # dh4 is [B,(kh,kw,128)]: channel = column % 128
-            else:
-                self._arm_bias_grad(pn, xin.shape[-1])
+            def wg(name=name, geom=geom, dout=dout, xin=xin):
+                self._arm_wgrad_bias(name, dout.shape[-1], 1, dout)   # dout is the S operand of a conv
+                self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
+                    C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
+            self._side(wg)
             self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad")
         dh1 = b["enc.conv1.dout"]
-        self._side(lambda: self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
-            B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream())))
+        def wg1():
+            self._arm_wgrad_bias("enc.conv1", 32, 1, dh1)
+            self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
+                B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
+        self._side(wg1)
         self.join_side()
 
     # ---- per-op device timing (bench.py roofline) -------------------------------------------------------------
