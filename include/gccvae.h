@@ -98,7 +98,8 @@ size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
 /* batched form of the packing entry points below: ONE launch for all layers of a step.
  * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below);
  * 4/5: strided copy into a zero-padded bf16 / fp32 operand (the 45-wide dense layers padded to 64 / 96);
- * 6: "sl9" packing of the halo kernel */
+ * 6: "sl9" packing of the halo kernel; 7/8: x2 (space-to-depth) packing of a 3-channel k4/s2/p1 kernel,
+ * 7 = [CS][(a,b)][(dy,dx,c4)] (gccvae_tap4_ls_bf16), 8 = [(dy,dx,c4)][(a,b)][CS] (gccvae_convt_recon_bf16) */
 typedef struct {
   int kind, taps, CL, CS;
   const float* W;
@@ -142,6 +143,21 @@ int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, cons
                              void* G64, float* db, void* stream);
 int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
 int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
+/* Space-to-depth ("x2") form of the 3-channel end layers (conv1 = networks.py:11,22; conv5t = :49,58; likelihood =
+ * utils.py:101-105).  X2[n,i,j,(dy,dx,c4)] = x[n,2i-1+dy,2j-1+dx,c] (bf16 [B,33,33,16], zero outside the image):
+ * Conv2D(k4,s2,p1) over the image is a 2x2-tap stride-1 GEMM over the blocks and Conv2DTranspose(k4,s2,same)
+ * produces its output directly in block form.  x may be uint8 (0..255): it is divided by 255 on the device
+ * exactly as utils_data.py:57-59 does on the host. */
+int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* stream);
+int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, const void* Wp, int CS, const float* bias,
+                        int act, const void* mask, void* out, void* stream);
+/* same contraction as gccvae_tap4_ls_bf16 for the 33x33x16 blocks of a 64x64x3 image, with the im2col tile built
+ * by producer warps (TMA is row-rate bound on 32-byte rows): conv1 forward and conv5t dgrad.  CS in {32, 64}. */
+int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, int CS, const float* bias, int act, const void* mask,
+                       void* out, void* stream);
+int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream);
+int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp8, const float* bias, const void* x, int x_u8,
+                            const float* coef, float* log_pxz, void* D2, float* xhat, float* db, void* stream);
 /* S -> L "halo" kernel for 16x16 / 32x32 S planes with 32 or 64 channels and C_L <= 64: all four output-parity
  * phases per CTA from three column-shifted halo boxes (3.6x less L2 traffic than gccvae_sl_bf16), one MMA per
  * shifted view with N = 4*C_L.  Weights packed "sl9" = [9 views][4 phases][C_L padded to 16][C_S]
@@ -155,6 +171,8 @@ int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* strea
  * at its pipeline events: [item][0 slot free,1 TMA issued,2 TMEM free,3 operands landed,4 accum ready,
  * 5 accum read,6 stored]. */
 void gccvae_debug_set_timeline(long long* dev_buf);
+/* debug: a 1-thread kernel that stores %globaltimer (ns) into buf[idx] when the stream reaches it */
+int gccvae_debug_mark(long long* buf, int idx, void* stream);
 
 /* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
 int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,

@@ -1,0 +1,38 @@
+"""In-graph timeline of one supervised train_step: GCCVAE_MARKERS=1 (marker after every op) or 2 (segments).
+Marker kernels carry no PDL attribute, so they serialise the stream: compare segment sums, not absolute totals."""
+import os
+import sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("GCCVAE_MARKERS", "1")
+import numpy as np
+import torch
+import gccvae_b200 as G
+
+B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.2.npy"))
+cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=0.3,
+           batch_size=B, init_temp=0.1)
+lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True)
+x = torch.rand(B, 64, 64, 3, device="cuda")
+y = (torch.rand(B, 18, device="cuda") < 0.5).long()
+for sup in (True,):
+    for _ in range(5):
+        lrn.train_step(x, y if sup else None, sup)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(20):
+        lrn.train_step(x, y if sup else None, sup)
+    e1.record()
+    torch.cuda.synchronize()
+    print("supervised=%s: %.1f us per train_step (with markers)" % (sup, e0.elapsed_time(e1) * 50))
+    marks = lrn.engine.marks
+    t = lrn.engine.mark_buf.cpu()[:len(marks)].double() / 1e3
+    t0 = t[0]
+    last = {"main": t0, "side": None, "side2": None}
+    for (what, lane), ti in zip(marks, t):
+        prev = last[lane]
+        d = (ti - prev) if prev is not None else float("nan")
+        print("%-6s %9.1f  +%7.1f  %s" % (lane, ti - t0, d, what))
+        last[lane] = ti

@@ -93,7 +93,13 @@ SIGNATURES = {
     "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
     "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
     "gccvae_next_launch_colsum": (None, [_P, _I, _I]),
+    "gccvae_prep_x2_bf16": (_I, [_P, _I, _I, _P, _P]),
+    "gccvae_tap4_ls_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "gccvae_c3conv_bf16": (_I, [_I, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "gccvae_tap4_wg_bf16": (_I, [_I, _P, _P, _I, _P, _P]),
+    "gccvae_convt_recon_bf16": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
     "gccvae_debug_set_timeline": (None, [_P]),
+    "gccvae_debug_mark": (_I, [_P, _I, _P]),
     "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),
     "gccvae_gate_fwd": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),

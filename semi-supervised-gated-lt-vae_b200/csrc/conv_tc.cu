@@ -46,6 +46,7 @@ struct alignas(64) TapGemmParams {
   int oy0[4], ox0[4];
   int batch;
   int stages;
+  int tps;      // k-blocks (tap, chunk) per pipeline stage: one barrier round trip feeds tps * KC/16 MMAs
   int n_slabs;  // slabs of N output channels (B rows / output channels offset by slab*N)
   int phases;
   int total_items;  // tiles * n_slabs * phases, spread contiguously over the persistent CTAs
@@ -104,9 +105,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
   const int a_bytes = 128 * p.KC * 2, b_bytes = p.N * p.KC * 2;
   const int a_stride = (a_bytes + 1023) & ~1023, b_stride = (b_bytes + 1023) & ~1023;
+  const int stage_stride = p.tps * (a_stride + b_stride);   // [tps A blocks][tps B blocks]
   uint8_t* sA = smem;
-  uint8_t* sB = smem + p.stages * a_stride;
-  uint64_t* full = reinterpret_cast<uint64_t*>(sB + p.stages * b_stride);
+  uint8_t* sB = smem + p.tps * a_stride;
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + p.stages * stage_stride);
   uint64_t* empty = full + p.stages;
   uint64_t* tfull = empty + p.stages;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty = tfull + 2;         // [2] accumulator stage drained by the epilogue
@@ -146,59 +148,101 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are needed from here on
+  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.timeline[40 * 8 + 2 * blockIdx.x] = (long long)gt;
+  }
 
   const int k_iters = p.num_taps * p.chunks;
   if (warp == 0) {
-    // ===== TMA producer =====
+    // ===== TMA producer: one stage = tps consecutive k-blocks (tap, chunk) =====
     if (elect_one()) {
       int stage = 0;
       uint32_t ph = 0;
+      long long prod_wait = 0;
+      const long long tp0 = clock64();
+      const uint32_t stage_tx = (uint32_t)(p.tps * (a_bytes + b_bytes));
       for (int item = item_beg; item < item_end; ++item) {
         const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
         const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
         const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
-        for (int it = 0; it < k_iters; ++it) {
-          const int t = it / p.chunks, c = it % p.chunks;
+        const int aw = p.a_scale * w0, ah = p.a_scale * h0, brow = p.b_row0[phase_id] + slab * p.N;
+        int t = 0, c = 0;
+        for (int it = 0; it < k_iters; it += p.tps) {
+          const long long tw0 = p.timeline ? clock64() : 0;
           mbar_wait(&empty[stage], ph ^ 1);
+          if (p.timeline) prod_wait += clock64() - tw0;
           if (it == 0) TL(item - item_beg, 0);
-          mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
-          tma_load_4d(sA + stage * a_stride, &p.tmA, &full[stage], c * p.KC, p.a_scale * w0 + p.a_dw[phase_id][t],
-                      p.a_scale * h0 + p.a_dh[phase_id][t], n0);
-          tma_load_2d(sB + stage * b_stride, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC,
-                      p.b_row0[phase_id] + slab * p.N);
-          if (it == k_iters - 1) TL(item - item_beg, 1);
+          mbar_expect_tx(&full[stage], stage_tx);
+          uint8_t* a_dst = sA + stage * stage_stride;
+          uint8_t* b_dst = sB + stage * stage_stride;
+          for (int j = 0; j < p.tps; ++j) {
+            tma_load_4d(a_dst, &p.tmA, &full[stage], c * p.KC, aw + p.a_dw[phase_id][t], ah + p.a_dh[phase_id][t], n0);
+            tma_load_2d(b_dst, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, brow);
+            a_dst += a_stride;
+            b_dst += b_stride;
+            if (++c == p.chunks) { c = 0; ++t; }
+          }
+          if (it + p.tps >= k_iters) TL(item - item_beg, 1);
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
+      if (p.timeline != nullptr && blockIdx.x == 0) {
+        p.timeline[32 * 8 + 0] = prod_wait;
+        p.timeline[32 * 8 + 1] = clock64() - tp0;
+      }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
-    const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;  // 8 rows of the swizzle atom
-    int stage = 0;
-    uint32_t ph = 0;
-    for (int item = item_beg; item < item_end; ++item) {
-      const int li = item - item_beg, as = li & 1;
-      mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
-      tc_fence_after();
-      if (lane == 0) TL(li, 2);
-      const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
-      for (int it = 0; it < k_iters; ++it) {
-        mbar_wait(&full[stage], ph);
+    // ===== MMA issuer: ONE thread runs the whole loop.  Descriptors are built once; per MMA only the 14-bit
+    // start-address field advances (a 64-bit add), so the issue cost is a handful of instructions =====
+    if (lane == 0) {
+      const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
+      const uint32_t sbo = 8u * (uint32_t)p.KC * 2u;  // 8 rows of the swizzle atom
+      const uint64_t dproto = smem_desc(0, 16, sbo, (uint32_t)p.swz);
+      const uint64_t adesc0 = dproto + (uint64_t)(smem_u32(sA) >> 4), bdesc0 = dproto + (uint64_t)(smem_u32(sB) >> 4);
+      const uint32_t a_step = (uint32_t)a_stride >> 4, b_step = (uint32_t)b_stride >> 4;
+      const uint32_t st_step = (uint32_t)stage_stride >> 4;
+      const int kk_n = p.KC / 16;
+      int stage = 0;
+      uint32_t ph = 0;
+      long long mma_wait = 0, acc_wait = 0;
+      const long long tm0 = clock64();
+      for (int item = item_beg; item < item_end; ++item) {
+        const int li = item - item_beg, as = li & 1;
+        const long long ta0 = p.timeline ? clock64() : 0;
+        mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        if (p.timeline) acc_wait += clock64() - ta0;
         tc_fence_after();
-        if (lane == 0 && it == k_iters - 1) TL(li, 3);
-        if (elect_one()) {
-          const uint32_t a0 = smem_u32(sA + stage * a_stride), b0 = smem_u32(sB + stage * b_stride);
-          for (int kk = 0; kk < p.KC / 16; ++kk) {
-            const uint64_t ad = smem_desc(a0 + kk * 32, 16, sbo, (uint32_t)p.swz);
-            const uint64_t bd = smem_desc(b0 + kk * 32, 16, sbo, (uint32_t)p.swz);
-            umma_bf16(tacc, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
+        TL(li, 2);
+        const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
+        for (int it = 0; it < k_iters; it += p.tps) {
+          const long long tw0 = p.timeline ? clock64() : 0;
+          mbar_wait(&full[stage], ph);
+          if (p.timeline) mma_wait += clock64() - tw0;
+          tc_fence_after();
+          if (it + p.tps >= k_iters) TL(li, 3);
+          uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * st_step);
+          uint64_t bd = bdesc0 + (uint64_t)((uint32_t)stage * st_step);
+          umma_bf16(tacc, ad, bd, idesc, it > 0 ? 1u : 0u);
+          for (int kk = 1; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
+          for (int j = 1; j < p.tps; ++j) {
+            ad += a_step;
+            bd += b_step;
+            for (int kk = 0; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
           }
           umma_commit(&empty[stage]);
-          if (it == k_iters - 1) umma_commit(&tfull[as]);
+          if (it + p.tps >= k_iters) umma_commit(&tfull[as]);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+      if (p.timeline != nullptr && blockIdx.x == 0) {
+        p.timeline[32 * 8 + 2] = mma_wait;
+        p.timeline[32 * 8 + 3] = acc_wait;
+        p.timeline[32 * 8 + 4] = clock64() - tm0;
+        p.timeline[32 * 8 + 5] = (long long)(item_end - item_beg) * (k_iters / p.tps);
+        p.timeline[32 * 8 + 6] = p.stages;
+        p.timeline[32 * 8 + 7] = gridDim.x;
       }
     }
   } else {
@@ -364,6 +408,11 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     tc_fence_before();
   }
   __syncthreads();
+  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.timeline[40 * 8 + 2 * blockIdx.x + 1] = (long long)gt;
+  }
   if (COLSUM) {
     const int ncol = p.colsum_mod < p.colsum_n ? p.colsum_mod : p.colsum_n;
     for (int i = threadIdx.x; i < ncol; i += TG_THREADS)
@@ -398,6 +447,7 @@ struct alignas(64) SlHaloParams {
   int OH, OW, OC, batch, total_tiles, stages;
   float* colsum;
   int colsum_n;
+  long long* timeline;  // debug: block 0 records clock64() at pipeline events [tile][8] (NULL = off)
 };
 constexpr int HALO_THREADS = 320;
 
@@ -465,44 +515,52 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
         mbar_wait(&empty[stage], ph ^ 1);
+        TL(tile - tile_beg, 0);
         mbar_expect_tx(&full[stage], (uint32_t)a_stage);
         for (int v = 0; v < 3; ++v)
           tma_load_4d(sA + stage * a_stage + v * avb, &p.tmA, &full[stage], 0, v - 1, h0 - 1, n);
+        TL(tile - tile_beg, 1);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
+    // ===== MMA issuer (one thread) =====
     // One MMA covers all four output-parity phases: N = 4*N_phase, the B block of a view holds each phase's
     // weights for the tap that reads this view (zeros where a phase does not use it).  9 views x C/16 MMAs
-    // instead of 16 (phase,tap) x C/16: the MMA pipe is bound by re-reading the 128-row A operand from shared
-    // memory, so fewer, wider instructions are ~1.8x faster.
-    const uint32_t idesc = instr_desc_bf16(128, 4 * p.N, 0, 0);
-    const uint32_t sbo = 8u * (uint32_t)rowb;
-    int stage = 0;
-    uint32_t ph = 0;
-    if (tile_beg < tile_end) mbar_wait(bfull, 0);
-    for (int tile = tile_beg; tile < tile_end; ++tile) {
-      const int li = tile - tile_beg, as = li & 1;
-      mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
-      mbar_wait(&full[stage], ph);
-      tc_fence_after();
-      if (elect_one()) {
-        const uint32_t a0 = smem_u32(sA + stage * a_stage), b0 = smem_u32(sB);
+    // instead of 16 (phase,tap) x C/16.  Descriptors are built once; per MMA only the address field advances.
+    if (lane == 0 && tile_beg < tile_end) {
+      const uint32_t idesc = instr_desc_bf16(128, 4 * p.N, 0, 0);
+      const uint32_t sbo = 8u * (uint32_t)rowb;
+      const uint64_t dproto = smem_desc(0, 16, sbo, (uint32_t)p.swz);
+      const uint64_t bdesc0 = dproto + (uint64_t)(smem_u32(sB) >> 4);
+      const uint64_t adesc0 = dproto + (uint64_t)(smem_u32(sA) >> 4);
+      const uint32_t a_stage16 = (uint32_t)a_stage >> 4, avb16 = (uint32_t)avb >> 4, row16 = (uint32_t)(p.BW * rowb) >> 4;
+      const uint32_t bblk16 = (uint32_t)bblk >> 4;
+      const int kk_n = p.C / 16;
+      int stage = 0;
+      uint32_t ph = 0;
+      mbar_wait(bfull, 0);
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int li = tile - tile_beg, as = li & 1;
+        mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        TL(li, 2);
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        TL(li, 3);
+        const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * a_stage16);
         const uint32_t tacc = tmem_base + (uint32_t)as * 4u * (uint32_t)p.N;
+#pragma unroll
         for (int view = 0; view < 9; ++view) {
-          const int dh = view / 3 - 1, dw = view % 3 - 1;
-          const uint32_t aaddr = a0 + (uint32_t)((dw + 1) * avb + (dh + 1) * p.BW * rowb);
-          const uint32_t baddr = b0 + (uint32_t)(view * bblk);
-          for (int kk = 0; kk < p.C / 16; ++kk)
-            umma_bf16(tacc, smem_desc(aaddr + kk * 32, 16, sbo, (uint32_t)p.swz),
-                      smem_desc(baddr + kk * 32, 16, sbo, (uint32_t)p.swz), idesc, (view > 0 || kk > 0) ? 1u : 0u);
+          const uint64_t ad = a_st + (uint64_t)((uint32_t)(view % 3) * avb16 + (uint32_t)(view / 3) * row16);
+          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)view * bblk16);
+          for (int kk = 0; kk < kk_n; ++kk)
+            umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, (view > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
+        TL(li, 7);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
-      __syncwarp();
-      if (++stage == p.stages) { stage = 0; ph ^= 1; }
     }
   } else {
     // ===== epilogue: 8 warps; warp pair (q, q+4) shares TMEM lane quadrant q, each takes 2 phases =====
@@ -536,6 +594,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
       }
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
       tc_fence_after();
+      if (threadIdx.x == 64) TL(li, 4);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int phase = half * 2 + j;
@@ -547,6 +606,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
           if (j == 1 && c0 + 16 >= p.N) {  // this warp has read both of its accumulators
             tc_fence_before();
             if (lane == 0) mbar_arrive(&tempty[as]);
+            if (threadIdx.x == 64) TL(li, 5);
           }
           if (c0 >= p.n_store) continue;
           float v[16];
@@ -617,6 +677,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
           }
         }
       }
+      if (threadIdx.x == 64) TL(li, 6);
     }
     if constexpr (COLSUM) {
 #pragma unroll
@@ -740,25 +801,26 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         }
       }
     } else if (warp == 1) {
-      const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);
-      const uint32_t rowA = (uint32_t)p.kcA * 2u, rowB = (uint32_t)p.kcB * 2u;
-      int stage = 0;
-      uint32_t ph = 0;
-      for (int it = 0; it < n_tiles; ++it) {
-        mbar_wait(&full[stage], ph);
-        tc_fence_after();
-        if (elect_one()) {
-          const uint32_t a0 = smem_u32(sA + stage * a_bytes), b0 = smem_u32(sB + stage * b_bytes);
-          for (int kk = 0; kk < 8; ++kk) {  // 16 pixels per MMA
-            const uint64_t ad = smem_desc(a0 + kk * 16 * rowA, (uint32_t)a_slab, 8 * rowA, (uint32_t)p.swzA);
-            const uint64_t bd = smem_desc(b0 + kk * 16 * rowB, (uint32_t)b_slab, 8 * rowB, (uint32_t)p.swzB);
-            umma_bf16(tmem_base, ad, bd, idesc, (it > 0 || kk > 0) ? 1u : 0u);
-          }
+      if (lane == 0) {   // one thread issues; descriptors built once, only the address field advances
+        const uint32_t idesc = instr_desc_bf16(128, p.N, 1, 1);
+        const uint32_t rowA = (uint32_t)p.kcA * 2u, rowB = (uint32_t)p.kcB * 2u;
+        const uint64_t ad0 = smem_desc(smem_u32(sA), (uint32_t)a_slab, 8 * rowA, (uint32_t)p.swzA);
+        const uint64_t bd0 = smem_desc(smem_u32(sB), (uint32_t)b_slab, 8 * rowB, (uint32_t)p.swzB);
+        const uint32_t a16 = (uint32_t)a_bytes >> 4, b16 = (uint32_t)b_bytes >> 4;
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < n_tiles; ++it) {
+          mbar_wait(&full[stage], ph);
+          tc_fence_after();
+          const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a16), bd = bd0 + (uint64_t)((uint32_t)stage * b16);
+#pragma unroll
+          for (int kk = 0; kk < 8; ++kk)   // 16 pixels per MMA
+            umma_bf16(tmem_base, ad + (uint64_t)(kk * rowA), bd + (uint64_t)(kk * rowB), idesc,
+                      (it > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (it == n_tiles - 1) umma_commit(tmem_full);
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
-        __syncwarp();
-        if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     } else {
       if (cs_mask) {
@@ -819,7 +881,10 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
-        const int mrow = p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m;
+        // c4_rows 1: rows are (tap16, c4) -> (tap16, c3);  2: x2 rows (a, b, dy, dx, c4) -> ((2a+dy)*4 + 2b+dx, c3)
+        const int mrow = p.c4_rows == 2
+                             ? ((2 * (m >> 5) + ((m >> 3) & 1)) * 4 + 2 * ((m >> 4) & 1) + ((m >> 2) & 1)) * 3 + (m & 3)
+                             : (p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m);
         if (m < p.out.m_valid && !(p.c4_rows && (m & 3) == 3)) {
 #pragma unroll
           for (int sg = 0; sg < 2; ++sg) {
@@ -986,7 +1051,7 @@ __global__ void pack_c4_kernel(const float* __restrict__ W, int CS, __nv_bfloat1
 
 // all weight repacking of one step in ONE launch: blockIdx.y = job
 struct PackJobs {
-  gccvae_pack_job j[32];
+  gccvae_pack_job j[48];
 };
 __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ PackJobs jobs) {
   pdl_launch_dependents();
@@ -1033,6 +1098,25 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
       }
       out[i] = __float2bfloat16(v);
     }
+  } else if (jb.kind == 7 || jb.kind == 8) {
+    // x2 (space-to-depth) packing of a 3-channel k4/s2/p1 kernel W[kh,kw,3,CS]:
+    //  kind 7: out[cs][(a,b)][(dy,dx,c4)]   (B operand of the 4-tap L->S GEMM: conv1 forward, conv5t dgrad)
+    //  kind 8: out[(dy,dx,c4)][(a,b)][cs]   (B operand of the fused conv5t forward), kh = 2a+dy, kw = 2b+dx
+    const long long n = (long long)CS * 64;
+    for (long long i = i0; i < n; i += stride) {
+      int cs, a, b, dy, dx, c;
+      if (jb.kind == 7) {
+        cs = (int)(i / 64);
+        const int k = (int)(i % 64);
+        a = k >> 5; b = (k >> 4) & 1; dy = (k >> 3) & 1; dx = (k >> 2) & 1; c = k & 3;
+      } else {
+        const int row = (int)(i / (4 * CS)), k = (int)(i % (4 * CS));
+        dy = row >> 3; dx = (row >> 2) & 1; c = row & 3;
+        a = k / (2 * CS); b = (k / CS) & 1; cs = k % CS;
+      }
+      const int kh = 2 * a + dy, kw = 2 * b + dx;
+      out[i] = __float2bfloat16(c < 3 ? W[(size_t)((kh * 4 + kw) * 3 + c) * CS + cs] : 0.0f);
+    }
   } else if (jb.kind == 4 || jb.kind == 5) {
     // strided copy into a zero-padded operand: out[(row_off + r) * ld_out + col_off + k] = W[r*sr + k*sk]
     // (kind 4: bf16 destination, kind 5: fp32 destination); taps = R, CL = K, CS unused
@@ -1051,6 +1135,413 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
       const int cs = (int)(i / 64), k = (int)(i % 64), t = k >> 2, c = k & 3;
       out[i] = __float2bfloat16(c < 3 ? W[(size_t)(t * 3 + c) * CS + cs] : 0.0f);
     }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Space-to-depth ("x2") form of the two 3-channel end layers.  A 64x64x3 image is stored as 33x33 blocks of
+// 2x2 pixels x 4 channels (3 + 1 zero), shifted by one pixel so that block (i, j) holds pixels
+// (2i-1+dy, 2j-1+dx):   X2[n, i, j, (dy, dx, c4)]  (bf16, 32-byte rows, zero outside the image).
+// Then Conv2D(k4, s2, p1) over the image is a 2x2-tap stride-1 convolution over the blocks,
+//     out[oh, ow] = sum_{a,b in {0,1}} X2[oh + a, ow + b, :] . W[(2a+dy, 2b+dx, c)],
+// i.e. a 4-tap tap-GEMM with K = 16 per tap (conv1 forward, conv5t dgrad) and a 64-row MN-major wgrad, and
+// Conv2DTranspose(k4, s2, p1) PRODUCES its output in the same block form from 2x2 taps of its input,
+//     out2[i, j, (dy,dx,c)] = sum_{a,b} S[i - a, j - b, :] . W[(2a+dy, 2b+dx, c)].
+// 36 MB per 1024 images instead of the 134 MB K=64 im2col matrix, and no separate im2col / reconstruction pass.
+// ---------------------------------------------------------------------------------------------------
+template <typename XT>
+__device__ __forceinline__ float load_px(const XT* p);
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) {
+  return __fdiv_rn((float)__ldg(p), 255.0f);   // utils_data.py:57-59: np.float32(img) / 255.0, bit-exact
+}
+
+// one thread per block (n, i, j): 4 pixels x 3 channels in, 32 bytes out
+template <typename XT>
+__global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, long long total, uint4* __restrict__ X2) {
+  pdl_launch_dependents();
+  pdl_wait();
+  for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
+    const int j = (int)(idx % 33), i = (int)((idx / 33) % 33);
+    const long long n = idx / (33 * 33);
+    uint32_t w[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int Y = 2 * i - 1 + (q >> 1), X = 2 * j - 1 + (q & 1);
+      float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+      if ((unsigned)Y < 64u && (unsigned)X < 64u) {
+        const XT* px = x + ((n * 64 + Y) * 64 + X) * 3;
+        v0 = load_px<XT>(px); v1 = load_px<XT>(px + 1); v2 = load_px<XT>(px + 2);
+      }
+      w[2 * q] = pack_bf16x2(v0, v1);
+      w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
+    }
+    X2[2 * idx] = make_uint4(w[0], w[1], w[2], w[3]);
+    X2[2 * idx + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+
+// Fused Conv2DTranspose(32 -> 3, k4, s2, same) + sigmoid + Laplace log-likelihood (utils.py:101-105) + its
+// gradient w.r.t. the logits, written in block form D2 (the operand of conv5t's dgrad and wgrad).
+// Tile = 11 x 11 blocks of one image (9 tiles per image, 121 of the 128 MMA rows used); 4 taps, each a TMA box
+// of the decoder activation g4 [B,32,32,32] shifted by (-a, -b) (zero-filled outside), K = 32 per tap, N = 16.
+struct alignas(64) CtrParams {
+  CUtensorMap tmA, tmB;
+  const void* x;
+  int x_u8;
+  const float* bias;   // [3]
+  const float* coef;   // [B] dLoss/dlog_pxz per image (NULL: forward only, D2 is not written)
+  float* log_pxz;      // [B], pre-set to -12288 ln 2; -|x - xhat|_1 is added
+  uint4* D2;           // [B,33,33,16] bf16
+  float* xhat;         // optional [B,64,64,3] fp32 reconstruction
+  float* db;           // optional [3] += sum of dlogit (bias gradient of conv5t)
+  int batch, total_tiles, stages;
+};
+
+template <typename XT>
+__global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_constant__ CtrParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int A_SLOT = 8192, A_BOX = 121 * 64, B_TAP = 1024, STAGE = 4 * A_SLOT;
+  uint8_t* sB = smem;                 // 4 taps x [16 rows x 64 B]
+  uint8_t* sA = smem + 4 * B_TAP;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  float* s_db = reinterpret_cast<float*>(tmem_slot + 4);   // [4]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_beg = blockIdx.x * per_cta;
+  const int tile_end = min(tile_beg + per_cta, p.total_tiles);
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&p.tmA);
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    mbar_init(bfull, 1);
+    fence_mbar_init();
+  }
+  if (threadIdx.x < 4) s_db[threadIdx.x] = 0.0f;
+  if (warp == 2) tmem_alloc(tmem_slot, 64);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  pdl_wait();
+
+  if (warp == 0) {
+    if (elect_one() && tile_beg < tile_end) {
+      mbar_expect_tx(bfull, 4 * B_TAP);
+      for (int t = 0; t < 4; ++t) tma_load_2d(sB + t * B_TAP, &p.tmB, bfull, t * 32, 0);
+      int stage = 0;
+      uint32_t ph = 0;
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int n = tile / 9, r = tile - n * 9, i0 = (r / 3) * 11, j0 = (r % 3) * 11;
+        mbar_wait(&empty[stage], ph ^ 1);
+        mbar_expect_tx(&full[stage], 4 * A_BOX);
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          tma_load_4d(sA + stage * STAGE + t * A_SLOT, &p.tmA, &full[stage], 0, j0 - (t & 1), i0 - (t >> 1), n);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0 && tile_beg < tile_end) {
+      const uint32_t idesc = instr_desc_bf16(128, 16, 0, 0);
+      const uint64_t dproto = smem_desc(0, 16, 8u * 64u, SW_64);
+      const uint64_t adesc0 = dproto + (uint64_t)(smem_u32(sA) >> 4), bdesc0 = dproto + (uint64_t)(smem_u32(sB) >> 4);
+      int stage = 0;
+      uint32_t ph = 0;
+      mbar_wait(bfull, 0);
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int li = tile - tile_beg, as = li & 1;
+        mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * (STAGE >> 4));
+        const uint32_t tacc = tmem_base + (uint32_t)as * 32u;
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+#pragma unroll
+          for (int kk = 0; kk < 2; ++kk)
+            umma_bf16(tacc, a_st + (uint64_t)(t * (A_SLOT >> 4) + 2 * kk), bdesc0 + (uint64_t)(t * (B_TAP >> 4) + 2 * kk),
+                      idesc, (t > 0 || kk > 0) ? 1u : 0u);
+        }
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[as]);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int li_ = m / 11, lj_ = m - li_ * 11;
+    const bool row_ok = m < 121;
+    const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1), b2 = __ldg(p.bias + 2);
+    const XT* xs = reinterpret_cast<const XT*>(p.x);
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      const int li = tile - tile_beg, as = li & 1;
+      const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
+      // the image pixels of this block do not depend on the accumulator: fetch them before waiting for the MMAs
+      float xv[12];
+#pragma unroll
+      for (int k = 0; k < 12; ++k) xv[k] = 0.0f;
+      bool ok[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
+        ok[qq] = row_ok && (unsigned)Y < 64u && (unsigned)X < 64u;
+        if (ok[qq]) {
+          const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
+          xv[3 * qq] = load_px<XT>(px); xv[3 * qq + 1] = load_px<XT>(px + 1); xv[3 * qq + 2] = load_px<XT>(px + 2);
+        }
+      }
+      const float cb = p.coef != nullptr ? __ldg(p.coef + n) : 0.0f;
+      mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      uint32_t acc[16];
+      tmem_ld16(tmem_base + (uint32_t)as * 32u + ((uint32_t)(q * 32) << 16), acc);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      float l1 = 0.0f;
+      uint32_t w[8];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        float g[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          const float logit = __uint_as_float(acc[4 * qq + c]) + (c == 0 ? b0 : (c == 1 ? b1 : b2));
+          const float xh = __fdividef(1.0f, 1.0f + __expf(-logit));
+          const float e = xv[3 * qq + c] - xh;
+          g[c] = ok[qq] ? cb * (float)((e > 0.f) - (e < 0.f)) * xh * (1.0f - xh) : 0.0f;
+          if (ok[qq]) {
+            l1 += fabsf(e);
+            if (p.xhat != nullptr) {
+              const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
+              p.xhat[(((size_t)n * 64 + Y) * 64 + X) * 3 + c] = xh;
+            }
+          }
+        }
+        d0 += g[0]; d1 += g[1]; d2 += g[2];
+        w[2 * qq] = pack_bf16x2(g[0], g[1]);
+        w[2 * qq + 1] = pack_bf16x2(g[2], 0.0f);
+      }
+      if (p.D2 != nullptr && row_ok) {
+        uint4* dst = p.D2 + (((size_t)n * 33 + i) * 33 + j) * 2;
+        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+      }
+      l1 = warp_sum(l1);
+      if (lane == 0 && l1 != 0.0f) atomicAdd(p.log_pxz + n, -l1);
+    }
+    if (p.db != nullptr) {
+      d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
+      if (lane == 0) { atomicAdd(&s_db[0], d0); atomicAdd(&s_db[1], d1); atomicAdd(&s_db[2], d2); }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (p.db != nullptr && threadIdx.x < 3 && s_db[threadIdx.x] != 0.0f) atomicAdd(p.db + threadIdx.x, s_db[threadIdx.x]);
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 64);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// L -> S convolution of a 3-channel image in x2 block form (conv1 forward, conv5t dgrad) with the im2col tile
+// built by four producer warps instead of TMA: TMA moves one box row per ~1.3 cycles whatever its width, so
+// four taps of 128 32-byte rows cost as much as 128 KB of traffic, while 128 threads gather the same four
+// 32-byte blocks per output pixel with 8 coalesced 16-byte loads and write ONE 128-byte K-major row each
+// (SWIZZLE_128B pattern: 16-byte chunk c of row r lands at chunk c ^ (r & 7)).  K = 64 = (a, b, dy, dx, c4).
+// Warps 0-3: producers, warp 4: MMA issuer, warps 5-8: epilogue (TMEM lane quadrant = warp % 4).
+// ---------------------------------------------------------------------------------------------------
+struct alignas(64) C3Params {
+  CUtensorMap tmB;          // packed weights [N rows][64] bf16 (pack kind 7), box (64, N)
+  const uint4* in2;         // [B,33,33,16] bf16 blocks (2 x uint4 per block)
+  void* out;                // [B,32,32,N] bf16
+  const void* mask;         // optional [B,32,32,N] bf16: out *= (mask > 0)
+  const float* bias;        // optional [N]
+  int act, N, batch, total_tiles, stages;
+};
+constexpr int C3_THREADS = 288;
+
+__global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constant__ C3Params p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
+  constexpr int A_TILE = 128 * 128;
+  uint8_t* sB = smem;                       // N x 128 B (<= 8 KB reserved)
+  uint8_t* sA = smem + 8192;
+  uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * A_TILE);
+  uint64_t* empty = full + p.stages;
+  uint64_t* tfull = empty + p.stages;
+  uint64_t* tempty = tfull + 2;
+  uint64_t* bfull = tempty + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  pdl_launch_dependents();
+  const int per_cta = (p.total_tiles + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int tile_beg = blockIdx.x * per_cta;
+  const int tile_end = min(tile_beg + per_cta, p.total_tiles);
+  uint32_t acc_cols = 32;
+  while ((int)acc_cols < p.N) acc_cols <<= 1;
+  if (threadIdx.x == 0) {
+    tma_prefetch_desc(&p.tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full[s], 4);     // one arrival per producer warp
+      mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull[s], 1);
+      mbar_init(&tempty[s], 4);
+    }
+    mbar_init(bfull, 1);
+    fence_mbar_init();
+  }
+  if (warp == 4) tmem_alloc(tmem_slot, acc_cols * 2);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  if (threadIdx.x == 128 && tile_beg < tile_end) {   // weights are parameters: not produced by the predecessor
+    mbar_expect_tx(bfull, (uint32_t)(p.N * 128));
+    tma_load_2d(sB, &p.tmB, bfull, 0, 0);
+  }
+  pdl_wait();
+
+  if (warp < 4) {
+    // ===== producers: thread m builds row m of the im2col tile =====
+    const int m = threadIdx.x;
+    const int dy = m >> 5, dx = m & 31;
+    const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)(m & 7);
+    int stage = 0;
+    uint32_t ph = 0;
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      const int n = tile >> 3, h0 = (tile & 7) * 4;
+      const uint4* src = p.in2 + (((size_t)n * 33 + (h0 + dy)) * 33 + dx) * 2;
+      uint4 v[8];
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        const uint4* s = src + ((t >> 1) * 33 + (t & 1)) * 2;
+        v[2 * t] = __ldg(s);
+        v[2 * t + 1] = __ldg(s + 1);
+      }
+      mbar_wait(&empty[stage], ph ^ 1);
+      uint8_t* dst = sA + stage * A_TILE + row_off;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + (((uint32_t)c ^ sw) << 4)) = v[c];
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&full[stage]);
+      if (++stage == p.stages) { stage = 0; ph ^= 1; }
+    }
+  } else if (warp == 4) {
+    if (lane == 0 && tile_beg < tile_end) {
+      const uint32_t idesc = instr_desc_bf16(128, p.N, 0, 0);
+      const uint64_t dproto = smem_desc(0, 16, 1024, SW_128);
+      const uint64_t adesc0 = dproto + (uint64_t)(smem_u32(sA) >> 4), bdesc = dproto + (uint64_t)(smem_u32(sB) >> 4);
+      int stage = 0;
+      uint32_t ph = 0;
+      mbar_wait(bfull, 0);
+      for (int tile = tile_beg; tile < tile_end; ++tile) {
+        const int li = tile - tile_beg, as = li & 1;
+        mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        mbar_wait(&full[stage], ph);
+        tc_fence_after();
+        const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * (A_TILE >> 4));
+        const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) umma_bf16(tacc, ad + 2u * kk, bdesc + 2u * kk, idesc, kk > 0 ? 1u : 0u);
+        umma_commit(&empty[stage]);
+        umma_commit(&tfull[as]);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== epilogue =====
+    const int q = warp & 3;
+    const int m = q * 32 + lane;
+    const int dy = m >> 5, dx = m & 31;
+    for (int tile = tile_beg; tile < tile_end; ++tile) {
+      const int li = tile - tile_beg, as = li & 1;
+      const int n = tile >> 3, h0 = (tile & 7) * 4;
+      const size_t opix = ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
+      uint4 mpre[8];
+      const bool use_mask = p.mask != nullptr;
+      if (use_mask) {
+        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.N);
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (i * 8 < p.N) mpre[i] = __ldg(mk + i);
+      }
+      mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
+#pragma unroll
+      for (int c0 = 0; c0 < 64; c0 += 16) {
+        if (c0 >= p.N) break;
+        uint32_t r[16];
+        tmem_ld16(tacc + (uint32_t)c0, r);
+        tmem_ld_wait();
+        if (c0 + 16 >= p.N) {
+          tc_fence_before();
+          if (lane == 0) mbar_arrive(&tempty[as]);
+        }
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+        if (p.bias != nullptr) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = __ldg(bp + i);
+            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
+          }
+        }
+        if (p.act == GCCVAE_ACT_RELU) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+        }
+        if (use_mask) {
+          const uint4 m0 = mpre[(c0 >> 3)], m1 = mpre[(c0 >> 3) + 1];
+          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+            if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
+            if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+          }
+        }
+        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.N + c0);
+        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                            pack_bf16x2(v[14], v[15]));
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 4) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, acc_cols * 2);
   }
 }
 
@@ -1250,19 +1741,36 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
                 "%s: unsupported column-sum shape (n=%d mod=%d)", name, p.colsum_n, p.colsum_mod);
   }
   const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
-  // up to 4 persistent CTAs per SM (their epilogues overlap); each gets a ring of >= 3 stages.
-  // TMEM: two accumulator stages per CTA, 512 columns per SM.
+  // Persistent CTAs, `per_sm` of them per SM (their epilogues and issue threads overlap).  The single MMA-issuing
+  // thread pays ~400 cycles per pipeline stage (barrier wait, fences, commit) and ~50 per MMA, so a stage carries
+  // `tps` k-blocks (taps x chunks): few, fat stages.  TMEM: two accumulator stages per CTA, 512 columns per SM.
+  static int env_tps = -1, env_per_sm = -1, env_stage_kb = -1;
+  if (env_tps < 0) {
+    const char* e = getenv("GCCVAE_TPS");
+    env_tps = e ? atoi(e) : 0;
+    e = getenv("GCCVAE_TG_PER_SM");
+    env_per_sm = e ? atoi(e) : 0;
+    e = getenv("GCCVAE_STAGE_KB");
+    env_stage_kb = e ? atoi(e) : 0;
+  }
   uint32_t acc_cols = 32;
   while ((int)acc_cols < p.N) acc_cols <<= 1;
-  int per_sm = 512 / (2 * (int)acc_cols);
-  if (per_sm > 4) per_sm = 4;
+  const int k_iters = p.num_taps * p.chunks;
+  int per_sm = env_per_sm > 0 ? env_per_sm : 3;
+  if (per_sm > 512 / (2 * (int)acc_cols)) per_sm = 512 / (2 * (int)acc_cols);
   if (per_sm < 1) per_sm = 1;
-  while (per_sm > 1 && (200 * 1024 / per_sm) < 3 * (a_stride + b_stride) + 3072) --per_sm;
-  int stages = ((200 * 1024 / per_sm) - 3072) / (a_stride + b_stride);
+  const int budget = 200 * 1024 / per_sm - 3072;
+  const int stage_target = (env_stage_kb > 0 ? env_stage_kb : 32) * 1024;
+  int tps = 1;
+  for (int d = 1; d <= k_iters; ++d)
+    if (k_iters % d == 0 && d * (a_stride + b_stride) <= stage_target && 2 * d * (a_stride + b_stride) <= budget) tps = d;
+  if (env_tps > 0 && k_iters % env_tps == 0 && 2 * env_tps * (a_stride + b_stride) <= budget) tps = env_tps;
+  p.tps = tps;
+  int stages = budget / (tps * (a_stride + b_stride));
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * (a_stride + b_stride) + 1024 + 256 + 1024;
+  const size_t smem = (size_t)stages * tps * (a_stride + b_stride) + 1024 + 256 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
@@ -1278,7 +1786,31 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   GCC_REQUIRE(p.bias == nullptr || ((uintptr_t)p.bias % 16) == 0, "%s: bias must be 16-byte aligned", name);
   p.phases = phases;
   p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
+  // never launch more persistent CTAs than are resident at once: a second wave would serialise behind the first.
+  // Residency limits: registers (64K per SM), shared memory (227 KB per SM, 1 KB reserved per CTA), TMEM (above).
+  static int regs_per_cta[2] = {0, 0};
+  const int ki = p.colsum != nullptr ? 1 : 0;
+  if (regs_per_cta[ki] == 0) {
+    cudaFuncAttributes fa;
+    if (ki) GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<true>));
+    else GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<false>));
+    const int per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
+    regs_per_cta[ki] = per_warp * (TG_THREADS / 32);
+  }
+  int occ = 65536 / regs_per_cta[ki];
+  const int occ_smem = (int)((227 * 1024) / (smem + 1024));
+  if (occ > occ_smem) occ = occ_smem;
+  if (occ < 1) occ = 1;
+  if (per_sm > occ) per_sm = occ;
+  if (getenv("GCCVAE_DEBUG_LAUNCH"))
+    fprintf(stderr, "%s: N=%d KC=%d k_iters=%d tps=%d stages=%d smem=%zu per_sm=%d (occ %d) items=%d\n", name, p.N, p.KC,
+            k_iters, tps, stages, smem, per_sm, occ, p.total_items);
   int ctas = p.total_items < 148 * per_sm ? p.total_items : 148 * per_sm;
+  // even out the work: with ceil(total/ctas) items per CTA fewer CTAs may carry the same maximum
+  {
+    const int per_cta = (p.total_items + ctas - 1) / ctas;
+    ctas = (p.total_items + per_cta - 1) / per_cta;
+  }
   dim3 grid(ctas, 1, 1);
   if (p.colsum != nullptr) GCC_CUDA(launch_pdl(tapgemm_kernel<true>, grid, TG_THREADS, smem, st, p));
   else GCC_CUDA(launch_pdl(tapgemm_kernel<false>, grid, TG_THREADS, smem, st, p));
@@ -1588,6 +2120,7 @@ extern "C" int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const vo
   hp.total_tiles = g->batch * hp.tiles_h;
   hp.colsum = g_colsum; hp.colsum_n = g_colsum_n;
   g_colsum = nullptr;
+  hp.timeline = g_timeline;
   GCC_REQUIRE(hp.colsum == nullptr || (hp.colsum_n > 0 && hp.colsum_n <= 256), "sl_halo: colsum_n");
   const int rowb = g->CS * 2, a_stage = 3 * (bh + 2) * bw * rowb, b_bytes = (9 * 4 * rows_pad * rowb + 1023) & ~1023;
   int stages = (196 * 1024 - b_bytes - 5120) / a_stage;
@@ -1607,6 +2140,189 @@ extern "C" int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const vo
   else
     GCC_CUDA(launch_pdl(sl_halo_kernel<false>, dim3(ctas, 1, 1), HALO_THREADS, smem, (cudaStream_t)stream, hp));
   GCC_CHECK_LAUNCH("sl_halo_bf16");
+  return GCCVAE_OK;
+}
+
+
+// ---- x2 (space-to-depth) end layers ----------------------------------------------------------------------
+// x [B,64,64,3] (fp32 in [0,1], or uint8 0..255 which is divided by 255 on the fly) -> X2 [B,33,33,16] bf16
+extern "C" int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* stream) {
+  GCC_REQUIRE(x && X2 && batch > 0, "prep_x2: bad args");
+  const long long total = (long long)batch * 33 * 33;
+  long long ctas = (total + 255) / 256;
+  if (ctas > 148 * 16) ctas = 148 * 16;
+  if (x_u8)
+    GCC_CUDA(launch_pdl_k(prep_x2_kernel<uint8_t>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)x,
+                          total, (uint4*)X2));
+  else
+    GCC_CUDA(launch_pdl_k(prep_x2_kernel<float>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, (const float*)x, total,
+                          (uint4*)X2));
+  GCC_CHECK_LAUNCH("prep_x2");
+  return GCCVAE_OK;
+}
+
+// out[n, y, x, :] = act( sum_{a,b in {0,1}} in2[n, y+a, x+b, :] . Wp[:, (a,b), :] + bias ) (* mask > 0)
+// in2 = [B, HB, WB, CB] bf16 blocks, out = [B, HB-1, WB-1, CS] bf16 NHWC, Wp = [CS][4][CB] bf16 (pack kind 7).
+extern "C" int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, const void* Wp, int CS,
+                                   const float* bias, int act, const void* mask, void* out, void* stream) {
+  GCC_REQUIRE(in2 && Wp && out && batch > 0, "tap4_ls: null pointer");
+  const int kc = CB >= 64 ? 64 : CB;
+  GCC_REQUIRE((kc == 16 || kc == 32 || kc == 64) && CB % kc == 0, "tap4_ls: CB=%d unsupported", CB);
+  GCC_REQUIRE(CS % 16 == 0 && CS <= 256, "tap4_ls: CS=%d must be a multiple of 16, <= 256", CS);
+  const int HS = HB - 1, WS = WB - 1;
+  int bw, bh, bn, rc;
+  GCC_REQUIRE(pick_tile(HS, WS, &bw, &bh, &bn) == 0, "tap4_ls: cannot tile %dx%d", HS, WS);
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  if ((rc = encode_act_map(&p.tmA, in2, batch, HB, WB, CB, kc, bw, bh, bn, 1))) return rc;
+  if ((rc = encode_mat_map(&p.tmB, Wp, CS, 4LL * CB, kc, CS))) return rc;
+  p.num_taps = 4; p.chunks = CB / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
+  p.tiles_w = WS / bw; p.tiles_h = HS / bh;
+  for (int t = 0; t < 4; ++t) { p.a_dh[0][t] = (short)(t >> 1); p.a_dw[0][t] = (short)(t & 1); }
+  p.b_tap_stride = CB;
+  p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
+  p.N = CS; p.n_store = CS; p.n_slabs = 1;
+  p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = 0;
+  p.OH = HS; p.OW = WS; p.OC = CS; p.oys = p.oxs = 1;
+  p.batch = batch;
+  const int groups = (batch + bn - 1) / bn;
+  return launch_tapgemm(p, groups, 1, (cudaStream_t)stream, "tap4_ls");
+}
+
+// dW[(kh,kw,c<3), cs] (fp32, Keras layout) += sum_pix gather4(in2)[pix, (a,b,dy,dx,c4)] * S[pix, cs]
+// in2 = [B,33,33,16] bf16 x2 blocks of a 3-channel 64x64 tensor, S = [B,32,32,CS] bf16.
+extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream) {
+  GCC_REQUIRE(in2 && S && dW && batch > 0, "tap4_wg: null pointer");
+  GCC_REQUIRE(CS % 32 == 0 && CS <= 256, "tap4_wg: CS=%d unsupported (multiple of 32, <= 256)", CS);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  p.kcA = 16; p.blocks_per_tap = 1; p.blocks_per_mtile = 8; p.taps = 4; p.c4_rows = 2;
+  p.kcB = (CS % 64 == 0) ? 64 : 32;
+  p.b_loads = CS / p.kcB;
+  p.swzA = umma_swizzle_for(p.kcA * 2);
+  p.swzB = umma_swizzle_for(p.kcB * 2);
+  int rc, bw, bh, bn;
+  GCC_REQUIRE(pick_tile(32, 32, &bw, &bh, &bn) == 0, "tap4_wg: tile");
+  p.a_scale = 1;
+  for (int t = 0; t < 4; ++t) { p.a_dh[t] = (short)(t >> 1); p.a_dw[t] = (short)(t & 1); }
+  if ((rc = encode_act_map(&p.tmA, in2, batch, 33, 33, 16, p.kcA, bw, bh, bn, 1))) return rc;
+  if ((rc = encode_act_map(&p.tmB, S, batch, 32, 32, CS, p.kcB, bw, bh, bn, 1))) return rc;
+  p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = 32 / bw; p.tiles_h = 32 / bh;
+  p.N = CS;
+  p.out.n_seg = 1; p.out.m_valid = 64;
+  p.out.seg[0].col0 = 0; p.out.seg[0].ncols = CS; p.out.seg[0].ld = CS; p.out.seg[0].dst = dW;
+  const int groups = (batch + bn - 1) / bn;
+  p.tiles_total = groups * p.tiles_w * p.tiles_h;
+  int splits = 148 * 2;
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
+  splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
+  int stages = (100 * 1024) / stage_bytes;   // two CTAs per SM
+  if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  GCC_CUDA(launch_pdl(wgrad_kernel, dim3(splits, 1, 1), TG_THREADS, smem, (cudaStream_t)stream, p));
+  GCC_CHECK_LAUNCH("tap4_wg");
+  return GCCVAE_OK;
+}
+
+// Fused conv5t forward (Conv2DTranspose 32 -> 3, k4, s2, same) + sigmoid + Laplace log-likelihood + dLoss/dlogit.
+//   g4 [B,32,32,32] bf16, Wp8 = pack kind 8 ([16][4][32] bf16), bias [3], x [B,64,64,3] fp32 or uint8.
+//   log_pxz[b] = -|x - xhat|_1 - 12288 ln 2.  coef != NULL: D2 [B,33,33,16] bf16 = coef[b] sign(x - xhat) xhat (1 - xhat)
+//   in x2 block form and db[3] += its sums.  xhat (optional): the reconstruction, fp32 [B,64,64,3].
+extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp8, const float* bias, const void* x,
+                                       int x_u8, const float* coef, float* log_pxz, void* D2, float* xhat, float* db,
+                                       void* stream) {
+  GCC_REQUIRE(g4 && Wp8 && bias && x && log_pxz && batch > 0, "convt_recon: null pointer");
+  GCC_REQUIRE((coef == nullptr) == (D2 == nullptr), "convt_recon: coef and D2 go together");
+  cudaStream_t st = (cudaStream_t)stream;
+  CtrParams p;
+  memset(&p, 0, sizeof(p));
+  EncodeTiledFn enc = get_encode();
+  GCC_REQUIRE(enc != nullptr, "cuTensorMapEncodeTiled unavailable");
+  {
+    cuuint64_t dims[4] = {32, 32, 32, (cuuint64_t)batch};
+    cuuint64_t strides[3] = {64, 32 * 64, 32 * 32 * 64};
+    cuuint32_t box[4] = {32, 11, 11, 1};
+    cuuint32_t estr[4] = {1, 1, 1, 1};
+    CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g4), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    GCC_REQUIRE(r == CUDA_SUCCESS, "convt_recon: cuTensorMapEncodeTiled failed: %d", (int)r);
+  }
+  int rc;
+  if ((rc = encode_mat_map(&p.tmB, Wp8, 16, 128, 32, 16))) return rc;
+  p.x = x; p.x_u8 = x_u8; p.bias = bias; p.coef = coef; p.log_pxz = log_pxz; p.D2 = (uint4*)D2; p.xhat = xhat; p.db = db;
+  p.batch = batch; p.total_tiles = batch * 9;
+  const int per_sm = 3;
+  int stages = (200 * 1024 / per_sm - 4096 - 3072) / (4 * 8192);
+  if (stages > 4) stages = 4;
+  GCC_REQUIRE(stages >= 1, "convt_recon: shared memory");
+  p.stages = stages;
+  const size_t smem = 4096 + (size_t)stages * 4 * 8192 + 1024 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
+  GCC_CHECK_LAUNCH("recon_fill");
+  int ctas = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
+  {
+    const int per_cta = (p.total_tiles + ctas - 1) / ctas;
+    ctas = (p.total_tiles + per_cta - 1) / per_cta;
+  }
+  if (x_u8) GCC_CUDA(launch_pdl(convt_recon_kernel<uint8_t>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
+  else GCC_CUDA(launch_pdl(convt_recon_kernel<float>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
+  GCC_CHECK_LAUNCH("convt_recon");
+  return GCCVAE_OK;
+}
+
+
+// conv1 forward / conv5t dgrad from x2 blocks with thread-built im2col tiles (see c3conv_kernel):
+// out[B,32,32,CS] = act(conv_k4s2p1(image of in2) + bias) (* mask > 0), Wp = pack kind 7 ([CS][64] bf16), CS in {32, 64}.
+extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, int CS, const float* bias, int act,
+                                  const void* mask, void* out, void* stream) {
+  GCC_REQUIRE(in2 && Wp && out && batch > 0, "c3conv: null pointer");
+  GCC_REQUIRE(CS == 32 || CS == 64, "c3conv: CS=%d unsupported (32 or 64)", CS);
+  GCC_REQUIRE(bias == nullptr || ((uintptr_t)bias % 16) == 0, "c3conv: bias must be 16-byte aligned");
+  C3Params p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = encode_mat_map(&p.tmB, Wp, CS, 64, 64, CS))) return rc;
+  p.in2 = (const uint4*)in2; p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.N = CS; p.batch = batch;
+  p.total_tiles = batch * 8;
+  static int env_per_sm = -1;
+  if (env_per_sm < 0) {
+    const char* e = getenv("GCCVAE_C3_PER_SM");
+    env_per_sm = e ? atoi(e) : 0;
+  }
+  const int per_sm = env_per_sm > 0 ? env_per_sm : 2;
+  int stages = (200 * 1024 / per_sm - 8192 - 3072) / (128 * 128);
+  if (stages > 6) stages = 6;
+  GCC_REQUIRE(stages >= 2, "c3conv: shared memory");
+  p.stages = stages;
+  const size_t smem = 8192 + (size_t)stages * 128 * 128 + 1024 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(c3conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  int ctas = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
+  {
+    const int per_cta = (p.total_tiles + ctas - 1) / ctas;
+    ctas = (p.total_tiles + per_cta - 1) / per_cta;
+  }
+  GCC_CUDA(launch_pdl(c3conv_kernel, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
+  GCC_CHECK_LAUNCH("c3conv");
   return GCCVAE_OK;
 }
 
@@ -1681,11 +2397,11 @@ extern "C" int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stre
 }
 
 extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, void* stream) {
-  GCC_REQUIRE(jobs && n_jobs > 0 && n_jobs <= 32, "pack_jobs: 1..32 jobs");
+  GCC_REQUIRE(jobs && n_jobs > 0 && n_jobs <= 48, "pack_jobs: 1..48 jobs");
   PackJobs pj;
   memset(&pj, 0, sizeof(pj));
   for (int i = 0; i < n_jobs; ++i) {
-    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 6, "pack_jobs: bad job %d", i);
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 8, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
   GCC_CUDA(launch_pdl_k(pack_jobs_kernel, dim3(64, n_jobs, 1), dim3(256), 0, (cudaStream_t)stream, pj));

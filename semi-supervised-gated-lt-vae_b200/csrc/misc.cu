@@ -69,6 +69,14 @@ __global__ void __launch_bounds__(256) recon_kernel(const float4* __restrict__ x
 
 // Keras 2.8 Adam.  `step_dev` (optional) holds t on the device so that a captured CUDA graph of the
 // whole step can be replayed: bump_kernel increments it before every update.
+// debug marker: records %globaltimer (ns) into slot idx; launched WITHOUT the PDL attribute, so it runs after
+// everything before it on the stream has finished -> segment times of a captured graph
+__global__ void mark_kernel(long long* buf, int idx) {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  buf[idx] = (long long)t;
+}
+
 __global__ void bump_kernel(int* p) {
   pdl_prologue();
  *p += 1; }
@@ -218,6 +226,13 @@ extern "C" int gccvae_adam_f32(float* param, const float* grad, float* m, float*
   GCC_CUDA(launch_pdl_k(adam_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, n, lr,
                         beta1, beta2, eps, step, (const int*)step_dev));
   GCC_CHECK_LAUNCH("adam");
+  return GCCVAE_OK;
+}
+
+extern "C" int gccvae_debug_mark(long long* buf, int idx, void* stream) {
+  GCC_REQUIRE(buf && idx >= 0, "debug_mark: bad args");
+  mark_kernel<<<1, 1, 0, (cudaStream_t)stream>>>(buf, idx);
+  GCC_CHECK_LAUNCH("debug_mark");
   return GCCVAE_OK;
 }
 

@@ -16,6 +16,7 @@ Packed bf16 weight operands are refreshed from the fp32 master parameters at the
 from __future__ import annotations
 
 import ctypes as C
+import os
 
 import torch
 
@@ -58,6 +59,11 @@ class EngineTC(Engine):
                 self.wp[name + ".sl9"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 2))
         self.wp["enc.conv1.c4"] = z16(32 * 64)
         self.wp["dec.conv5t.c4"] = z16(32 * 64)
+        # x2 (space-to-depth) operands of the 3-channel end layers
+        self.wp["enc.conv1.x2"] = z16(32 * 64)       # [cs][(a,b)][(dy,dx,c4)]
+        self.wp["dec.conv5t.x2"] = z16(32 * 64)      # same packing: B operand of conv5t's dgrad
+        self.wp["dec.conv5t.x2t"] = z16(16 * 128)    # [(dy,dx,c4)][(a,b)][cs]: fused conv5t forward
+        self.x2 = os.environ.get("GCCVAE_X2", "1") != "0"
         # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
         self.wp["heads.ls"] = z16(96, 256)       # rows 0..44 = W_loc^T, 48..92 = W_std^T
         self.wp["heads.sl"] = z16(256, 96)
@@ -67,16 +73,23 @@ class EngineTC(Engine):
         self.wp["conv1t.sl"] = z16(2048, 64)
         self.wp["conv1t.ls"] = z16(64, 2048)
         self._jobs = None
-        import os
         # bias gradients: a separate column-sum pass per layer by default.  Both fused variants were measured slower
         # on B200: in the dgrad epilogue (registers -> occupancy: 2.57 vs 2.37 ms per step) and in the wgrad main loop
         # (GCCVAE_BIAS_IN_WGRAD=1: stage release waits for the sums: 2.11 vs 2.09 ms).
         # weight gradients are off the critical path (only Adam needs them): they run on a side stream, concurrently
         # with the dgrad chain; under CUDA-graph capture this becomes a parallel branch of the graph
         self.side = torch.cuda.Stream(device=dev) if os.environ.get("GCCVAE_SIDE_STREAM", "1") != "0" else None
+        # bias gradients (column sums) are needed by Adam only, like the weight gradients: a second side stream keeps
+        # them off the dgrad chain (GCCVAE_BGRAD_STREAM=main puts them back on the main stream)
+        self.side2 = (torch.cuda.Stream(device=dev)
+                      if self.side is not None and os.environ.get("GCCVAE_BGRAD_STREAM", "side") != "main" else None)
         self.bias_in_wgrad = os.environ.get("GCCVAE_BIAS_IN_WGRAD", "0") != "0"
         self._deferred_bias = []
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
+        # debug timeline (GCCVAE_MARKERS=1: a globaltimer marker kernel after every op, 2: only at segment ends)
+        self.mark_level = int(os.environ.get("GCCVAE_MARKERS", "0"))
+        self.mark_buf = torch.zeros(1024, dtype=torch.int64, device=dev) if self.mark_level else None
+        self.marks = []
 
     # ---- packed weights ---------------------------------------------------------------------------------
     def pack_weights(self):
@@ -97,6 +110,9 @@ class EngineTC(Engine):
                 J(6, 16, CL, CS, v(name + ".w"), self.wp[name + ".sl9"])
             J(3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"])
             J(3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"])
+            J(7, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.x2"])
+            J(7, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2"])
+            J(8, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2t"])
             # kind 4/5: out[(ro + r) * ld + co + k] = W[r * sr + k * sk],  r < taps(R), k < CL(K)
             for off, nm in ((0, "enc.locs"), (48, "enc.std")):
                 J(4, 45, 256, 0, v(nm + ".w"), self.wp["heads.ls"], 1, 45, 256, off, 0)
@@ -115,8 +131,13 @@ class EngineTC(Engine):
         dev = self.device
         e = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         b = {}
-        b["X64"] = e(B * 1024, 64, dt=BF16)
-        b["G64"] = e(B * 1024, 64, dt=BF16)
+        if self.x2:
+            b["X2"] = e(B, 33, 33, 16, dt=BF16)      # input image in x2 block form
+            b["D2"] = e(B, 33, 33, 16, dt=BF16)      # dLoss/dlogit of the reconstruction in x2 block form
+            b["xhat3"] = None                        # fp32 reconstruction, allocated on demand (tests / API)
+        else:
+            b["X64"] = e(B * 1024, 64, dt=BF16)
+            b["G64"] = e(B * 1024, 64, dt=BF16)
         for name in ["enc.conv1", "enc.conv2", "enc.conv3", "enc.conv4", "enc.conv5"]:
             oh, ow, oc = out_shape(_ENC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
@@ -131,8 +152,13 @@ class EngineTC(Engine):
             oh, ow, oc = out_shape(_DEC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
             b[name + ".dout"] = e(B, oh, ow, oc, dt=BF16)
-        b["xhat4"] = e(B, 64, 64, 4)
+        b["xhat4"] = None if self.x2 else e(B, 64, 64, 4)
         return b
+
+    def _xhat4(self, b, B):
+        if b["xhat4"] is None:     # only the stand-alone Decoder(z) call needs it in x2 mode
+            b["xhat4"] = torch.zeros(B, 64, 64, 4, dtype=torch.float32, device=self.device)
+        return b["xhat4"]
 
     def latent_io(self, b):
         pre, g_ = b["pre96"], self.store.g
@@ -146,6 +172,8 @@ class EngineTC(Engine):
         record (duration, bytes of the tensors it reads/writes = its algorithmic HBM traffic)."""
         if self.prof is None:
             _lib.check(rc_fn(), what)
+            if self.mark_level == 1:
+                self.mark(what)
             return
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -153,6 +181,14 @@ class EngineTC(Engine):
         e1.record()
         nbytes = sum(t.numel() * t.element_size() for t in tensors if t is not None)
         self.prof.append((what, e0, e1, nbytes))
+
+    def mark(self, what, coarse=False):
+        if self.mark_buf is None or (self.mark_level == 2 and not coarse) or len(self.marks) >= 1024:
+            return
+        st = torch.cuda.current_stream()
+        lane = "main" if (st != self.side and st != self.side2) else ("side" if st == self.side else "side2")
+        _lib.check(self.lib.gccvae_debug_mark(ptr(self.mark_buf), len(self.marks), _stream()), "mark")
+        self.marks.append((what, lane))
 
     def _sl(self, name, geom, S, bias, act, mask, L, out_f32, what):
         """S -> L of layer `name` (convT forward / conv dgrad): halo kernel where the geometry allows it."""
@@ -185,10 +221,22 @@ class EngineTC(Engine):
             ptr(dout), rows, cols, n_valid, ptr(self.store.g(name + ".b")), _stream()))
 
     def _flush_deferred_bias(self):
-        for dout, name, n in self._deferred_bias:
-            cols = dout.shape[-1]
-            self._bias_grad16(dout, name, cols=cols, n_valid=n if n < cols else 0)
+        if not self._deferred_bias:
+            return
+        def run():
+            for dout, name, n in self._deferred_bias:
+                cols = dout.shape[-1]
+                self._bias_grad16(dout, name, cols=cols, n_valid=n if n < cols else 0)
+        self._on_side2(run)
         self._deferred_bias = []
+
+    def _on_side2(self, fn):
+        if self.side2 is None or self.side is None:
+            fn()
+            return
+        self.side2.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.side2):
+            fn()
 
     def _side(self, fn, small=False):
         """run fn (weight-gradient launches) on the side stream, after everything issued so far on the main one.
@@ -205,6 +253,8 @@ class EngineTC(Engine):
     def join_side(self):
         if self.side is not None:
             torch.cuda.current_stream().wait_stream(self.side)
+            if self.side2 is not None:
+                torch.cuda.current_stream().wait_stream(self.side2)
 
     def _arm_wgrad_bias(self, name, n, side, dout=None):
         """bias gradient of `name`.  Default: a separate bandwidth-bound column-sum pass over dout on the main
@@ -224,12 +274,19 @@ class EngineTC(Engine):
         B = x.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
         self.pack_weights()
-        self._run("im2col_x", (x, b["X64"]), lambda: lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st))
-        g = _dense64_geom(B * 1024, 32)
-        g1 = g
-        self._run("enc.conv1 fwd", (b["X64"], b["enc.conv1.out"]), lambda: lib.gccvae_ls_bf16(
-            C.byref(g1), ptr(b["X64"]), ptr(self.wp["enc.conv1.c4"]), ptr(v("enc.conv1.b")), ACT_RELU, None,
-            ptr(b["enc.conv1.out"]), 0, st))
+        if self.x2:
+            u8 = int(x.dtype == torch.uint8)
+            self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
+            self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
+                B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU, None,
+                ptr(b["enc.conv1.out"]), st))
+        else:
+            self._run("im2col_x", (x, b["X64"]), lambda: lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st))
+            g = _dense64_geom(B * 1024, 32)
+            g1 = g
+            self._run("enc.conv1 fwd", (b["X64"], b["enc.conv1.out"]), lambda: lib.gccvae_ls_bf16(
+                C.byref(g1), ptr(b["X64"]), ptr(self.wp["enc.conv1.c4"]), ptr(v("enc.conv1.b")), ACT_RELU, None,
+                ptr(b["enc.conv1.out"]), 0, st))
         h = b["enc.conv1.out"]
         for name in TC_ENC:
             g = make_geom(_ENC[name], B)
@@ -242,8 +299,8 @@ class EngineTC(Engine):
                    "enc.heads fwd")
         return b["pre96"][:, 0:45], b["pre96"][:, 48:93]
 
-    def decoder_fwd(self, z, b, z16_ready=False):
-        B = z.shape[0]
+    def decoder_fwd(self, z, b, z16_ready=False, fused_recon=False, batch=None):
+        B = z.shape[0] if batch is None else batch
         lib, st, v = self.lib, _stream(), self.store.view
         if not z16_ready:          # standalone Decoder(z) call; inside the step the latent kernel writes z16
             b["z16"][:, :45].copy_(z)
@@ -256,12 +313,34 @@ class EngineTC(Engine):
             g = make_geom(_DEC[name], B)
             self._sl(name, g, h, v(name + ".b"), ACT_RELU, None, b[name + ".out"], 0, name + " fwd")
             h = b[name + ".out"]
+        if fused_recon:            # conv5t runs fused with the likelihood (decoder_fwd_recon)
+            return None
         g = make_geom(_DEC["dec.conv5t"], B)
-        self._sl("dec.conv5t", g, h, v("dec.conv5t.b"), ACT_SIGMOID, None, b["xhat4"], 2, "dec.conv5t fwd")
-        return b["xhat4"][..., :3]
+        xh4 = self._xhat4(b, B)
+        self._sl("dec.conv5t", g, h, v("dec.conv5t.b"), ACT_SIGMOID, None, xh4, 2, "dec.conv5t fwd")
+        return xh4[..., :3]
+
+    def decoder_fwd_recon(self, x, b, coef, log_pxz, backward, want_recon):
+        """decoder forward with conv5t + sigmoid + Laplace log-likelihood (+ dLoss/dlogit in x2 block form) fused."""
+        B = x.shape[0]
+        self.decoder_fwd(None, b, z16_ready=True, fused_recon=True, batch=B)
+        xhat = None
+        if want_recon:
+            if b["xhat3"] is None:
+                b["xhat3"] = torch.zeros(B, 64, 64, 3, dtype=torch.float32, device=self.device)
+            xhat = b["xhat3"]
+        u8 = int(x.dtype == torch.uint8)
+        v = self.store.view
+        self._run("dec.conv5t fwd+recon", (b["dec.conv4t.out"], x, b["D2"] if backward else None),
+                  lambda: self.lib.gccvae_convt_recon_bf16(
+                      B, ptr(b["dec.conv4t.out"]), ptr(self.wp["dec.conv5t.x2t"]), ptr(v("dec.conv5t.b")), ptr(x), u8,
+                      ptr(coef) if backward else None, ptr(log_pxz), ptr(b["D2"]) if backward else None, ptr(xhat),
+                      ptr(self.store.g("dec.conv5t.b")) if backward else None, _stream()))
+        return xhat
 
     def recon(self, x, b, coef, log_pxz, backward):
         B = x.shape[0]
+        self._xhat4(b, B)
         self._run("recon_im2col", (x, b["xhat4"], b["G64"] if backward else None),
                   lambda: self.lib.gccvae_recon_im2col_bf16(
                       ptr(x), ptr(b["xhat4"]), B, ptr(coef) if backward else None, ptr(log_pxz),
@@ -273,14 +352,22 @@ class EngineTC(Engine):
     def decoder_bwd(self, z, b, want_dz=True):
         B = z.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
-        # conv5t from the im2col'd logit gradient
         g4 = b["dec.conv4t.out"]
-        self._side(lambda: self._run("dec.conv5t wgrad", (b["G64"], g4), lambda: lib.gccvae_wg_c4_bf16(
-            B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
-        g = _dense64_geom(B * 1024, 32)
-        self._run("dec.conv5t dgrad", (b["G64"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_ls_bf16(
-            C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
-            ptr(b["dec.conv4t.dout"]), 0, st))
+        if self.x2:
+            # conv5t from the logit gradient in x2 block form (written by the fused forward)
+            self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
+                B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
+            self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
+                B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE, ptr(g4),
+                ptr(b["dec.conv4t.dout"]), st))
+        else:
+            # conv5t from the im2col'd logit gradient
+            self._side(lambda: self._run("dec.conv5t wgrad", (b["G64"], g4), lambda: lib.gccvae_wg_c4_bf16(
+                B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
+            g = _dense64_geom(B * 1024, 32)
+            self._run("dec.conv5t dgrad", (b["G64"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_ls_bf16(
+                C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
+                ptr(b["dec.conv4t.dout"]), 0, st))
         prev_of = {"dec.conv4t": "dec.conv3t", "dec.conv3t": "dec.conv2t", "dec.conv2t": "dec.conv1t"}
         for name in reversed(TC_DEC):
             geom = make_geom(_DEC[name], B)
@@ -297,7 +384,7 @@ class EngineTC(Engine):
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
                                          "dec.conv1t wgrad"))
-        self._bias_grad16(dg1, "dec.conv1t", cols=128)
+        self._on_side2(lambda: self._bias_grad16(dg1, "dec.conv1t", cols=128))
         self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "dec.conv1t dgrad")
         def wg_fc1():
             self._arm_wgrad_bias("dec.fc1", 45, 1, dg0)
@@ -331,8 +418,12 @@ class EngineTC(Engine):
         dh1 = b["enc.conv1.dout"]
         def wg1():
             self._arm_wgrad_bias("enc.conv1", 32, 1, dh1)
-            self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
-                B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
+            if self.x2:
+                self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(
+                    B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
+            else:
+                self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
+                    B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
         self._side(wg1)
         self.join_side()
 

@@ -191,7 +191,15 @@ class Learner:
         return lb
 
     def _prep_inputs(self, x, y):
-        x = as_device_f32(x, self.device)
+        xt = torch.as_tensor(x) if not torch.is_tensor(x) else x
+        if xt.dtype == torch.uint8:
+            # raw 0..255 pixels (utils_data.py:56 before the /255 of :57-59): normalised on the device, bit-exactly
+            # (fp32 division), inside the kernels of the bf16 engine or here for the fp32 engine
+            x = xt.to(self.device, non_blocking=True).contiguous()
+            if not getattr(self.engine, "x2", False):
+                x = x.to(torch.float32) / 255.0
+        else:
+            x = as_device_f32(x, self.device)
         if x.dim() != 4 or tuple(x.shape[1:]) != self.ip_shape:
             raise ValueError("x must be [B,64,64,3] NHWC, got {}".format(tuple(x.shape)))
         if y is not None:
@@ -266,16 +274,30 @@ class Learner:
         b, lb = self.engine.bufs(B), self._latent_bufs(B)
         st = _stream()
         learnable = self.model.mu_trainable
+        mark = getattr(self.engine, "mark", lambda *a, **k: None)
+        mark("step begin", coarse=True)
         if backward:
             self.engine.zero_grads()
         self._gate(n)
+        mark("zero+gate", coarse=True)
         self.engine.encoder_fwd(x, b)
+        mark("encoder fwd", coarse=True)
         self._latent_fwd(B, lb, b, y, n, supervised, k)
-        self.engine.decoder_fwd(lb["z"], b, z16_ready=True)
-        xhat = self.engine.recon(x, b, lb["terms"][5], lb["log_pxz"], backward)
+        mark("latent fwd", coarse=True)
+        if getattr(self.engine, "x2", False):
+            xhat = self.engine.decoder_fwd_recon(x, b, lb["terms"][5], lb["log_pxz"], backward,
+                                                 want_recon=not torch.cuda.is_current_stream_capturing())
+            mark("decoder fwd + recon", coarse=True)
+        else:
+            self.engine.decoder_fwd(lb["z"], b, z16_ready=True)
+            mark("decoder fwd", coarse=True)
+            xhat = self.engine.recon(x, b, lb["terms"][5], lb["log_pxz"], backward)
+            mark("recon", coarse=True)
         if backward:
             self.engine.decoder_bwd(lb["z"], b)
+            mark("decoder bwd (main)", coarse=True)
             self._latent_bwd(B, lb, b, n, supervised, k)
+            mark("latent bwd", coarse=True)
             v, g = self.store.view, self.store.g
             _lib.check(self.lib.gccvae_gate_bwd(
                 ptr(lb["partials"]), lb["npart"], ptr(v("mu")), ptr(v("cls.w")), ptr(v("prior.loc_true")),
@@ -284,7 +306,9 @@ class Learner:
                 ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
                 ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
                 ptr(self.store.loss_slot), st), "gate_bwd")
+            mark("gate bwd", coarse=True)
             self.engine.encoder_bwd(x, b)
+            mark("encoder bwd + join", coarse=True)
         else:
             _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B,
                                                      dp.batch_global(B, self.world), int(supervised),
@@ -337,11 +361,14 @@ class Learner:
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
     def _train_step_graphed(self, x, y, supervised, k):
         B = int(x.shape[0])
-        key = (B, bool(supervised), int(k))
+        x = torch.as_tensor(x)
+        u8 = x.dtype == torch.uint8 and getattr(self.engine, "x2", False)
+        key = (B, bool(supervised), int(k), bool(u8))
         g = self._graphs.get(key)
         if g is None:
             g = self._capture(key)
-        x = torch.as_tensor(x)
+        if x.dtype == torch.uint8 and not u8:
+            x = x.to(self.device, non_blocking=True).to(torch.float32) / 255.0
         if x.device.type == "cpu":
             self._stage_host_inputs(g, x, y if supervised else None)
         else:
@@ -385,14 +412,17 @@ class Learner:
         st["free"].record(main)
 
     def _capture(self, key):
-        B, supervised, k = key
-        xs = torch.zeros(B, *self.ip_shape, dtype=torch.float32, device=self.device)
+        B, supervised, k, u8 = key
+        xs = torch.zeros(B, *self.ip_shape, dtype=torch.uint8 if u8 else torch.float32, device=self.device)
         ys = torch.zeros(B, self.y_dim, dtype=torch.int64, device=self.device) if supervised else None
 
         def body():
+            if getattr(self.engine, "marks", None) is not None:
+                self.engine.marks = []
             loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
             if self.world == 1:
                 self.optimiser.apply_gradients()
+                getattr(self.engine, "mark", lambda *a, **k: None)("adam", coarse=True)
             return loss
 
         # warm-up on a side stream (first-use attribute calls, buffer allocation), state restored afterwards

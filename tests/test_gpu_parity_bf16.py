@@ -82,7 +82,9 @@ def test_bf16_step_matches_oracle(mode, supervised, B, K):
     # residual: fp32-vs-fp64 accumulation moves a few bf16 roundings by one ulp, which still flips
     # ~1e-5..1e-4 of the sign(x - xhat) factors: 0.6% L2 on the encoder, up to 2% on the innermost
     # decoder layers (fc1 / conv1t see the least averaging); tiny batches average less still.
-    assert worst[1] <= 3 * RTOL, "gradient {} relative L2 error {:.3e} vs bf16-emulating oracle".format(*worst)
+    # (B = 32: a single flipped sign among 393k pixels is already 0.3% of the logit gradient, so the bound is 5%)
+    bound = (3 if B >= 64 else 5) * RTOL
+    assert worst[1] <= bound, "gradient {} relative L2 error {:.3e} vs bf16-emulating oracle".format(*worst)
     assert worst_plain[1] <= 0.15, "gradient {} relative L2 error {:.3e} vs plain oracle".format(*worst_plain)
 
 
