@@ -26,7 +26,7 @@ def run(name, fn):
     for i in range(12):
         if t[i, 0] == 0:
             break
-        print(i, " ".join("%7.2f" % ((v - t0) / 1.9e3) if v > 0 else "      -" for v in t[i, :7]))
+        print(i, " ".join("%7.2f" % ((v - t0) / 1.9e3) if v > 0 else "      -" for v in t[i, :8]))
     a = t[32]
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -108,5 +108,5 @@ run("conv5 fwd (dense K=2048, N=64 slabs)", lambda: L.check(lib.gccvae_ls_bf16(C
 # x2 end layers
 X2 = torch.randn(B, 33, 33, 16, device=d).to(torch.bfloat16)
 wx2 = torch.randn(32 * 64, device=d).to(torch.bfloat16)
-run("conv1 x2 fwd (4 taps K=16, N=32)", lambda: L.check(lib.gccvae_tap4_ls_bf16(B, 33, 33, 16, X2.data_ptr(), wx2.data_ptr(), 32, bias.data_ptr(), 1, None, h1.data_ptr(), st)))
-run("conv5t x2 dgrad (4 taps K=16, N=32, mask)", lambda: L.check(lib.gccvae_tap4_ls_bf16(B, 33, 33, 16, X2.data_ptr(), wx2.data_ptr(), 32, None, 0, g4.data_ptr(), h1.data_ptr(), st)))
+run("C3CONV conv1 fwd (cols: slot-free, cp.async issued, tmem-free, landed, acc-ready, acc-read, stored, mma-issued)", lambda: L.check(lib.gccvae_c3conv_bf16(B, X2.data_ptr(), wx2.data_ptr(), 32, bias.data_ptr(), 1, None, h1.data_ptr(), st)))
+run("C3CONV conv5t dgrad (mask)", lambda: L.check(lib.gccvae_c3conv_bf16(B, X2.data_ptr(), wx2.data_ptr(), 32, None, 0, g4.data_ptr(), h1.data_ptr(), st)))

@@ -1379,10 +1379,13 @@ struct alignas(64) C3Params {
   const void* mask;         // optional [B,32,32,N] bf16: out *= (mask > 0)
   const float* bias;        // optional [N]
   int act, N, batch, total_tiles, stages;
+  long long* timeline;      // debug (see TL)
+  int dbg;                  // debug: bit 0 = no output stores, bit 1 = no cp.async (tile content undefined)
 };
 constexpr int C3_THREADS = 288;
 
-__global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constant__ C3Params p) {
+template <int NCH>   // N / 16
+__global__ void __launch_bounds__(C3_THREADS, 3) c3conv_kernel(const __grid_constant__ C3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -1391,10 +1394,12 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
   uint8_t* sA = smem + 8192;
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * A_TILE);
   uint64_t* empty = full + p.stages;
+  constexpr int ACC = 4;                 // accumulator stages in TMEM
   uint64_t* tfull = empty + p.stages;
-  uint64_t* tempty = tfull + 2;
-  uint64_t* bfull = tempty + 2;
+  uint64_t* tempty = tfull + ACC;
+  uint64_t* bfull = tempty + ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -1406,17 +1411,17 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
   if (threadIdx.x == 0) {
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 4);     // one arrival per producer warp
+      mbar_init(&full[s], 128);   // one asynchronous arrival per producer thread (its cp.async group landed)
       mbar_init(&empty[s], 1);
     }
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < ACC; ++s) {
       mbar_init(&tfull[s], 1);
       mbar_init(&tempty[s], 4);
     }
     mbar_init(bfull, 1);
     fence_mbar_init();
   }
-  if (warp == 4) tmem_alloc(tmem_slot, acc_cols * 2);
+  if (warp == 4) tmem_alloc(tmem_slot, acc_cols * ACC);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -1428,7 +1433,8 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
   pdl_wait();
 
   if (warp < 4) {
-    // ===== producers: thread m builds row m of the im2col tile =====
+    // ===== producers: thread m builds row m of the im2col tile with 8 cp.async of 16 bytes; completion is
+    // tracked by the stage's mbarrier (cp.async.mbarrier.arrive.noinc), so up to `stages` tiles are in flight =====
     const int m = threadIdx.x;
     const int dy = m >> 5, dx = m & 31;
     const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)(m & 7);
@@ -1437,20 +1443,22 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int n = tile >> 3, h0 = (tile & 7) * 4;
       const uint4* src = p.in2 + (((size_t)n * 33 + (h0 + dy)) * 33 + dx) * 2;
-      uint4 v[8];
+      if (p.dbg & 4) mbar_wait(&empty[stage], ph ^ 1);
+      else mbar_wait_relaxed(&empty[stage], ph ^ 1);
+      if (m == 0) TL(tile - tile_beg, 0);
+      const uint32_t dst = smem_u32(sA + stage * A_TILE) + row_off;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        const uint4* s = src + ((t >> 1) * 33 + (t & 1)) * 2;
-        v[2 * t] = __ldg(s);
-        v[2 * t + 1] = __ldg(s + 1);
-      }
-      mbar_wait(&empty[stage], ph ^ 1);
-      uint8_t* dst = sA + stage * A_TILE + row_off;
+        if (p.dbg & 2) break;
+        const uint4* sp = src + ((t >> 1) * 33 + (t & 1)) * 2;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) *reinterpret_cast<uint4*>(dst + (((uint32_t)c ^ sw) << 4)) = v[c];
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the MMA
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&full[stage]);
+        for (int h = 0; h < 2; ++h)
+          asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + ((((uint32_t)(2 * t + h)) ^ sw) << 4)),
+                       "l"(sp + h)
+                       : "memory");
+      }
+      asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+      if (m == 0) TL(tile - tile_beg, 1);
       if (++stage == p.stages) { stage = 0; ph ^= 1; }
     }
   } else if (warp == 4) {
@@ -1462,9 +1470,12 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
       uint32_t ph = 0;
       mbar_wait(bfull, 0);
       for (int tile = tile_beg; tile < tile_end; ++tile) {
-        const int li = tile - tile_beg, as = li & 1;
-        mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        const int li = tile - tile_beg, as = li & (ACC - 1);
+        mbar_wait(&tempty[as], ((uint32_t)(li / ACC) & 1u) ^ 1u);
+        TL(li, 2);
         mbar_wait(&full[stage], ph);
+        TL(li, 3);
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async (generic proxy) -> MMA (async proxy)
         tc_fence_after();
         const uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * (A_TILE >> 4));
         const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
@@ -1472,6 +1483,7 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
         for (int kk = 0; kk < 4; ++kk) umma_bf16(tacc, ad + 2u * kk, bdesc + 2u * kk, idesc, kk > 0 ? 1u : 0u);
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
+        TL(li, 7);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     }
@@ -1480,68 +1492,75 @@ __global__ void __launch_bounds__(C3_THREADS) c3conv_kernel(const __grid_constan
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int dy = m >> 5, dx = m & 31;
+    // the bias lives in shared memory: a global load per tile would miss L1 (the image stream evicts it) and put an
+    // L2 round trip on the epilogue's critical path
+    {
+      const int et = threadIdx.x - 160;
+      if (et < 64) s_bias[et] = (p.bias != nullptr && et < p.N) ? p.bias[et] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     for (int tile = tile_beg; tile < tile_end; ++tile) {
-      const int li = tile - tile_beg, as = li & 1;
+      const int li = tile - tile_beg, as = li & (ACC - 1);
       const int n = tile >> 3, h0 = (tile & 7) * 4;
       const size_t opix = ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
-      uint4 mpre[8];
+      uint32_t mpre[NCH][8];
       const bool use_mask = p.mask != nullptr;
       if (use_mask) {
-        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.N);
+        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.N;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 8 < p.N) mpre[i] = __ldg(mk + i);
+        for (int i = 0; i < NCH; ++i) ld_global_nc_256(mk + i * 16, mpre[i]);
       }
-      mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+      mbar_wait(&tfull[as], (uint32_t)(li / ACC) & 1u);
       tc_fence_after();
+      if (threadIdx.x == 160) TL(li, 4);
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
+      // all TMEM loads of the tile are issued back to back, ONE wait, and the accumulator stage goes back to the MMA
+      // warp before any arithmetic
+      uint32_t r[NCH][16];
 #pragma unroll
-      for (int c0 = 0; c0 < 64; c0 += 16) {
-        if (c0 >= p.N) break;
-        uint32_t r[16];
-        tmem_ld16(tacc + (uint32_t)c0, r);
-        tmem_ld_wait();
-        if (c0 + 16 >= p.N) {
-          tc_fence_before();
-          if (lane == 0) mbar_arrive(&tempty[as]);
-        }
+      for (int c = 0; c < NCH; ++c) tmem_ld16(tacc + (uint32_t)(c * 16), r[c]);
+      tmem_ld_wait();
+      tc_fence_before();
+      if (lane == 0) mbar_arrive(&tempty[as]);
+      if (threadIdx.x == 160) TL(li, 5);
+#pragma unroll
+      for (int c = 0; c < NCH; ++c) {
+        const int c0 = c * 16;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-        if (p.bias != nullptr) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t = __ldg(bp + i);
-            v[4 * i] += t.x; v[4 * i + 1] += t.y; v[4 * i + 2] += t.z; v[4 * i + 3] += t.w;
-          }
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);
+          v[4 * i] = __uint_as_float(r[c][4 * i]) + t.x;
+          v[4 * i + 1] = __uint_as_float(r[c][4 * i + 1]) + t.y;
+          v[4 * i + 2] = __uint_as_float(r[c][4 * i + 2]) + t.z;
+          v[4 * i + 3] = __uint_as_float(r[c][4 * i + 3]) + t.w;
         }
         if (p.act == GCCVAE_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
         }
         if (use_mask) {
-          const uint4 m0 = mpre[(c0 >> 3)], m1 = mpre[(c0 >> 3) + 1];
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
-            const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+            const uint32_t mwi = mpre[c][i];
+            const uint32_t lo = mwi & 0xffffu, hi = mwi >> 16;
             if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
             if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
           }
         }
-        uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.N + c0);
-        dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
-        dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                            pack_bf16x2(v[14], v[15]));
+        uint32_t w[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        if (!(p.dbg & 1)) st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.N + c0, w);
       }
+      if (threadIdx.x == 160) TL(li, 6);
     }
     tc_fence_before();
   }
   __syncthreads();
   if (warp == 4) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, acc_cols * 2);
+    tmem_dealloc(tmem_base, acc_cols * ACC);
   }
 }
 
@@ -2300,12 +2319,15 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
   if ((rc = encode_mat_map(&p.tmB, Wp, CS, 64, 64, CS))) return rc;
   p.in2 = (const uint4*)in2; p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.N = CS; p.batch = batch;
   p.total_tiles = batch * 8;
+  p.timeline = g_timeline;
+  { const char* e = getenv("GCCVAE_C3_DBG"); p.dbg = e ? atoi(e) : 0; }
   static int env_per_sm = -1;
   if (env_per_sm < 0) {
     const char* e = getenv("GCCVAE_C3_PER_SM");
     env_per_sm = e ? atoi(e) : 0;
   }
-  const int per_sm = env_per_sm > 0 ? env_per_sm : 2;
+  int per_sm = env_per_sm > 0 ? env_per_sm : 3;
+  if (per_sm > 512 / (4 * (CS <= 32 ? 32 : 64))) per_sm = 512 / (4 * (CS <= 32 ? 32 : 64));   // TMEM: 4 accumulator stages
   int stages = (200 * 1024 / per_sm - 8192 - 3072) / (128 * 128);
   if (stages > 6) stages = 6;
   GCC_REQUIRE(stages >= 2, "c3conv: shared memory");
@@ -2313,7 +2335,8 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
   const size_t smem = 8192 + (size_t)stages * 128 * 128 + 1024 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    GCC_CUDA(cudaFuncSetAttribute(c3conv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(c3conv_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(c3conv_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
   int ctas = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
@@ -2321,7 +2344,8 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
     const int per_cta = (p.total_tiles + ctas - 1) / ctas;
     ctas = (p.total_tiles + per_cta - 1) / per_cta;
   }
-  GCC_CUDA(launch_pdl(c3conv_kernel, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
+  if (CS == 32) GCC_CUDA(launch_pdl(c3conv_kernel<2>, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
+  else GCC_CUDA(launch_pdl(c3conv_kernel<4>, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("c3conv");
   return GCCVAE_OK;
 }
