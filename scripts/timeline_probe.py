@@ -110,3 +110,12 @@ X2 = torch.randn(B, 33, 33, 16, device=d).to(torch.bfloat16)
 wx2 = torch.randn(32 * 64, device=d).to(torch.bfloat16)
 run("C3CONV conv1 fwd (cols: slot-free, cp.async issued, tmem-free, landed, acc-ready, acc-read, stored, mma-issued)", lambda: L.check(lib.gccvae_c3conv_bf16(B, X2.data_ptr(), wx2.data_ptr(), 32, bias.data_ptr(), 1, None, h1.data_ptr(), st)))
 run("C3CONV conv5t dgrad (mask)", lambda: L.check(lib.gccvae_c3conv_bf16(B, X2.data_ptr(), wx2.data_ptr(), 32, None, 0, g4.data_ptr(), h1.data_ptr(), st)))
+
+w8 = torch.randn(16 * 128, device=d).to(torch.bfloat16) * 0.05
+xf = torch.rand(B, 64, 64, 3, device=d)
+coef = -torch.rand(B, device=d) / B
+lpx = torch.empty(B, device=d)
+D2 = torch.empty(B, 33, 33, 16, dtype=torch.bfloat16, device=d)
+db3 = torch.zeros(3, device=d)
+run("CTR conv5t fwd + recon fused (cols: slot-free, tma-issued, tmem-free, landed, acc-ready, acc-read, stored, mma-issued)",
+    lambda: L.check(lib.gccvae_convt_recon_bf16(B, g4.data_ptr(), w8.data_ptr(), b3.data_ptr(), xf.data_ptr(), 0, coef.data_ptr(), lpx.data_ptr(), D2.data_ptr(), None, db3.data_ptr(), st)))

@@ -1198,6 +1198,7 @@ struct alignas(64) CtrParams {
   float* xhat;         // optional [B,64,64,3] fp32 reconstruction
   float* db;           // optional [3] += sum of dlogit (bias gradient of conv5t)
   int batch, total_tiles, stages;
+  long long* timeline;
 };
 
 template <typename XT>
@@ -1252,10 +1253,12 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         const int n = tile / 9, r = tile - n * 9, i0 = (r / 3) * 11, j0 = (r % 3) * 11;
         mbar_wait(&empty[stage], ph ^ 1);
+        TL(tile - tile_beg, 0);
         mbar_expect_tx(&full[stage], 4 * A_BOX);
 #pragma unroll
         for (int t = 0; t < 4; ++t)
           tma_load_4d(sA + stage * STAGE + t * A_SLOT, &p.tmA, &full[stage], 0, j0 - (t & 1), i0 - (t >> 1), n);
+        TL(tile - tile_beg, 1);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     }
@@ -1270,8 +1273,10 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         const int li = tile - tile_beg, as = li & 1;
         mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
+        TL(li, 2);
         mbar_wait(&full[stage], ph);
         tc_fence_after();
+        TL(li, 3);
         const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * (STAGE >> 4));
         const uint32_t tacc = tmem_base + (uint32_t)as * 32u;
 #pragma unroll
@@ -1283,6 +1288,7 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
+        TL(li, 7);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
       }
     }
@@ -1294,61 +1300,85 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
     const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1), b2 = __ldg(p.bias + 2);
     const XT* xs = reinterpret_cast<const XT*>(p.x);
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+    // The image pixels of a block do not depend on the accumulator and come straight from HBM: they are fetched one
+    // tile AHEAD (register double buffer), so their latency hides behind the arithmetic of the current tile.
+    float xn[12];
+    auto fetch_x = [&](int tile, float (&xv)[12]) {
+      const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
+        const bool okq = row_ok && (unsigned)Y < 64u && (unsigned)X < 64u;
+        xv[3 * qq] = xv[3 * qq + 1] = xv[3 * qq + 2] = 0.0f;
+        if (okq) {
+          const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
+          xv[3 * qq] = load_px<XT>(px); xv[3 * qq + 1] = load_px<XT>(px + 1); xv[3 * qq + 2] = load_px<XT>(px + 2);
+        }
+      }
+    };
+    if (tile_beg < tile_end) fetch_x(tile_beg, xn);
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int li = tile - tile_beg, as = li & 1;
       const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
-      // the image pixels of this block do not depend on the accumulator: fetch them before waiting for the MMAs
       float xv[12];
 #pragma unroll
-      for (int k = 0; k < 12; ++k) xv[k] = 0.0f;
+      for (int k2 = 0; k2 < 12; ++k2) xv[k2] = xn[k2];
+      if (tile + 1 < tile_end) fetch_x(tile + 1, xn);
       bool ok[4];
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) {
         const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
         ok[qq] = row_ok && (unsigned)Y < 64u && (unsigned)X < 64u;
-        if (ok[qq]) {
-          const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
-          xv[3 * qq] = load_px<XT>(px); xv[3 * qq + 1] = load_px<XT>(px + 1); xv[3 * qq + 2] = load_px<XT>(px + 2);
-        }
       }
       const float cb = p.coef != nullptr ? __ldg(p.coef + n) : 0.0f;
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
       tc_fence_after();
+      if (threadIdx.x == 64) TL(li, 4);
       uint32_t acc[16];
       tmem_ld16(tmem_base + (uint32_t)as * 32u + ((uint32_t)(q * 32) << 16), acc);
       tmem_ld_wait();
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty[as]);
+      if (threadIdx.x == 64) TL(li, 5);
+      // branch-free arithmetic: 12 independent sigmoid / sign chains the scheduler can interleave
+      float xh[12], g[12];
       float l1 = 0.0f;
-      uint32_t w[8];
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        float g[3];
-#pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          const float logit = __uint_as_float(acc[4 * qq + c]) + (c == 0 ? b0 : (c == 1 ? b1 : b2));
-          const float xh = __fdividef(1.0f, 1.0f + __expf(-logit));
-          const float e = xv[3 * qq + c] - xh;
-          g[c] = ok[qq] ? cb * (float)((e > 0.f) - (e < 0.f)) * xh * (1.0f - xh) : 0.0f;
-          if (ok[qq]) {
-            l1 += fabsf(e);
-            if (p.xhat != nullptr) {
-              const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
-              p.xhat[(((size_t)n * 64 + Y) * 64 + X) * 3 + c] = xh;
-            }
-          }
-        }
-        d0 += g[0]; d1 += g[1]; d2 += g[2];
-        w[2 * qq] = pack_bf16x2(g[0], g[1]);
-        w[2 * qq + 1] = pack_bf16x2(g[2], 0.0f);
+      for (int k2 = 0; k2 < 12; ++k2) {
+        const int qq = k2 / 3, c = k2 % 3;
+        // rows 121..127 of the MMA tile are never loaded (stale shared memory, possibly NaN patterns): zero them
+        const float a = row_ok ? __uint_as_float(acc[4 * qq + c]) : 0.0f;
+        const float logit = a + (c == 0 ? b0 : (c == 1 ? b1 : b2));
+        xh[k2] = __fdividef(1.0f, 1.0f + __expf(-logit));
       }
+#pragma unroll
+      for (int k2 = 0; k2 < 12; ++k2) {
+        const float okf = ok[k2 / 3] ? 1.0f : 0.0f;
+        const float e = xv[k2] - xh[k2];
+        const float sgn = (e > 0.0f ? 1.0f : 0.0f) - (e < 0.0f ? 1.0f : 0.0f);
+        l1 = fmaf(okf, fabsf(e), l1);
+        g[k2] = okf * cb * sgn * xh[k2] * (1.0f - xh[k2]);
+      }
+      d0 += g[0] + g[3] + g[6] + g[9];
+      d1 += g[1] + g[4] + g[7] + g[10];
+      d2 += g[2] + g[5] + g[8] + g[11];
       if (p.D2 != nullptr && row_ok) {
         uint4* dst = p.D2 + (((size_t)n * 33 + i) * 33 + j) * 2;
-        dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
-        dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+        dst[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], 0.0f), pack_bf16x2(g[3], g[4]), pack_bf16x2(g[5], 0.0f));
+        dst[1] = make_uint4(pack_bf16x2(g[6], g[7]), pack_bf16x2(g[8], 0.0f), pack_bf16x2(g[9], g[10]), pack_bf16x2(g[11], 0.0f));
+      }
+      if (p.xhat != nullptr) {   // optional fp32 reconstruction (tests / module API), off the training path
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq)
+          if (ok[qq]) {
+            const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
+            float* dstx = p.xhat + (((size_t)n * 64 + Y) * 64 + X) * 3;
+            dstx[0] = xh[3 * qq]; dstx[1] = xh[3 * qq + 1]; dstx[2] = xh[3 * qq + 2];
+          }
       }
       l1 = warp_sum(l1);
       if (lane == 0 && l1 != 0.0f) atomicAdd(p.log_pxz + n, -l1);
+      if (threadIdx.x == 64) TL(li, 6);
     }
     if (p.db != nullptr) {
       d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
@@ -1499,16 +1529,28 @@ __global__ void __launch_bounds__(C3_THREADS, 3) c3conv_kernel(const __grid_cons
       if (et < 64) s_bias[et] = (p.bias != nullptr && et < p.N) ? p.bias[et] : 0.0f;
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    // the ReLU mask does not depend on the accumulator: it is fetched one tile ahead (register double buffer)
+    const bool use_mask = p.mask != nullptr;
+    uint32_t mnext[NCH][8];
+    auto fetch_mask = [&](int tile, uint32_t (&mm)[NCH][8]) {
+      const int n = tile >> 3, h0 = (tile & 7) * 4;
+      const size_t opix = ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
+      const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.N;
+#pragma unroll
+      for (int i = 0; i < NCH; ++i) ld_global_nc_256(mk + i * 16, mm[i]);
+    };
+    if (use_mask && tile_beg < tile_end) fetch_mask(tile_beg, mnext);
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int li = tile - tile_beg, as = li & (ACC - 1);
       const int n = tile >> 3, h0 = (tile & 7) * 4;
       const size_t opix = ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
       uint32_t mpre[NCH][8];
-      const bool use_mask = p.mask != nullptr;
       if (use_mask) {
-        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.N;
 #pragma unroll
-        for (int i = 0; i < NCH; ++i) ld_global_nc_256(mk + i * 16, mpre[i]);
+        for (int i = 0; i < NCH; ++i)
+#pragma unroll
+          for (int j = 0; j < 8; ++j) mpre[i][j] = mnext[i][j];
+        if (tile + 1 < tile_end) fetch_mask(tile + 1, mnext);
       }
       mbar_wait(&tfull[as], (uint32_t)(li / ACC) & 1u);
       tc_fence_after();
@@ -2230,6 +2272,11 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   p.N = CS;
   p.out.n_seg = 1; p.out.m_valid = 64;
   p.out.seg[0].col0 = 0; p.out.seg[0].ncols = CS; p.out.seg[0].ld = CS; p.out.seg[0].dst = dW;
+  if (g_colsum != nullptr && g_colsum_mod < 0) {   // armed by gccvae_next_launch_colsum(ptr, n, -1): sums of S
+    p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_side = -g_colsum_mod;
+    g_colsum = nullptr;
+    GCC_REQUIRE(p.colsum_side == 1 && p.colsum_n > 0 && p.colsum_n <= CS, "tap4_wg: fused bias gradient: S side only");
+  }
   const int groups = (batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
   int splits = 148 * 2;
@@ -2280,6 +2327,7 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   if ((rc = encode_mat_map(&p.tmB, Wp8, 16, 128, 32, 16))) return rc;
   p.x = x; p.x_u8 = x_u8; p.bias = bias; p.coef = coef; p.log_pxz = log_pxz; p.D2 = (uint4*)D2; p.xhat = xhat; p.db = db;
   p.batch = batch; p.total_tiles = batch * 9;
+  p.timeline = g_timeline;
   const int per_sm = 3;
   int stages = (200 * 1024 / per_sm - 4096 - 3072) / (4 * 8192);
   if (stages > 4) stages = 4;

@@ -84,6 +84,8 @@ class EngineTC(Engine):
         self.side2 = (torch.cuda.Stream(device=dev)
                       if self.side is not None and os.environ.get("GCCVAE_BGRAD_STREAM", "side") != "main" else None)
         self.bias_in_wgrad = os.environ.get("GCCVAE_BIAS_IN_WGRAD", "0") != "0"
+        self.wg_rr = os.environ.get("GCCVAE_WG_RR", "0") != "0"   # weight gradients alternate between both side streams
+        self._rr = 0
         self._deferred_bias = []
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
         # debug timeline (GCCVAE_MARKERS=1: a globaltimer marker kernel after every op, 2: only at segment ends)
@@ -245,10 +247,14 @@ class EngineTC(Engine):
             fn()
             self._flush_deferred_bias()
             return
-        self.side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(self.side):
+        side = self.side
+        if self.wg_rr and self.side2 is not None:
+            side = (self.side, self.side2)[self._rr & 1]
+            self._rr += 1
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
             fn()
-        self._flush_deferred_bias()      # (main stream) column-sum passes requested by fn's _arm_wgrad_bias
+        self._flush_deferred_bias()      # column-sum passes requested by fn's _arm_wgrad_bias
 
     def join_side(self):
         if self.side is not None:
