@@ -1415,7 +1415,7 @@ struct alignas(64) C3Params {
 constexpr int C3_THREADS = 288;
 
 template <int NCH>   // N / 16
-__global__ void __launch_bounds__(C3_THREADS, 3) c3conv_kernel(const __grid_constant__ C3Params p) {
+__global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_constant__ C3Params p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
@@ -2374,7 +2374,8 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
     const char* e = getenv("GCCVAE_C3_PER_SM");
     env_per_sm = e ? atoi(e) : 0;
   }
-  int per_sm = env_per_sm > 0 ? env_per_sm : 3;
+  int per_sm = env_per_sm > 0 ? env_per_sm : 2;
+  if (per_sm > 2) per_sm = 2;   // __launch_bounds__(288, 2): no register spills in the epilogue
   if (per_sm > 512 / (4 * (CS <= 32 ? 32 : 64))) per_sm = 512 / (4 * (CS <= 32 ? 32 : 64));   // TMEM: 4 accumulator stages
   int stages = (200 * 1024 / per_sm - 8192 - 3072) / (128 * 128);
   if (stages > 6) stages = 6;
