@@ -113,7 +113,8 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   uint64_t* tfull = empty + p.stages;   // [2] accumulator stage ready for the epilogue
   uint64_t* tempty = tfull + 2;         // [2] accumulator stage drained by the epilogue
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
-  float* s_col = reinterpret_cast<float*>(tmem_slot + 4);   // [256] per-CTA column sums (bias gradient)
+  float* s_col = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [256] column sums
+  float* s_bias = s_col + 256;                                // [256] bias (zero beyond bias_n)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -250,6 +251,12 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     const int q = warp & 3;
     const int m = q * 32 + lane;
     const int dx = m % p.BW, dy = (m / p.BW) % p.BH, dn = m / (p.BW * p.BH);
+    // bias -> shared memory once per CTA (a global load per item would sit on the epilogue's critical path)
+    {
+      const int nb = p.bias == nullptr ? 0 : (p.bias_mod < p.bias_n ? p.bias_mod : p.bias_n);
+      for (int i = threadIdx.x - 64; i < 256; i += 128) s_bias[i] = i < nb ? p.bias[i] : 0.0f;
+      asm volatile("bar.sync 1, 128;" ::: "memory");
+    }
     // bias-gradient column sums: with a single N slab of <= 64 columns every thread keeps running sums of its own
     // row in registers across all items and the cross-lane reduction happens once, after the loop
     float cacc[COLSUM ? 4 : 1][16];
@@ -273,13 +280,13 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
       // the mask (ReLU derivative of the consumer) does not depend on the accumulator: fetch the first
       // 64 channels of it BEFORE waiting for the MMAs so its latency hides behind the main loop
-      uint4 mpre[8];
+      uint32_t mpre[4][8];
       const bool use_mask = p.mask != nullptr && valid;
       if (use_mask) {
-        const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.OC + slab0);
+        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.OC + slab0;
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (i * 8 < p.N && slab0 + i * 8 < p.n_store) mpre[i] = __ldg(mk + i);
+        for (int i = 0; i < 4; ++i)
+          if (i * 16 < p.N && slab0 + i * 16 < p.n_store) ld_global_nc_256(mk + i * 16, mpre[i]);
       }
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
       tc_fence_after();
@@ -289,21 +296,8 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const int bias_base = slab0 % p.bias_mod;
       for (int c0 = 0; c0 < p.N; c0 += 16) {
         const int cg = slab0 + c0;  // global output channel of this chunk
-        // issue the bias loads first so that their latency overlaps the TMEM load
-        float bv[16];
-        const bool full_bias = p.bias != nullptr && cg + 16 <= p.bias_n;
-        if (full_bias) {
-          const float4* bp = reinterpret_cast<const float4*>(p.bias + bias_base + c0);
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const float4 t = __ldg(bp + i);
-            bv[4 * i] = t.x; bv[4 * i + 1] = t.y; bv[4 * i + 2] = t.z; bv[4 * i + 3] = t.w;
-          }
-        } else {
-#pragma unroll
-          for (int i = 0; i < 16; ++i)
-            bv[i] = (p.bias != nullptr && cg + i < p.bias_n) ? __ldg(p.bias + bias_base + c0 + i) : 0.0f;
-        }
+        // bias_base + c0 + i < 256 always: bias_mod <= 256 wraps it, otherwise n_store <= 256
+        const float* bsrc = s_bias + ((bias_base + c0) & 255);
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)c0, r);
         tmem_ld_wait();
@@ -315,7 +309,13 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
         if ((!valid && !COLSUM) || cg >= p.n_store) continue;
         float v[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + bv[i];
+        for (int i = 0; i < 4; ++i) {
+          const float4 t = *reinterpret_cast<const float4*>(bsrc + 4 * i);
+          v[4 * i] = __uint_as_float(r[4 * i]) + t.x;
+          v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + t.y;
+          v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + t.z;
+          v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + t.w;
+        }
         if (p.act == GCCVAE_ACT_RELU) {
 #pragma unroll
           for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
@@ -330,21 +330,30 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
         }
         const size_t o = opix * p.OC + cg;
         if (use_mask) {
-          uint4 m0, m1;
+          uint32_t mw[8];
           if (c0 < 64) {
             // static indexing keeps mpre[] in registers
             switch (c0 >> 4) {
-              case 0: m0 = mpre[0]; m1 = mpre[1]; break;
-              case 1: m0 = mpre[2]; m1 = mpre[3]; break;
-              case 2: m0 = mpre[4]; m1 = mpre[5]; break;
-              default: m0 = mpre[6]; m1 = mpre[7]; break;
+              case 0:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mw[i] = mpre[0][i];
+                break;
+              case 1:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mw[i] = mpre[1][i];
+                break;
+              case 2:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mw[i] = mpre[2][i];
+                break;
+              default:
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mw[i] = mpre[3][i];
+                break;
             }
           } else {
-            const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
-            m0 = __ldg(mk);
-            m1 = __ldg(mk + 1);
+            ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o, mw);
           }
-          const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
             // bf16 > 0  <=>  sign bit clear and magnitude non-zero
@@ -386,15 +395,17 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           // 3-channel image padded to 4 (decoder output): one float4 per pixel, pad channel = 0
           if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix] = make_float4(v[0], v[1], v[2], 0.0f);
         } else if (p.out_f32) {
-          float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+          float* dst = reinterpret_cast<float*>(p.out) + o;
+          uint32_t w0[8], w1[8];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+          for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(v[i]); w1[i] = __float_as_uint(v[8 + i]); }
+          st_global_256(dst, w0);
+          st_global_256(dst + 8, w1);
         } else {
-          uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-          dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                              pack_bf16x2(v[6], v[7]));
-          dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                              pack_bf16x2(v[14], v[15]));
+          uint32_t w[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + o, w);   // one full 32-byte sector per lane
         }
       }
       if (threadIdx.x == 64) TL(li, 6);
@@ -579,17 +590,17 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
       const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
       const int y = h0 + dy;
       size_t opix[2];
-      uint4 mpre[2][4];
+      uint32_t mpre[2][2][8];
       const bool use_mask = p.mask != nullptr;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int phase = half * 2 + j;
         opix[j] = ((size_t)n * p.OH + (size_t)(2 * y + (phase >> 1))) * p.OW + (2 * dx + (phase & 1));
         if (use_mask) {   // first 32 channels of the ReLU mask, fetched before the accumulator is ready
-          const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix[j] * p.OC);
+          const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix[j] * p.OC;
 #pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (i * 8 < p.n_store) mpre[j][i] = __ldg(mk + i);
+          for (int i = 0; i < 2; ++i)
+            if (i * 16 < p.n_store) ld_global_nc_256(mk + i * 16, mpre[j][i]);
         }
       }
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
@@ -626,15 +637,16 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
           }
           const size_t o = opix[j] * p.OC + c0;
           if (use_mask) {
-            uint4 m0, m1;
-            if (c0 == 0) { m0 = mpre[j][0]; m1 = mpre[j][1]; }
-            else if (c0 == 16) { m0 = mpre[j][2]; m1 = mpre[j][3]; }
-            else {
-              const uint4* mk = reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o);
-              m0 = __ldg(mk);
-              m1 = __ldg(mk + 1);
+            uint32_t mw[8];
+            if (c0 == 0) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) mw[i] = mpre[j][0][i];
+            } else if (c0 == 16) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) mw[i] = mpre[j][1][i];
+            } else {
+              ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o, mw);
             }
-            const uint32_t mw[8] = {m0.x, m0.y, m0.z, m0.w, m1.x, m1.y, m1.z, m1.w};
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
               const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
@@ -665,15 +677,17 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
           if (p.out_f32 == 2) {
             if (c0 == 0) reinterpret_cast<float4*>(p.out)[opix[j]] = make_float4(v[0], v[1], v[2], 0.0f);
           } else if (p.out_f32) {
-            float4* dst = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + o);
+            float* dst = reinterpret_cast<float*>(p.out) + o;
+            uint32_t w0[8], w1[8];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) dst[i] = make_float4(v[4 * i], v[4 * i + 1], v[4 * i + 2], v[4 * i + 3]);
+            for (int i = 0; i < 8; ++i) { w0[i] = __float_as_uint(v[i]); w1[i] = __float_as_uint(v[8 + i]); }
+            st_global_256(dst, w0);
+            st_global_256(dst + 8, w1);
           } else {
-            uint4* dst = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + o);
-            dst[0] = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
-                                pack_bf16x2(v[6], v[7]));
-            dst[1] = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
-                                pack_bf16x2(v[14], v[15]));
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + o, w);
           }
         }
       }
@@ -1820,7 +1834,7 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   int per_sm = env_per_sm > 0 ? env_per_sm : 3;
   if (per_sm > 512 / (2 * (int)acc_cols)) per_sm = 512 / (2 * (int)acc_cols);
   if (per_sm < 1) per_sm = 1;
-  const int budget = 200 * 1024 / per_sm - 3072;
+  const int budget = 200 * 1024 / per_sm - 4608;
   const int stage_target = (env_stage_kb > 0 ? env_stage_kb : 32) * 1024;
   int tps = 1;
   for (int d = 1; d <= k_iters; ++d)
@@ -1831,7 +1845,7 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   if (stages > 8) stages = 8;
   if (stages < 2) stages = 2;
   p.stages = stages;
-  const size_t smem = (size_t)stages * tps * (a_stride + b_stride) + 1024 + 256 + 1024;
+  const size_t smem = (size_t)stages * tps * (a_stride + b_stride) + 1024 + 256 + 2048 + 64;
   static bool attr_set = false;
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
