@@ -732,6 +732,9 @@ struct alignas(64) WgParams {
   // S operand (side 1: Conv2D / Dense, dout = S) or of the L operand's own-pixel taps (side 2: Conv2DTranspose)
   float* colsum;
   int colsum_side, colsum_n;
+  // x2 mode: the A operand (128 pixels x 64 (a,b,dy,dx,c4) values, 128-byte rows) is built by warps 2-5 with cp.async
+  // from the [B,33,33,16] block tensor instead of 8 TMA boxes of 32-byte rows (TMA is row-rate bound)
+  const uint4* in2;
 };
 
 __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
@@ -775,7 +778,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
     tma_prefetch_desc(&p.tmA);
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full[s], 1);
+      mbar_init(&full[s], p.in2 != nullptr ? 129 : 1);   // TMA transaction (+ one cp.async arrival per A-builder thread)
       mbar_init(&empty[s], cs_mask ? 5 : 1);   // MMA commit (+ the four column-sum warps)
     }
     mbar_init(tmem_full, 1);
@@ -799,8 +802,8 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
           const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
           const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
           mbar_wait(&empty[stage], ph ^ 1);
-          mbar_expect_tx(&full[stage], (uint32_t)(a_bytes + b_bytes));
-          for (int bl = 0; bl < p.blocks_per_mtile; ++bl) {
+          mbar_expect_tx(&full[stage], (uint32_t)((p.in2 != nullptr ? 0 : a_bytes) + b_bytes));
+          for (int bl = 0; bl < (p.in2 != nullptr ? 0 : p.blocks_per_mtile); ++bl) {
             const int bg = mtile * p.blocks_per_mtile + bl;
             const int t = bg / p.blocks_per_tap, cb = bg % p.blocks_per_tap;
             // blocks past the last tap are loaded from out-of-range images: TMA zero-fills them
@@ -825,6 +828,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         uint32_t ph = 0;
         for (int it = 0; it < n_tiles; ++it) {
           mbar_wait(&full[stage], ph);
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async-built A tile -> async proxy
           tc_fence_after();
           const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a16), bd = bd0 + (uint64_t)((uint32_t)stage * b16);
 #pragma unroll
@@ -837,6 +841,32 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         }
       }
     } else {
+      if (p.in2 != nullptr) {
+        // ---- x2 mode: thread m builds row m (one pixel, 128 bytes = four 32-byte blocks) of the A tile ----
+        const int m = threadIdx.x - 64;
+        const int dy = m >> 5, dx = m & 31;
+        const uint32_t row_off = (uint32_t)m * 128u, sw = (uint32_t)(m & 7);
+        int stage = 0;
+        uint32_t ph = 0;
+        for (int it = 0; it < n_tiles; ++it) {
+          const int tile = tile_beg + it;
+          const int n = tile >> 3, h0 = (tile & 7) * 4;
+          const uint4* src = p.in2 + (((size_t)n * 33 + (h0 + dy)) * 33 + dx) * 2;
+          mbar_wait_relaxed(&empty[stage], ph ^ 1);
+          const uint32_t dst = smem_u32(sA + stage * a_bytes) + row_off;
+#pragma unroll
+          for (int t = 0; t < 4; ++t) {
+            const uint4* sp = src + ((t >> 1) * 33 + (t & 1)) * 2;
+#pragma unroll
+            for (int h = 0; h < 2; ++h)
+              asm volatile("cp.async.ca.shared.global [%0], [%1], 16;" ::"r"(dst + ((((uint32_t)(2 * t + h)) ^ sw) << 4)),
+                           "l"(sp + h)
+                           : "memory");
+          }
+          asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(&full[stage])) : "memory");
+          if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        }
+      }
       if (cs_mask) {
         // ---- fused bias gradient: column sums of the staged operand tiles, straight from shared memory ----
         const bool sideS = p.colsum_side == 1;
@@ -2271,7 +2301,16 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   GCC_REQUIRE(CS % 32 == 0 && CS <= 256, "tap4_wg: CS=%d unsupported (multiple of 32, <= 256)", CS);
   WgParams p;
   memset(&p, 0, sizeof(p));
-  p.kcA = 16; p.blocks_per_tap = 1; p.blocks_per_mtile = 8; p.taps = 4; p.c4_rows = 2;
+  static int env_tma = -1;
+  if (env_tma < 0) { const char* e = getenv("GCCVAE_TAP4_WG_TMA"); env_tma = e ? atoi(e) : 0; }
+  if (!env_tma) {
+    // A tile built by the (otherwise idle) epilogue warps: one 128-byte row per pixel, SWIZZLE_128B, which is an
+    // MN-major operand with M = 64 (a,b,dy,dx,c4); the instruction's rows 64..127 come from the unused second slab
+    p.in2 = (const uint4*)in2;
+    p.kcA = 64; p.blocks_per_tap = 1; p.blocks_per_mtile = 2; p.taps = 1; p.c4_rows = 2;
+  } else {
+    p.kcA = 16; p.blocks_per_tap = 1; p.blocks_per_mtile = 8; p.taps = 4; p.c4_rows = 2;
+  }
   p.kcB = (CS % 64 == 0) ? 64 : 32;
   p.b_loads = CS / p.kcB;
   p.swzA = umma_swizzle_for(p.kcA * 2);
@@ -2280,7 +2319,7 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   GCC_REQUIRE(pick_tile(32, 32, &bw, &bh, &bn) == 0, "tap4_wg: tile");
   p.a_scale = 1;
   for (int t = 0; t < 4; ++t) { p.a_dh[t] = (short)(t >> 1); p.a_dw[t] = (short)(t & 1); }
-  if ((rc = encode_act_map(&p.tmA, in2, batch, 33, 33, 16, p.kcA, bw, bh, bn, 1))) return rc;
+  if ((rc = encode_act_map(&p.tmA, in2, batch, 33, 33, 16, 16, bw, bh, bn, 1))) return rc;   // unused in x2 mode
   if ((rc = encode_act_map(&p.tmB, S, batch, 32, 32, CS, p.kcB, bw, bh, bn, 1))) return rc;
   p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = 32 / bw; p.tiles_h = 32 / bh;
   p.N = CS;
