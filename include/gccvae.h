@@ -156,8 +156,11 @@ int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, cons
 int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, int CS, const float* bias, int act, const void* mask,
                        void* out, void* stream);
 int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream);
+/* log_pxz_ready != 0: the caller has already set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32), e.g. on a side stream */
 int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp8, const float* bias, const void* x, int x_u8,
-                            const float* coef, float* log_pxz, void* D2, float* xhat, float* db, void* stream);
+                            const float* coef, float* log_pxz, void* D2, float* xhat, float* db, int log_pxz_ready,
+                            void* stream);
+int gccvae_fill_f32(float* p, long long n, float v, void* stream);
 /* S -> L "halo" kernel for 16x16 / 32x32 S planes with 32 or 64 channels and C_L <= 64: all four output-parity
  * phases per CTA from three column-shifted halo boxes (3.6x less L2 traffic than gccvae_sl_bf16), one MMA per
  * shifted view with N = 4*C_L.  Weights packed "sl9" = [9 views][4 phases][C_L padded to 16][C_S]

@@ -118,4 +118,4 @@ lpx = torch.empty(B, device=d)
 D2 = torch.empty(B, 33, 33, 16, dtype=torch.bfloat16, device=d)
 db3 = torch.zeros(3, device=d)
 run("CTR conv5t fwd + recon fused (cols: slot-free, tma-issued, tmem-free, landed, acc-ready, acc-read, stored, mma-issued)",
-    lambda: L.check(lib.gccvae_convt_recon_bf16(B, g4.data_ptr(), w8.data_ptr(), b3.data_ptr(), xf.data_ptr(), 0, coef.data_ptr(), lpx.data_ptr(), D2.data_ptr(), None, db3.data_ptr(), st)))
+    lambda: L.check(lib.gccvae_convt_recon_bf16(B, g4.data_ptr(), w8.data_ptr(), b3.data_ptr(), xf.data_ptr(), 0, coef.data_ptr(), lpx.data_ptr(), D2.data_ptr(), None, db3.data_ptr(), 0, st)))

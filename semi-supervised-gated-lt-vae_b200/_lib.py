@@ -97,7 +97,8 @@ SIGNATURES = {
     "gccvae_tap4_ls_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_c3conv_bf16": (_I, [_I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_tap4_wg_bf16": (_I, [_I, _P, _P, _I, _P, _P]),
-    "gccvae_convt_recon_bf16": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _P]),
+    "gccvae_convt_recon_bf16": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P]),
+    "gccvae_fill_f32": (_I, [_P, _LL, _F, _P]),
     "gccvae_debug_set_timeline": (None, [_P]),
     "gccvae_debug_mark": (_I, [_P, _I, _P]),
     "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),

@@ -2356,9 +2356,16 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
 //   g4 [B,32,32,32] bf16, Wp8 = pack kind 8 ([16][4][32] bf16), bias [3], x [B,64,64,3] fp32 or uint8.
 //   log_pxz[b] = -|x - xhat|_1 - 12288 ln 2.  coef != NULL: D2 [B,33,33,16] bf16 = coef[b] sign(x - xhat) xhat (1 - xhat)
 //   in x2 block form and db[3] += its sums.  xhat (optional): the reconstruction, fp32 [B,64,64,3].
+extern "C" int gccvae_fill_f32(float* p, long long n, float v, void* stream) {
+  GCC_REQUIRE(p && n > 0 && n < (1LL << 31), "fill_f32: bad args");
+  fill_kernel<<<(int)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(p, (int)n, v);
+  GCC_CHECK_LAUNCH("fill_f32");
+  return GCCVAE_OK;
+}
+
 extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp8, const float* bias, const void* x,
                                        int x_u8, const float* coef, float* log_pxz, void* D2, float* xhat, float* db,
-                                       void* stream) {
+                                       int log_pxz_ready, void* stream) {
   GCC_REQUIRE(g4 && Wp8 && bias && x && log_pxz && batch > 0, "convt_recon: null pointer");
   GCC_REQUIRE((coef == nullptr) == (D2 == nullptr), "convt_recon: coef and D2 go together");
   cudaStream_t st = (cudaStream_t)stream;
@@ -2393,8 +2400,10 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
     GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
-  fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
-  GCC_CHECK_LAUNCH("recon_fill");
+  if (!log_pxz_ready) {   // otherwise the caller pre-set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32) off the critical path
+    fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
+    GCC_CHECK_LAUNCH("recon_fill");
+  }
   int ctas = p.total_tiles < 148 * per_sm ? p.total_tiles : 148 * per_sm;
   {
     const int per_cta = (p.total_tiles + ctas - 1) / ctas;

@@ -276,13 +276,40 @@ class EngineTC(Engine):
         self.store.grad.zero_()   # the tensor-core wgrad / bias-grad kernels accumulate (split-K red.global)
 
     # ---- forward -----------------------------------------------------------------------------------------------
+    def begin_step(self, x, b, log_pxz=None):
+        """Work that depends only on the inputs and the parameters - packing the bf16 weight operands, the x2 block
+        transform of the image, pre-setting log_pxz - forked onto the two side streams, so that it overlaps the
+        gradient memset and the gate kernel on the main stream (parallel branches of the captured graph)."""
+        self._begun = False
+        if self.side is None or self.side2 is None or not self.x2:
+            return
+        B = x.shape[0]
+        main = torch.cuda.current_stream()
+        self.side.wait_stream(main)
+        with torch.cuda.stream(self.side):
+            self.pack_weights()
+        self.side2.wait_stream(main)
+        with torch.cuda.stream(self.side2):
+            u8 = int(x.dtype == torch.uint8)
+            self._run("prep_x2", (x, b["X2"]), lambda: self.lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), _stream()))
+            if log_pxz is not None:
+                _lib.check(self.lib.gccvae_fill_f32(ptr(log_pxz), B, -12288.0 * 0.6931471805599453, _stream()), "fill")
+        self._begun = True
+        self._log_pxz_ready = log_pxz is not None
+
     def encoder_fwd(self, x, b):
         B = x.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
-        self.pack_weights()
+        begun, self._begun = getattr(self, "_begun", False), False
+        if begun:
+            self.join_side()
+        else:
+            self._log_pxz_ready = False
+            self.pack_weights()
         if self.x2:
             u8 = int(x.dtype == torch.uint8)
-            self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
+            if not begun:
+                self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
             self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
                 B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU, None,
                 ptr(b["enc.conv1.out"]), st))
@@ -341,7 +368,9 @@ class EngineTC(Engine):
                   lambda: self.lib.gccvae_convt_recon_bf16(
                       B, ptr(b["dec.conv4t.out"]), ptr(self.wp["dec.conv5t.x2t"]), ptr(v("dec.conv5t.b")), ptr(x), u8,
                       ptr(coef) if backward else None, ptr(log_pxz), ptr(b["D2"]) if backward else None, ptr(xhat),
-                      ptr(self.store.g("dec.conv5t.b")) if backward else None, _stream()))
+                      ptr(self.store.g("dec.conv5t.b")) if backward else None, int(getattr(self, "_log_pxz_ready", False)),
+                      _stream()))
+        self._log_pxz_ready = False
         return xhat
 
     def recon(self, x, b, coef, log_pxz, backward):

@@ -276,6 +276,8 @@ class Learner:
         learnable = self.model.mu_trainable
         mark = getattr(self.engine, "mark", lambda *a, **k: None)
         mark("step begin", coarse=True)
+        if hasattr(self.engine, "begin_step"):
+            self.engine.begin_step(x, b, lb["log_pxz"])
         if backward:
             self.engine.zero_grads()
         self._gate(n)

@@ -78,7 +78,7 @@ def test_u8_normalisation_is_bit_exact_for_all_256_values():
     lp = torch.zeros(1, device=d)
     xh = torch.zeros(1, 64, 64, 3, device=d)
     L.check(lib.gccvae_convt_recon_bf16(1, L.ptr(g4), L.ptr(w8), L.ptr(b3), L.ptr(xi.to(d)), 1, None, L.ptr(lp), None,
-                                        L.ptr(xh), None, _stream()))
+                                        L.ptr(xh), None, 0, _stream()))
     torch.cuda.synchronize()
     ref = -(want.double() - 0.5).abs().sum() - 12288 * np.log(2.0)
     assert abs(float(lp[0]) - float(ref)) / abs(float(ref)) < 1e-6
@@ -155,7 +155,7 @@ def test_fused_conv5t_recon(u8):
     xhat = torch.full((B, 64, 64, 3), float("nan"), device=d)
     db = torch.zeros(3, device=d)
     L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), int(u8), L.ptr(coefd), L.ptr(lpx),
-                                        L.ptr(D2), L.ptr(xhat), L.ptr(db), _stream()))
+                                        L.ptr(D2), L.ptr(xhat), L.ptr(db), 0, _stream()))
     torch.cuda.synchronize()
     want_xh = torch.sigmoid(O._convT(bf(g4).double(), bf(W5).double(), b5.double(), 2, 1))
     got_xh = xhat.cpu().double()
@@ -171,7 +171,7 @@ def test_fused_conv5t_recon(u8):
     # forward-only form: no gradient outputs
     lp2 = torch.empty(B, device=d)
     L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), int(u8), None, L.ptr(lp2), None,
-                                        None, None, _stream()))
+                                        None, None, 0, _stream()))
     torch.cuda.synchronize()
     assert float((lp2 - lpx).abs().max() / lpx.abs().max()) < 1e-6
     # dgrad and wgrad of conv5t from D2
