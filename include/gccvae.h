@@ -99,7 +99,8 @@ size_t gccvae_packed_weight_elems(const gccvae_geom* g, int which);
  * kind 0: "ls"; 1: "sl" phases (k4/s2/p1); 2: plain bf16 cast of taps*CL*CS values; 3: "c4" (see below);
  * 4/5: strided copy into a zero-padded bf16 / fp32 operand (the 45-wide dense layers padded to 64 / 96);
  * 6: "sl9" packing of the halo kernel; 7/8: x2 (space-to-depth) packing of a 3-channel k4/s2/p1 kernel,
- * 7 = [CS][(a,b)][(dy,dx,c4)] (gccvae_tap4_ls_bf16), 8 = [(dy,dx,c4)][(a,b)][CS] (gccvae_convt_recon_bf16) */
+ * 7 = [CS][(a,b)][(dy,dx,c4)] (gccvae_tap4_ls_bf16), 8 = [(dy,dx,c4)][(a,b)][CS] (gccvae_convt_recon_bf16);
+ * 9: s2d packing [CS][(a,b)][(dy,dx,CL)] of a k4/s2/p1 kernel with CL input channels */
 typedef struct {
   int kind, taps, CL, CS;
   const float* W;
@@ -143,6 +144,16 @@ int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, cons
                              void* G64, float* db, void* stream);
 int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
 int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
+/* s2d storage of the stride-2 layers' L tensors (an H x W x C plane as (H/2+1) x (W/2+1) blocks of 2x2 pixels, block
+ * (i,j) = pixels (2i-1+dy, 2j-1+dx) in slot dy*2+dx, zero outside): Conv2D(k4,s2,p1) forward, Conv2DTranspose dgrad and
+ * their weight gradients gather 2x2 blocks of 4C channels (gccvae_tap4_ls_bf16 / gccvae_wg_s2d_bf16, weights packed
+ * with kind 9) instead of 16 strided taps of C channels.  These flags are OR-ed into the `act` argument of
+ * gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_sl_halo_bf16 / gccvae_tap4_ls_bf16 / gccvae_c3conv_bf16:            */
+#define GCCVAE_OUT_S2D 0x10      /* store the (bf16, spatial) output in s2d block form                          */
+#define GCCVAE_MASK_S2D 0x20     /* the mask tensor is stored in s2d block form                                 */
+#define GCCVAE_LAYOUT_FLAGS 0x30
+int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void* in2, const void* S, int CS, float* dW,
+                       void* stream);
 /* Space-to-depth ("x2") form of the 3-channel end layers (conv1 = networks.py:11,22; conv5t = :49,58; likelihood =
  * utils.py:101-105).  X2[n,i,j,(dy,dx,c4)] = x[n,2i-1+dy,2j-1+dx,c] (bf16 [B,33,33,16], zero outside the image):
  * Conv2D(k4,s2,p1) over the image is a 2x2-tap stride-1 GEMM over the blocks and Conv2DTranspose(k4,s2,same)

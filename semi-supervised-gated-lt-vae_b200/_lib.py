@@ -10,6 +10,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libgccvae.so")
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ACCUMULATE = 0, 1, 2, 0x100
+OUT_S2D, MASK_S2D = 0x10, 0x20   # layout flags OR-ed into `act` (include/gccvae.h)
 GATE_WS_FLOATS = 7 * 324 + 32
 LATENT_PARTIAL_FLOATS = 5 * 324 + 32
 
@@ -96,6 +97,7 @@ SIGNATURES = {
     "gccvae_prep_x2_bf16": (_I, [_P, _I, _I, _P, _P]),
     "gccvae_tap4_ls_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_c3conv_bf16": (_I, [_I, _P, _P, _I, _P, _I, _P, _P, _P]),
+    "gccvae_wg_s2d_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P]),
     "gccvae_tap4_wg_bf16": (_I, [_I, _P, _P, _I, _P, _P]),
     "gccvae_convt_recon_bf16": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "gccvae_fill_f32": (_I, [_P, _LL, _F, _P]),

@@ -26,6 +26,15 @@
 namespace gccvae {
 using namespace tc;
 
+// Space-to-depth ("s2d") storage of an H x W x C plane: (H/2+1) x (W/2+1) blocks of 2x2 pixels, block (i, j) holding
+// pixels (2i-1+dy, 2j-1+dx) in slot dy*2+dx (zero slots outside the plane).  s2d_slot() = index of pixel (y, x) of
+// image n in units of C channels.  A stride-2 k4/p1 gather over the plane is then a 2x2-tap stride-1 gather over the
+// blocks with 4C channels per tap: TMA rows of 4C*2 bytes instead of 16 taps of C*2 bytes with element stride 2.
+__device__ __forceinline__ size_t s2d_slot(int n, int y, int x, int H, int W) {
+  const int HB = (H >> 1) + 1, WB = (W >> 1) + 1;
+  return (((size_t)n * HB + ((y + 1) >> 1)) * WB + ((x + 1) >> 1)) * 4 + (((y + 1) & 1) * 2 + ((x + 1) & 1));
+}
+
 struct alignas(64) TapGemmParams {
   CUtensorMap tmA, tmB;
   int num_taps, chunks, KC, swz;
@@ -54,6 +63,7 @@ struct alignas(64) TapGemmParams {
   long long* timeline;  // debug: block 0 records clock64() at pipeline events [item][8] (NULL = off)
   float* colsum;        // optional: += column sums of the stored tile (bias gradient of the producer layer)
   int colsum_n, colsum_mod;
+  int out_s2d, mask_s2d;   // the output / the mask tensor is stored in s2d block form (bf16 only)
 };
 
 #define TL(item_local, slot)                                                              \
@@ -275,15 +285,18 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const int slab0 = slab * p.N;
       const int n = n0 + dn, y = h0 + dy, x = w0 + dx;
       const bool valid = n < p.batch;
-      const size_t opix =
-          ((size_t)n * p.OH + (size_t)(y * p.oys + p.oy0[phase_id])) * p.OW + (x * p.oxs + p.ox0[phase_id]);
+      const int oyy = y * p.oys + p.oy0[phase_id], oxx = x * p.oxs + p.ox0[phase_id];
+      const size_t opix_lin = ((size_t)n * p.OH + (size_t)oyy) * p.OW + oxx;
+      const size_t opix_s2d = (p.out_s2d | p.mask_s2d) ? s2d_slot(n, oyy, oxx, p.OH, p.OW) : 0;
+      const size_t opix = p.out_s2d ? opix_s2d : opix_lin;
+      const size_t mpix = p.mask_s2d ? opix_s2d : opix_lin;
       const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
       // the mask (ReLU derivative of the consumer) does not depend on the accumulator: fetch the first
       // 64 channels of it BEFORE waiting for the MMAs so its latency hides behind the main loop
       uint32_t mpre[4][8];
       const bool use_mask = p.mask != nullptr && valid;
       if (use_mask) {
-        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix * p.OC + slab0;
+        const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mpix * p.OC + slab0;
 #pragma unroll
         for (int i = 0; i < 4; ++i)
           if (i * 16 < p.N && slab0 + i * 16 < p.n_store) ld_global_nc_256(mk + i * 16, mpre[i]);
@@ -352,7 +365,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
                 break;
             }
           } else {
-            ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o, mw);
+            ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + mpix * p.OC + cg, mw);
           }
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -459,6 +472,7 @@ struct alignas(64) SlHaloParams {
   float* colsum;
   int colsum_n;
   long long* timeline;  // debug: block 0 records clock64() at pipeline events [tile][8] (NULL = off)
+  int mask_s2d;         // the mask tensor is stored in s2d block form
 };
 constexpr int HALO_THREADS = 320;
 
@@ -589,15 +603,16 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
       const int li = tile - tile_beg, as = li & 1;
       const int n = tile / p.tiles_h, h0 = (tile % p.tiles_h) * p.BH;
       const int y = h0 + dy;
-      size_t opix[2];
+      size_t opix[2], mpix[2];
       uint32_t mpre[2][2][8];
       const bool use_mask = p.mask != nullptr;
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int phase = half * 2 + j;
         opix[j] = ((size_t)n * p.OH + (size_t)(2 * y + (phase >> 1))) * p.OW + (2 * dx + (phase & 1));
+        mpix[j] = p.mask_s2d ? s2d_slot(n, 2 * y + (phase >> 1), 2 * dx + (phase & 1), p.OH, p.OW) : opix[j];
         if (use_mask) {   // first 32 channels of the ReLU mask, fetched before the accumulator is ready
-          const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + opix[j] * p.OC;
+          const __nv_bfloat16* mk = reinterpret_cast<const __nv_bfloat16*>(p.mask) + mpix[j] * p.OC;
 #pragma unroll
           for (int i = 0; i < 2; ++i)
             if (i * 16 < p.n_store) ld_global_nc_256(mk + i * 16, mpre[j][i]);
@@ -645,7 +660,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
 #pragma unroll
               for (int i = 0; i < 8; ++i) mw[i] = mpre[j][1][i];
             } else {
-              ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + o, mw);
+              ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + mpix[j] * p.OC + c0, mw);
             }
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -735,6 +750,7 @@ struct alignas(64) WgParams {
   // x2 mode: the A operand (128 pixels x 64 (a,b,dy,dx,c4) values, 128-byte rows) is built by warps 2-5 with cp.async
   // from the [B,33,33,16] block tensor instead of 8 TMA boxes of 32-byte rows (TMA is row-rate bound)
   const uint4* in2;
+  int s2d_cl;   // c4_rows == 3: channels per pixel of the s2d L operand
 };
 
 __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
@@ -926,10 +942,17 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
         tmem_ld_wait();
         // c4_rows 1: rows are (tap16, c4) -> (tap16, c3);  2: x2 rows (a, b, dy, dx, c4) -> ((2a+dy)*4 + 2b+dx, c3)
-        const int mrow = p.c4_rows == 2
-                             ? ((2 * (m >> 5) + ((m >> 3) & 1)) * 4 + 2 * ((m >> 4) & 1) + ((m >> 2) & 1)) * 3 + (m & 3)
-                             : (p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m);
-        if (m < p.out.m_valid && !(p.c4_rows && (m & 3) == 3)) {
+        //             3: s2d rows (a, b, dy, dx, c < CL) -> ((2a+dy)*4 + 2b+dx, c)   [CL = p.kcB_unused / out.cl]
+        int mrow;
+        if (p.c4_rows == 3) {
+          const int CL = p.s2d_cl, t = m / (4 * CL), r = m - t * 4 * CL, sub = r / CL, c = r - sub * CL;
+          mrow = ((2 * (t >> 1) + (sub >> 1)) * 4 + 2 * (t & 1) + (sub & 1)) * CL + c;
+        } else {
+          mrow = p.c4_rows == 2
+                     ? ((2 * (m >> 5) + ((m >> 3) & 1)) * 4 + 2 * ((m >> 4) & 1) + ((m >> 2) & 1)) * 3 + (m & 3)
+                     : (p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m);
+        }
+        if (m < p.out.m_valid && !((p.c4_rows == 1 || p.c4_rows == 2) && (m & 3) == 3)) {
 #pragma unroll
           for (int sg = 0; sg < 2; ++sg) {
             if (sg >= p.out.n_seg) break;
@@ -1141,6 +1164,17 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
         v = W[((size_t)(kh * 4 + kw) * CL + cl) * CS + cs];
       }
       out[i] = __float2bfloat16(v);
+    }
+  } else if (jb.kind == 9) {
+    // s2d packing of a k4/s2/p1 kernel W[kh,kw,CL,CS]: out[cs][(a,b)][(dy,dx,cl)], kh = 2a+dy, kw = 2b+dx
+    // (B operand of the 4-tap L->S GEMM over s2d blocks: gccvae_tap4_ls_bf16 with CB = 4 CL)
+    const int K = 16 * CL, rows_pad = (CS + 15) / 16 * 16;
+    const long long n = (long long)rows_pad * K;
+    for (long long i = i0; i < n; i += stride) {
+      const int cs = (int)(i / K), k = (int)(i % K);
+      const int t = k / (4 * CL), r = k % (4 * CL), sub = r / CL, c = r % CL;
+      const int kh = 2 * (t >> 1) + (sub >> 1), kw = 2 * (t & 1) + (sub & 1);
+      out[i] = __float2bfloat16(cs < CS ? W[((size_t)(kh * 4 + kw) * CL + c) * CS + cs] : 0.0f);
     }
   } else if (jb.kind == 7 || jb.kind == 8) {
     // x2 (space-to-depth) packing of a 3-channel k4/s2/p1 kernel W[kh,kw,3,CS]:
@@ -1453,6 +1487,7 @@ struct alignas(64) C3Params {
   const void* mask;         // optional [B,32,32,N] bf16: out *= (mask > 0)
   const float* bias;        // optional [N]
   int act, N, batch, total_tiles, stages;
+  int out_s2d;              // store the 32x32xN output in s2d block form [B,17,17,4N]
   long long* timeline;      // debug (see TL)
   int dbg;                  // debug: bit 0 = no output stores, bit 1 = no cp.async (tile content undefined)
 };
@@ -1587,7 +1622,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int li = tile - tile_beg, as = li & (ACC - 1);
       const int n = tile >> 3, h0 = (tile & 7) * 4;
-      const size_t opix = ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
+      const size_t opix = p.out_s2d ? s2d_slot(n, h0 + dy, dx, 32, 32) : ((size_t)n * 32 + (h0 + dy)) * 32 + dx;
       uint32_t mpre[NCH][8];
       if (use_mask) {
 #pragma unroll
@@ -1961,7 +1996,9 @@ extern "C" int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* W
   }
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
   p.N = n_slab; p.n_store = g->CS; p.n_slabs = g->CS / n_slab;
-  p.out = S; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
+  p.out = S; p.mask = mask; p.bias = bias; p.act = act & ~GCCVAE_LAYOUT_FLAGS; p.out_f32 = out_f32;
+  p.out_s2d = (act & GCCVAE_OUT_S2D) ? 1 : 0; p.mask_s2d = (act & GCCVAE_MASK_S2D) ? 1 : 0;
+  GCC_REQUIRE(!p.out_s2d || (out_f32 == 0 && !dense), "ls_bf16: s2d output needs a bf16 spatial output");
   p.OH = g->HS; p.OW = g->WS; p.OC = g->CS; p.oys = p.oxs = 1;
   p.batch = g->batch;
   const int groups = (g->batch + p.BN - 1) / p.BN;
@@ -2014,7 +2051,9 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
     p.OH = g->HL; p.OW = g->WL; p.OC = g->CL; p.oys = p.oxs = 2;
   }
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
-  p.out = L; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = out_f32;
+  p.out = L; p.mask = mask; p.bias = bias; p.act = act & ~GCCVAE_LAYOUT_FLAGS; p.out_f32 = out_f32;
+  p.mask_s2d = (act & GCCVAE_MASK_S2D) ? 1 : 0;
+  GCC_REQUIRE(!(act & GCCVAE_OUT_S2D), "sl_bf16: s2d output is not supported");
   p.batch = g->batch;
   const int groups = (g->batch + p.BN - 1) / p.BN;
   return launch_tapgemm(p, groups, phases, (cudaStream_t)stream, "sl_bf16");
@@ -2220,7 +2259,9 @@ extern "C" int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const vo
   if ((rc = encode_mat_map(&hp.tmB, Wp_sl9, 9LL * 4 * rows_pad, g->CS, g->CS, 4 * rows_pad))) return rc;
   hp.C = g->CS; hp.BW = bw; hp.BH = bh; hp.tiles_h = g->HS / bh;
   hp.N = rows_pad; hp.n_store = g->CL; hp.swz = umma_swizzle_for(g->CS * 2);
-  hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act; hp.out_f32 = out_f32;
+  hp.out = L; hp.mask = mask; hp.bias = bias; hp.bias_n = bias ? g->CL : 0; hp.act = act & ~GCCVAE_LAYOUT_FLAGS;
+  hp.out_f32 = out_f32; hp.mask_s2d = (act & GCCVAE_MASK_S2D) ? 1 : 0;
+  GCC_REQUIRE(!(act & GCCVAE_OUT_S2D), "sl_halo: s2d output is not supported");
   hp.OH = g->HL; hp.OW = g->WL; hp.OC = g->CL; hp.batch = g->batch;
   hp.total_tiles = g->batch * hp.tiles_h;
   hp.colsum = g_colsum; hp.colsum_n = g_colsum_n;
@@ -2287,7 +2328,8 @@ extern "C" int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void
   p.b_tap_stride = CB;
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
   p.N = CS; p.n_store = CS; p.n_slabs = 1;
-  p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.out_f32 = 0;
+  p.out = out; p.mask = mask; p.bias = bias; p.act = act & ~GCCVAE_LAYOUT_FLAGS; p.out_f32 = 0;
+  p.out_s2d = (act & GCCVAE_OUT_S2D) ? 1 : 0; p.mask_s2d = (act & GCCVAE_MASK_S2D) ? 1 : 0;
   p.OH = HS; p.OW = WS; p.OC = CS; p.oys = p.oxs = 1;
   p.batch = batch;
   const int groups = (batch + bn - 1) / bn;
@@ -2427,7 +2469,9 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
   memset(&p, 0, sizeof(p));
   int rc;
   if ((rc = encode_mat_map(&p.tmB, Wp, CS, 64, 64, CS))) return rc;
-  p.in2 = (const uint4*)in2; p.out = out; p.mask = mask; p.bias = bias; p.act = act; p.N = CS; p.batch = batch;
+  p.in2 = (const uint4*)in2; p.out = out; p.mask = mask; p.bias = bias; p.act = act & ~GCCVAE_LAYOUT_FLAGS; p.N = CS;
+  p.batch = batch; p.out_s2d = (act & GCCVAE_OUT_S2D) ? 1 : 0;
+  GCC_REQUIRE(!(act & GCCVAE_MASK_S2D), "c3conv: s2d mask is not supported");
   p.total_tiles = batch * 8;
   p.timeline = g_timeline;
   { const char* e = getenv("GCCVAE_C3_DBG"); p.dbg = e ? atoi(e) : 0; }
@@ -2458,6 +2502,62 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
   if (CS == 32) GCC_CUDA(launch_pdl(c3conv_kernel<2>, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
   else GCC_CUDA(launch_pdl(c3conv_kernel<4>, dim3(ctas, 1, 1), C3_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("c3conv");
+  return GCCVAE_OK;
+}
+
+
+// dW[kh,kw,cl,cs] (fp32, Keras layout) += gather(L)^T S for a k4/s2/p1 layer whose L operand is stored in s2d block
+// form in2 = [B, HL/2+1, WL/2+1, 4 CL] bf16; S = [B, HS, WS, CS] bf16 NHWC (HS = HL/2).  CL in {32, 64}.
+extern "C" int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void* in2, const void* S, int CS, float* dW,
+                                  void* stream) {
+  GCC_REQUIRE(in2 && S && dW && batch > 0, "wg_s2d: null pointer");
+  GCC_REQUIRE(CL == 16 || CL == 32 || CL == 64, "wg_s2d: CL=%d unsupported", CL);
+  GCC_REQUIRE(CS % 32 == 0 && CS <= 256, "wg_s2d: CS=%d unsupported (multiple of 32, <= 256)", CS);
+  WgParams p;
+  memset(&p, 0, sizeof(p));
+  const int CB = 4 * CL;
+  p.kcA = 64; p.blocks_per_tap = CB / 64; p.blocks_per_mtile = 2; p.taps = 4; p.c4_rows = 3; p.s2d_cl = CL;
+  p.kcB = (CS % 64 == 0) ? 64 : 32;
+  p.b_loads = CS / p.kcB;
+  p.swzA = umma_swizzle_for(p.kcA * 2);
+  p.swzB = umma_swizzle_for(p.kcB * 2);
+  int rc, bw, bh, bn;
+  GCC_REQUIRE(pick_tile(HS, WS, &bw, &bh, &bn) == 0, "wg_s2d: cannot tile %dx%d", HS, WS);
+  p.a_scale = 1;
+  for (int t = 0; t < 4; ++t) { p.a_dh[t] = (short)(t >> 1); p.a_dw[t] = (short)(t & 1); }
+  if ((rc = encode_act_map(&p.tmA, in2, batch, HS + 1, WS + 1, CB, p.kcA, bw, bh, bn, 1))) return rc;
+  if ((rc = encode_act_map(&p.tmB, S, batch, HS, WS, CS, p.kcB, bw, bh, bn, 1))) return rc;
+  p.BW = bw; p.BH = bh; p.BN = bn; p.tiles_w = WS / bw; p.tiles_h = HS / bh;
+  p.N = CS;
+  p.out.n_seg = 1; p.out.m_valid = 16 * CL;
+  p.out.seg[0].col0 = 0; p.out.seg[0].ncols = CS; p.out.seg[0].ld = CS; p.out.seg[0].dst = dW;
+  if (g_colsum != nullptr && g_colsum_mod < 0) {
+    p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_side = -g_colsum_mod;
+    g_colsum = nullptr;
+    GCC_REQUIRE(p.colsum_side == 1 && p.colsum_n > 0 && p.colsum_n <= CS, "wg_s2d: fused bias gradient: S side only");
+  }
+  const int groups = (batch + bn - 1) / bn;
+  p.tiles_total = groups * p.tiles_w * p.tiles_h;
+  const int mtiles = (16 * CL) / 128;
+  int splits = (148 * 2 + mtiles - 1) / mtiles;
+  if (splits > p.tiles_total) splits = p.tiles_total;
+  if (splits < 1) splits = 1;
+  p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
+  splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
+  const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
+  int stages = (100 * 1024) / stage_bytes;   // two CTAs per SM
+  if (stages > 4) stages = 4;
+  if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
+  if (stages < 1) stages = 1;
+  p.stages = stages;
+  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    attr_set = true;
+  }
+  GCC_CUDA(launch_pdl(wgrad_kernel, dim3(splits, mtiles, 1), TG_THREADS, smem, (cudaStream_t)stream, p));
+  GCC_CHECK_LAUNCH("wg_s2d");
   return GCCVAE_OK;
 }
 
@@ -2536,7 +2636,7 @@ extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, vo
   PackJobs pj;
   memset(&pj, 0, sizeof(pj));
   for (int i = 0; i < n_jobs; ++i) {
-    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 8, "pack_jobs: bad job %d", i);
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 9, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
   GCC_CUDA(launch_pdl_k(pack_jobs_kernel, dim3(64, n_jobs, 1), dim3(256), 0, (cudaStream_t)stream, pj));

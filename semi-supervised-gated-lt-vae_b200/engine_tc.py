@@ -21,7 +21,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ACT_ACCUMULATE, ACT_NONE, ACT_RELU, ACT_SIGMOID, Geom, ptr
+from ._lib import ACT_ACCUMULATE, ACT_NONE, ACT_RELU, ACT_SIGMOID, MASK_S2D, OUT_S2D, Geom, ptr
 from .engine import DEC_LAYERS, ENC_LAYERS, HEAD_LAYERS, Engine, _stream, make_geom, out_shape
 
 BF16 = torch.bfloat16
@@ -29,6 +29,9 @@ _ENC = {lay[0]: lay for lay in ENC_LAYERS}
 _DEC = {lay[0]: lay for lay in DEC_LAYERS}
 TC_ENC = ["enc.conv2", "enc.conv3", "enc.conv4", "enc.conv5"]
 TC_DEC = ["dec.conv2t", "dec.conv3t", "dec.conv4t"]
+S2D_LAYERS = ["enc.conv2", "enc.conv3", "enc.conv4", "dec.conv2t", "dec.conv3t", "dec.conv4t"]   # k4/s2/p1, C_L >= 32
+# tensors stored in s2d block form when the engine runs in s2d mode: the L operands of the layers above
+S2D_TENSORS = ["enc.conv1.out", "enc.conv2.out", "enc.conv3.out", "dec.conv4t.dout", "dec.conv3t.dout", "dec.conv2t.dout"]
 
 
 def _dense64_geom(rows, cs):
@@ -64,6 +67,12 @@ class EngineTC(Engine):
         self.wp["dec.conv5t.x2"] = z16(32 * 64)      # same packing: B operand of conv5t's dgrad
         self.wp["dec.conv5t.x2t"] = z16(16 * 128)    # [(dy,dx,c4)][(a,b)][cs]: fused conv5t forward
         self.x2 = os.environ.get("GCCVAE_X2", "1") != "0"
+        # s2d storage of the L tensors of the six k4/s2/p1 layers in the middle (include/gccvae.h, GCCVAE_OUT_S2D)
+        self.s2d = self.x2 and os.environ.get("GCCVAE_S2D", "1") != "0"
+        if self.s2d:
+            for name in S2D_LAYERS:
+                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+                self.wp[name + ".s2d"] = z16(((CS + 15) // 16 * 16) * 16 * CL)
         # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
         self.wp["heads.ls"] = z16(96, 256)       # rows 0..44 = W_loc^T, 48..92 = W_std^T
         self.wp["heads.sl"] = z16(256, 96)
@@ -104,7 +113,8 @@ class EngineTC(Engine):
             for name in TC_ENC + TC_DEC:
                 lay = _ENC.get(name) or _DEC[name]
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
-                J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
+                if not (self.s2d and name in S2D_LAYERS):     # the s2d layers use the kind-9 operand instead
+                    J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
                 J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
             J(1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"])
             for name in self.halo:
@@ -112,6 +122,10 @@ class EngineTC(Engine):
                 J(6, 16, CL, CS, v(name + ".w"), self.wp[name + ".sl9"])
             J(3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"])
             J(3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"])
+            if self.s2d:
+                for name in S2D_LAYERS:
+                    _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+                    J(9, 16, CL, CS, v(name + ".w"), self.wp[name + ".s2d"])
             J(7, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.x2"])
             J(7, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2"])
             J(8, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2t"])
@@ -155,6 +169,10 @@ class EngineTC(Engine):
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
             b[name + ".dout"] = e(B, oh, ow, oc, dt=BF16)
         b["xhat4"] = None if self.x2 else e(B, 64, 64, 4)
+        if self.s2d:
+            for tname in S2D_TENSORS:
+                Bq, H, W, Cc = b[tname].shape
+                b[tname] = e(B, H // 2 + 1, W // 2 + 1, 4 * Cc, dt=BF16)   # zero borders are never written
         return b
 
     def _xhat4(self, b, B):
@@ -192,9 +210,11 @@ class EngineTC(Engine):
         _lib.check(self.lib.gccvae_debug_mark(ptr(self.mark_buf), len(self.marks), _stream()), "mark")
         self.marks.append((what, lane))
 
-    def _sl(self, name, geom, S, bias, act, mask, L, out_f32, what):
+    def _sl(self, name, geom, S, bias, act, mask, L, out_f32, what, mask_s2d=False):
         """S -> L of layer `name` (convT forward / conv dgrad): halo kernel where the geometry allows it."""
         st = _stream()
+        if mask_s2d:
+            act = act | MASK_S2D
         if name in self.halo:
             W = self.wp[name + ".sl9"]
             self._run(what, (S, mask, L), lambda: self.lib.gccvae_sl_halo_bf16(
@@ -228,6 +248,8 @@ class EngineTC(Engine):
         def run():
             for dout, name, n in self._deferred_bias:
                 cols = dout.shape[-1]
+                if cols == 4 * n:        # s2d tensor: four slots of n channels per block (empty slots are zero)
+                    cols = n
                 self._bias_grad16(dout, name, cols=cols, n_valid=n if n < cols else 0)
         self._on_side2(run)
         self._deferred_bias = []
@@ -267,7 +289,7 @@ class EngineTC(Engine):
         stream.  GCCVAE_BIAS_IN_WGRAD=1: the next wgrad launch produces it from its staged operand tiles (side 1:
         S operand, 2: L operand) with its idle epilogue warps - one pass less over dout, but measured 1 % slower
         end to end on B200 (the stage release waits for the column sums), so it is off by default."""
-        if self.bias_in_wgrad:
+        if self.bias_in_wgrad and not (self.s2d and side == 2):   # (the s2d wgrad sums the S operand only)
             self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, -side)
         elif dout is not None:
             self._deferred_bias.append((dout, name, n))
@@ -311,8 +333,8 @@ class EngineTC(Engine):
             if not begun:
                 self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
             self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
-                B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU, None,
-                ptr(b["enc.conv1.out"]), st))
+                B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")),
+                ACT_RELU | (OUT_S2D if self.s2d else 0), None, ptr(b["enc.conv1.out"]), st))
         else:
             self._run("im2col_x", (x, b["X64"]), lambda: lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st))
             g = _dense64_geom(B * 1024, 32)
@@ -323,6 +345,17 @@ class EngineTC(Engine):
         h = b["enc.conv1.out"]
         for name in TC_ENC:
             g = make_geom(_ENC[name], B)
+            if self.s2d and name in S2D_LAYERS:
+                # L operand in s2d block form: 2x2 taps of 4 C_L channels; the output is stored in s2d form when the
+                # next layer is a stride-2 layer too
+                _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _ENC[name]
+                flag = OUT_S2D if (name + ".out") in S2D_TENSORS else 0
+                self._run(name + " fwd", (h, self.wp[name + ".s2d"], b[name + ".out"]),
+                          lambda h=h, name=name, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag: lib.gccvae_tap4_ls_bf16(
+                              B, HS + 1, WS + 1, 4 * CL, ptr(h), ptr(self.wp[name + ".s2d"]), CS, ptr(v(name + ".b")),
+                              ACT_RELU | flag, None, ptr(b[name + ".out"]), st))
+                h = b[name + ".out"]
+                continue
             self._run(name + " fwd", (h, self.wp[name + ".ls"], b[name + ".out"]),
                       lambda g=g, h=h, name=name: lib.gccvae_ls_bf16(
                           C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU, None,
@@ -393,7 +426,7 @@ class EngineTC(Engine):
             self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
                 B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
             self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
-                B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE, ptr(g4),
+                B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE | (OUT_S2D if self.s2d else 0), ptr(g4),
                 ptr(b["dec.conv4t.dout"]), st))
         else:
             # conv5t from the im2col'd logit gradient
@@ -408,13 +441,25 @@ class EngineTC(Engine):
             geom = make_geom(_DEC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            def wg(name=name, geom=geom, dout=dout, xin=xin):
-                self._arm_wgrad_bias(name, dout.shape[-1], 2, dout)   # dout is the L operand of a transposed conv
-                self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
-                    C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), _stream()))
+            _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _DEC[name]
+            def wg(name=name, geom=geom, dout=dout, xin=xin, HS=HS, WS=WS, CL=CL, CS=CS):
+                self._arm_wgrad_bias(name, CL, 2, dout)   # dout is the L operand of a transposed conv
+                if self.s2d:
+                    self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_s2d_bf16(
+                        B, HS, WS, CL, ptr(dout), ptr(xin), CS, ptr(g_(name + ".w")), _stream()))
+                else:
+                    self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
+                        C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), _stream()))
             self._side(wg)
-            self._run(name + " dgrad", (dout, self.wp[name + ".ls"], xin, dxin), lambda: lib.gccvae_ls_bf16(
-                C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
+            if self.s2d:
+                flag = OUT_S2D if (pn + ".dout") in S2D_TENSORS else 0
+                self._run(name + " dgrad", (dout, self.wp[name + ".s2d"], xin, dxin),
+                          lambda name=name, dout=dout, xin=xin, dxin=dxin, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag:
+                          lib.gccvae_tap4_ls_bf16(B, HS + 1, WS + 1, 4 * CL, ptr(dout), ptr(self.wp[name + ".s2d"]), CS, None,
+                                                  ACT_NONE | flag, ptr(xin), ptr(dxin), st))
+            else:
+                self._run(name + " dgrad", (dout, self.wp[name + ".ls"], xin, dxin), lambda: lib.gccvae_ls_bf16(
+                    C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
@@ -444,12 +489,18 @@ class EngineTC(Engine):
             geom = make_geom(_ENC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            def wg(name=name, geom=geom, dout=dout, xin=xin):
+            s2d_l = self.s2d and name in S2D_LAYERS        # xin (L operand, and the ReLU mask of the dgrad) is s2d
+            _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _ENC[name]
+            def wg(name=name, geom=geom, dout=dout, xin=xin, s2d_l=s2d_l, HS=HS, WS=WS, CL=CL, CS=CS):
                 self._arm_wgrad_bias(name, dout.shape[-1], 1, dout)   # dout is the S operand of a conv
-                self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
-                    C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
+                if s2d_l:
+                    self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_s2d_bf16(
+                        B, HS, WS, CL, ptr(xin), ptr(dout), CS, ptr(g_(name + ".w")), _stream()))
+                else:
+                    self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
+                        C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
             self._side(wg)
-            self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad")
+            self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad", mask_s2d=s2d_l)
         dh1 = b["enc.conv1.dout"]
         def wg1():
             self._arm_wgrad_bias("enc.conv1", 32, 1, dh1)
