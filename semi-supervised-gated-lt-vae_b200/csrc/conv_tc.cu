@@ -1896,11 +1896,11 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   uint32_t acc_cols = 32;
   while ((int)acc_cols < p.N) acc_cols <<= 1;
   const int k_iters = p.num_taps * p.chunks;
-  int per_sm = env_per_sm > 0 ? env_per_sm : 3;
+  int per_sm = env_per_sm > 0 ? env_per_sm : 2;
   if (per_sm > 512 / (2 * (int)acc_cols)) per_sm = 512 / (2 * (int)acc_cols);
   if (per_sm < 1) per_sm = 1;
   const int budget = 200 * 1024 / per_sm - 4608;
-  const int stage_target = (env_stage_kb > 0 ? env_stage_kb : 32) * 1024;
+  const int stage_target = (env_stage_kb > 0 ? env_stage_kb : 48) * 1024;
   int tps = 1;
   for (int d = 1; d <= k_iters; ++d)
     if (k_iters % d == 0 && d * (a_stride + b_stride) <= stage_target && 2 * d * (a_stride + b_stride) <= budget) tps = d;
@@ -2180,8 +2180,11 @@ extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int 
   GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256 && (256 % (cols / 2)) == 0,
               "colsum_bf16: bad args (cols=%d)", cols);
   if (n_valid <= 0 || n_valid > cols) n_valid = cols;
-  long long ctas = (rows + 255) / 256;
+  // enough CTAs to fill the machine even for short tensors (1024 rows): each CTA pass covers 256 / (cols/2) rows
+  const int rows_per_pass = 256 / (cols / 2);
+  long long ctas = (rows + 4LL * rows_per_pass - 1) / (4LL * rows_per_pass);
   if (ctas > 148 * 4) ctas = 148 * 4;
+  if (ctas < 1) ctas = 1;
   const int rpc = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rpc - 1) / rpc;
   GCC_CUDA(launch_pdl_k(colsum_bf16_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
