@@ -188,7 +188,9 @@ def run_ours(args, rank, world, local_rank):
     host_u8 = [torch.randint(0, 256, (B, 64, 64, 3), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(NBUF)]
     host_x = [(t.to(torch.float32) / 255.0).pin_memory() for t in host_u8]
     host_y = [(torch.rand(B, 18, generator=gen) < 0.5).to(torch.int64).pin_memory() for _ in range(NBUF)]
-    dev_x = [t.to(dev) for t in host_x]
+    # `value`: the batches are resident in HBM in the dataset's native form (uint8 pixels) for the bf16 engine, which
+    # normalises inside its first kernel; fp32 (u8/255) for the fp32 engine
+    dev_x = [(t if precision == "bf16" else f).to(dev) for t, f in zip(host_u8, host_x)]
     dev_y = [t.to(dev) for t in host_y]
 
     def step_resident(i):
@@ -295,9 +297,10 @@ def run_ours(args, rank, world, local_rank):
         "config": {"workload": WORKLOAD.format(gate=args.gate, frac=args.frac, b=B),
                    "step": "1 supervised + {} unsupervised train_step(s) (fwd+bwd+allreduce+Adam)".format(U),
                    "precision": precision, "noise": "in-kernel Philox4x32-10",
-                   "images": "synthetic 8-bit pixels; `value` feeds them resident in HBM as fp32 = u8/255 (the reference "
-                             "loader's normalisation, utils_data.py:57-59); `e2e` feeds HOST uint8 pixels and normalises "
-                             "on the device bit-exactly; `e2e_alt` feeds HOST fp32 (4x the PCIe bytes)",
+                   "images": "synthetic 8-bit pixels (what a CelebA JPEG decodes to); `value`: uint8 batches resident in HBM; "
+                             "`e2e`: HOST uint8 batches; both are normalised u8/255 on the device, bit-exactly as the "
+                             "reference loader does on the host (utils_data.py:57-59); `e2e_alt`: HOST fp32 batches "
+                             "(the reference API's dtype, 4x the PCIe bytes)",
                    "l2": "ring of 4 input batches (201 MB) + ~1 GB of activations per step exceed the 126 MB L2",
                    "parallelism": "dp{}".format(world)},
         "e2e": e2e[head],

@@ -13,6 +13,8 @@ cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.
            batch_size=B, init_temp=0.1)
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16")
 x = torch.rand(B, 64, 64, 3, device="cuda")
+if os.environ.get("PROFILE_U8"):
+    x = torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")
 y = (torch.rand(B, 18, device="cuda") < 0.5).long()
 for _ in range(3):
     lrn.train_step(x, y, True)

@@ -400,7 +400,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
                 break;
             }
           } else {
-            warp_colsum16(v, s_col, cg % p.colsum_mod, p.colsum_n - cg, lane);
+            {   // with a wrap (mod) every column of the slab is valid; otherwise columns below colsum_n
+              const int cidx = cg % p.colsum_mod;
+              warp_colsum16(v, s_col, cidx, (p.colsum_mod < (1 << 29) ? p.colsum_mod - cidx : p.colsum_n - cg), lane);
+            }
           }
           if (!valid) continue;
         }
@@ -1227,19 +1230,34 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
 //     out2[i, j, (dy,dx,c)] = sum_{a,b} S[i - a, j - b, :] . W[(2a+dy, 2b+dx, c)].
 // 36 MB per 1024 images instead of the 134 MB K=64 im2col matrix, and no separate im2col / reconstruction pass.
 // ---------------------------------------------------------------------------------------------------
-template <typename XT>
-__device__ __forceinline__ float load_px(const XT* p);
-template <>
-__device__ __forceinline__ float load_px<float>(const float* p) { return __ldg(p); }
-template <>
-__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p) {
-  return __fdiv_rn((float)__ldg(p), 255.0f);   // utils_data.py:57-59: np.float32(img) / 255.0, bit-exact
+// uint8 pixels are normalised through a 256-entry table of float(u) / 255.0f computed ONCE on the host with IEEE
+// division (utils_data.py:57-59: np.float32(img) / 255.0, bit-exact); an in-kernel __fdiv_rn costs ~10 instructions
+// and a slow-path branch per pixel, which serialised the epilogue's independent chains (83 vs 58 us).
+__device__ float g_u8lut[256];
+static int ensure_u8lut() {
+  static bool done = false;
+  if (!done) {
+    float h[256];
+    for (int i = 0; i < 256; ++i) h[i] = (float)i / 255.0f;
+    GCC_CUDA(cudaMemcpyToSymbol(g_u8lut, h, sizeof(h)));
+    done = true;
+  }
+  return GCCVAE_OK;
 }
+template <typename XT>
+__device__ __forceinline__ float load_px(const XT* p, const float* lut);
+template <>
+__device__ __forceinline__ float load_px<float>(const float* p, const float*) { return __ldg(p); }
+template <>
+__device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
 
 // one thread per block (n, i, j): 4 pixels x 3 channels in, 32 bytes out
 template <typename XT>
 __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, long long total, uint4* __restrict__ X2) {
   pdl_launch_dependents();
+  __shared__ float s_lut[256];
+  s_lut[threadIdx.x] = g_u8lut[threadIdx.x];   // written once at library initialisation, never by a kernel
+  __syncthreads();
   pdl_wait();
   for (long long idx = blockIdx.x * 256LL + threadIdx.x; idx < total; idx += (long long)gridDim.x * 256) {
     const int j = (int)(idx % 33), i = (int)((idx / 33) % 33);
@@ -1251,7 +1269,7 @@ __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, 
       float v0 = 0.f, v1 = 0.f, v2 = 0.f;
       if ((unsigned)Y < 64u && (unsigned)X < 64u) {
         const XT* px = x + ((n * 64 + Y) * 64 + X) * 3;
-        v0 = load_px<XT>(px); v1 = load_px<XT>(px + 1); v2 = load_px<XT>(px + 2);
+        v0 = load_px<XT>(px, s_lut); v1 = load_px<XT>(px + 1, s_lut); v2 = load_px<XT>(px + 2, s_lut);
       }
       w[2 * q] = pack_bf16x2(v0, v1);
       w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
@@ -1294,6 +1312,7 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
   uint64_t* bfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   float* s_db = reinterpret_cast<float*>(tmem_slot + 4);   // [4]
+  float* s_lut = s_db + 4;                                 // [256] uint8 -> float(u) / 255
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -1315,6 +1334,7 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
     fence_mbar_init();
   }
   if (threadIdx.x < 4) s_db[threadIdx.x] = 0.0f;
+  for (int i = threadIdx.x; i < 256; i += TG_THREADS) s_lut[i] = g_u8lut[i];
   if (warp == 2) tmem_alloc(tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
@@ -1390,7 +1410,8 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
         xv[3 * qq] = xv[3 * qq + 1] = xv[3 * qq + 2] = 0.0f;
         if (okq) {
           const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
-          xv[3 * qq] = load_px<XT>(px); xv[3 * qq + 1] = load_px<XT>(px + 1); xv[3 * qq + 2] = load_px<XT>(px + 2);
+          xv[3 * qq] = load_px<XT>(px, s_lut); xv[3 * qq + 1] = load_px<XT>(px + 1, s_lut);
+          xv[3 * qq + 2] = load_px<XT>(px + 2, s_lut);
         }
       }
     };
@@ -1488,6 +1509,7 @@ struct alignas(64) C3Params {
   const float* bias;        // optional [N]
   int act, N, batch, total_tiles, stages;
   int out_s2d;              // store the 32x32xN output in s2d block form [B,17,17,4N]
+  float* colsum;            // optional: += column sums of the stored values (bias gradient of the producer layer)
   long long* timeline;      // debug (see TL)
   int dbg;                  // debug: bit 0 = no output stores, bit 1 = no cp.async (tile content undefined)
 };
@@ -1509,6 +1531,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
   uint64_t* bfull = tempty + ACC;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
   float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [64]
+  float* s_col = s_bias + 64;                                                                                     // [64]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   pdl_launch_dependents();
@@ -1605,7 +1628,10 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
     // L2 round trip on the epilogue's critical path
     {
       const int et = threadIdx.x - 160;
-      if (et < 64) s_bias[et] = (p.bias != nullptr && et < p.N) ? p.bias[et] : 0.0f;
+      if (et < 64) {
+        s_bias[et] = (p.bias != nullptr && et < p.N) ? p.bias[et] : 0.0f;
+        s_col[et] = 0.0f;
+      }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
     // the ReLU mask does not depend on the accumulator: it is fetched one tile ahead (register double buffer)
@@ -1669,6 +1695,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
             if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
           }
         }
+        if (p.colsum != nullptr) warp_colsum16(v, s_col, c0, p.N - c0, lane);   // bias gradient of the producer layer
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -1679,6 +1706,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
     tc_fence_before();
   }
   __syncthreads();
+  if (p.colsum != nullptr && threadIdx.x < p.N && s_col[threadIdx.x] != 0.0f) atomicAdd(p.colsum + threadIdx.x, s_col[threadIdx.x]);
   if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem_base, acc_cols * ACC);
@@ -2180,11 +2208,10 @@ extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int 
   GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256 && (256 % (cols / 2)) == 0,
               "colsum_bf16: bad args (cols=%d)", cols);
   if (n_valid <= 0 || n_valid > cols) n_valid = cols;
-  // enough CTAs to fill the machine even for short tensors (1024 rows): each CTA pass covers 256 / (cols/2) rows
-  const int rows_per_pass = 256 / (cols / 2);
-  long long ctas = (rows + 4LL * rows_per_pass - 1) / (4LL * rows_per_pass);
+  // One CTA per 256 rows, not more: these kernels run on a side stream next to the dgrad chain, and spreading a
+  // short tensor over more SMs made the whole step slower (1.505 vs 1.480 ms per pair, measured)
+  long long ctas = (rows + 255) / 256;
   if (ctas > 148 * 4) ctas = 148 * 4;
-  if (ctas < 1) ctas = 1;
   const int rpc = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rpc - 1) / rpc;
   GCC_CUDA(launch_pdl_k(colsum_bf16_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
@@ -2300,6 +2327,7 @@ extern "C" int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2,
   const long long total = (long long)batch * 33 * 33;
   long long ctas = (total + 255) / 256;
   if (ctas > 148 * 16) ctas = 148 * 16;
+  if (int rc2 = ensure_u8lut()) return rc2;
   if (x_u8)
     GCC_CUDA(launch_pdl_k(prep_x2_kernel<uint8_t>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)x,
                           total, (uint4*)X2));
@@ -2434,11 +2462,12 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   p.batch = batch; p.total_tiles = batch * 9;
   p.timeline = g_timeline;
   const int per_sm = 3;
-  int stages = (200 * 1024 / per_sm - 4096 - 3072) / (4 * 8192);
+  int stages = (200 * 1024 / per_sm - 4096 - 4096) / (4 * 8192);
   if (stages > 4) stages = 4;
   GCC_REQUIRE(stages >= 1, "convt_recon: shared memory");
   p.stages = stages;
-  const size_t smem = 4096 + (size_t)stages * 4 * 8192 + 1024 + 1024;
+  const size_t smem = 4096 + (size_t)stages * 4 * 8192 + 1024 + 2048;
+  if (int rc2 = ensure_u8lut()) return rc2;
   static bool attr_set = false;
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
@@ -2477,6 +2506,11 @@ extern "C" int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, in
   GCC_REQUIRE(!(act & GCCVAE_MASK_S2D), "c3conv: s2d mask is not supported");
   p.total_tiles = batch * 8;
   p.timeline = g_timeline;
+  if (g_colsum != nullptr && g_colsum_mod >= 0) {   // armed by gccvae_next_launch_colsum
+    GCC_REQUIRE(g_colsum_n == CS, "c3conv: fused bias gradient needs n == CS");
+    p.colsum = g_colsum;
+    g_colsum = nullptr;
+  }
   { const char* e = getenv("GCCVAE_C3_DBG"); p.dbg = e ? atoi(e) : 0; }
   static int env_per_sm = -1;
   if (env_per_sm < 0) {

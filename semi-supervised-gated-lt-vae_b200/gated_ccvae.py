@@ -167,6 +167,7 @@ class Learner:
         self.seed = int(seed)
         self.use_graphs = bool(graphs)   # replay the whole train_step as ONE CUDA graph (Philox-noise steps only)
         self._graphs = {}
+        self._graph_turn = {}
         self._copy_stream = None
         self.last = {}
         self._lat = {}
@@ -366,52 +367,43 @@ class Learner:
         x = torch.as_tensor(x)
         u8 = x.dtype == torch.uint8 and getattr(self.engine, "x2", False)
         key = (B, bool(supervised), int(k), bool(u8))
-        g = self._graphs.get(key)
+        # two captured variants per key with their own static input buffers, used alternately: the host->device copy
+        # of a batch goes STRAIGHT into the static input of the variant that is not executing (no staging copy) and
+        # overlaps the step in flight
+        variants = self._graphs.setdefault(key, [None, None])
+        turn = self._graph_turn.get(key, 0)
+        self._graph_turn[key] = turn ^ 1
+        g = variants[turn]
         if g is None:
-            g = self._capture(key)
+            g = variants[turn] = self._capture(key)
         if x.dtype == torch.uint8 and not u8:
             x = x.to(self.device, non_blocking=True).to(torch.float32) / 255.0
+        main = torch.cuda.current_stream()
         if x.device.type == "cpu":
-            self._stage_host_inputs(g, x, y if supervised else None)
+            if self._copy_stream is None:
+                self._copy_stream = torch.cuda.Stream(device=self.device)
+            cs = self._copy_stream
+            if g.get("done") is not None:
+                cs.wait_event(g["done"])          # the previous replay of this variant no longer reads its inputs
+            with torch.cuda.stream(cs):
+                g["x"].copy_(x, non_blocking=True)
+                if supervised:
+                    g["y"].copy_(torch.as_tensor(y), non_blocking=True)
+                ready = torch.cuda.Event()
+                ready.record(cs)
+            main.wait_event(ready)
         else:
             g["x"].copy_(x, non_blocking=True)
             if supervised:
                 g["y"].copy_(torch.as_tensor(y), non_blocking=True)
         g["graph"].replay()
+        g["done"] = torch.cuda.Event()
+        g["done"].record(main)
         self.lib.gccvae_add_launch_count(g["launches"])
         if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
             self._allreduce_grads()
             self.optimiser.apply_gradients()
         return g["loss"], self._c
-
-    def _stage_host_inputs(self, g, x, y):
-        """Host batches: the H2D copy runs on a dedicated copy stream into one of two staging buffers, so that the
-        copy of batch n+1 overlaps the compute of batch n (the host never blocks); the main stream then moves the
-        staged batch into the graph's static input with a device-to-device copy."""
-        main = torch.cuda.current_stream()
-        if self._copy_stream is None:
-            self._copy_stream = torch.cuda.Stream(device=self.device)
-        if "stage" not in g:
-            g["stage"] = [dict(x=torch.empty_like(g["x"]), y=None if g["y"] is None else torch.empty_like(g["y"]),
-                               free=None) for _ in range(2)]
-            g["turn"] = 0
-        st = g["stage"][g["turn"]]
-        g["turn"] ^= 1
-        cs = self._copy_stream
-        if st["free"] is not None:
-            cs.wait_event(st["free"])            # the previous consumer of this staging buffer has finished
-        with torch.cuda.stream(cs):
-            st["x"].copy_(x, non_blocking=True)
-            if y is not None:
-                st["y"].copy_(torch.as_tensor(y), non_blocking=True)
-            ready = torch.cuda.Event()
-            ready.record(cs)
-        main.wait_event(ready)
-        g["x"].copy_(st["x"], non_blocking=True)
-        if y is not None:
-            g["y"].copy_(st["y"], non_blocking=True)
-        st["free"] = torch.cuda.Event()
-        st["free"].record(main)
 
     def _capture(self, key):
         B, supervised, k, u8 = key
@@ -444,9 +436,7 @@ class Learner:
         torch.cuda.synchronize(self.device)
         for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
             dst.copy_(src)
-        g = dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches)
-        self._graphs[key] = g
-        return g
+        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None)
 
     def classifier_accuracy(self, x, y, noise=None):
         """gated_ccvae.py:421-446."""
