@@ -32,7 +32,7 @@ from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, LatentBwdArgs, LatentFw
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
 from .params import ParamStore, keras_default_init
-from .utils_data import load_learned_gating_matrix
+from .utils_data import CELEBA_EASY_LABELS, load_learned_gating_matrix
 
 logger = logging.getLogger(__name__)
 
@@ -302,14 +302,25 @@ class Learner:
             self._latent_bwd(B, lb, b, n, supervised, k)
             mark("latent bwd", coarse=True)
             v, g = self.store.view, self.store.g
-            _lib.check(self.lib.gccvae_gate_bwd(
-                ptr(lb["partials"]), lb["npart"], ptr(v("mu")), ptr(v("cls.w")), ptr(v("prior.loc_true")),
-                ptr(v("prior.loc_false")), ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
-                ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), dp.l1_scale(self.world),
-                ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
-                ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
-                ptr(self.store.loss_slot), st), "gate_bwd")
-            mark("gate bwd", coarse=True)
+
+            def gate_bwd():
+                _lib.check(self.lib.gccvae_gate_bwd(
+                    ptr(lb["partials"]), lb["npart"], ptr(v("mu")), ptr(v("cls.w")), ptr(v("prior.loc_true")),
+                    ptr(v("prior.loc_false")), ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
+                    ptr(self._gate_ws), float(self.train_config.get("gating_reg", 0.0)), dp.l1_scale(self.world),
+                    ptr(g("cls.w")), ptr(g("cls.b")), ptr(g("prior.loc_true")), ptr(g("prior.loc_false")),
+                    ptr(g("prior.scale_true")), ptr(g("prior.scale_false")), ptr(g("mu")) if learnable else None,
+                    ptr(self.store.loss_slot), _stream()), "gate_bwd")
+                mark("gate bwd", coarse=True)
+
+            # the reduction of the per-block partial sums and the gate / classifier / prior parameter gradients feed
+            # only Adam (and the returned loss): on the tensor-core engine they leave the dgrad chain for the second
+            # side stream, which encoder_bwd joins at the end of the step
+            on_side2 = getattr(self.engine, "_on_side2", None)
+            if on_side2 is not None and os.environ.get("GCCVAE_GATE_BWD_STREAM", "side") != "main":
+                on_side2(gate_bwd)
+            else:
+                gate_bwd()
             self.engine.encoder_bwd(x, b)
             mark("encoder bwd + join", coarse=True)
         else:
@@ -366,7 +377,8 @@ class Learner:
         B = int(x.shape[0])
         x = torch.as_tensor(x)
         u8 = x.dtype == torch.uint8 and getattr(self.engine, "x2", False)
-        key = (B, bool(supervised), int(k), bool(u8))
+        # the captured kernels bake the gate temperature in as an argument: it is part of the key
+        key = (B, bool(supervised), int(k), bool(u8), float(self.gating_sampler_temp))
         # two captured variants per key with their own static input buffers, used alternately: the host->device copy
         # of a batch goes STRAIGHT into the static input of the variant that is not executing (no staging copy) and
         # overlaps the step in flight
@@ -406,7 +418,7 @@ class Learner:
         return g["loss"], self._c
 
     def _capture(self, key):
-        B, supervised, k, u8 = key
+        B, supervised, k, u8, _temperature = key
         xs = torch.zeros(B, *self.ip_shape, dtype=torch.uint8 if u8 else torch.float32, device=self.device)
         ys = torch.zeros(B, self.y_dim, dtype=torch.int64, device=self.device) if supervised else None
 
@@ -461,14 +473,134 @@ class Learner:
             acc += float(self.classifier_accuracy(xs, ys))
         return acc / num_batches
 
+    # ---- checkpoints (gated_ccvae.py:146-165, 391-419) ---------------------------------------------------------------
+    # file stem -> parameter prefix; inside a file the tensors follow Keras' own order (layer_names x weight_names),
+    # which is the order of params.param_specs()
+    _H5_FILES = (("encoder_model", "enc."), ("decoder_model", "dec."), ("classifier", "cls."), ("cond_prior", "prior."))
+
     def load_model(self, param_dir, model_id):
-        """gated_ccvae.py:146-165.  Only the learned gating matrix (.npy) is on the ELBO path; the Keras
-        .h5 weight files need an HDF5 reader and are not read here."""
+        """gated_ccvae.py:146-165: the four Keras `save_weights` files `{encoder_model,decoder_model,classifier,
+        cond_prior}_{model_id}.h5` (read by the pure-Python HDF5 subset reader `h5lite`; Keras layouts = ours: HWIO
+        conv kernels, [Cin... ] conv-transpose kernels [kh,kw,Cout,Cin], [in,out] dense kernels) and, in learnable
+        mode, `learned_gating_matrix_{model_id}.npy` into mu."""
+        from .h5lite import keras_weights
+        logger.info("Loading model from {} of model_id {}".format(param_dir, model_id))
+        loaded = {}
+        for stem, prefix in self._H5_FILES:
+            path = os.path.join(param_dir, "{}_{}.h5".format(stem, model_id))
+            names = [n for n in self.store.names() if n.startswith(prefix)]
+            weights = keras_weights(path)
+            if len(weights) != len(names):
+                raise ValueError("{}: {} weight tensors, expected {}".format(path, len(weights), len(names)))
+            for name, (wname, arr) in zip(names, weights):
+                shape = self.store.offsets[name][2]
+                if tuple(arr.shape) != tuple(shape):
+                    raise ValueError("{}: {} has shape {}, expected {} for {}".format(path, wname, arr.shape, shape, name))
+                loaded[name] = arr
+        self.store.load_dict(loaded)
         if self.train_config["gate_type"] == "learnable":
             mu_init = load_learned_gating_matrix(param_dir, model_id)
             with torch.no_grad():
                 self.store.view("mu").copy_(torch.from_numpy(np.asarray(mu_init, dtype=np.float32)))
             logging.info("Loaded learned mu")
+
+    def save_model(self, param_dir, model_id):
+        """gated_ccvae.py:391-419.  The reference writes four Keras .h5 files; there is no HDF5 writer here, so the
+        same tensors go to `{stem}_{model_id}.npz` under their parameter names (load with `load_model_npz`).  The
+        learned gating matrix is written exactly as the reference does: `.npy` (+ `.csv`, z1..z18 x label names)."""
+        os.makedirs(param_dir, exist_ok=True)
+        d = {k: v.cpu().numpy() for k, v in self.store.to_dict().items()}
+        for stem, prefix in self._H5_FILES:
+            np.savez(os.path.join(param_dir, "{}_{}.npz".format(stem, model_id)),
+                     **{k: v for k, v in d.items() if k.startswith(prefix)})
+        if self.train_config["gate_type"] == "learnable":
+            mu = d["mu"]
+            np.save(os.path.join(param_dir, "learned_gating_matrix_{}.npy".format(model_id)), mu)
+            with open(os.path.join(param_dir, "learned_gating_matrix_{}.csv".format(model_id)), "w") as fh:
+                fh.write("," + ",".join(CELEBA_EASY_LABELS) + "\n")
+                for i in range(mu.shape[0]):
+                    fh.write("z{},".format(i + 1) + ",".join(str(t) for t in mu[i]) + "\n")   # shortest fp32 repr
+
+    def load_model_npz(self, param_dir, model_id):
+        for stem, _ in self._H5_FILES:
+            with np.load(os.path.join(param_dir, "{}_{}.npz".format(stem, model_id))) as z:
+                self.store.load_dict({k: z[k] for k in z.files})
+        if self.train_config["gate_type"] == "learnable":
+            mu = load_learned_gating_matrix(param_dir, model_id)
+            with torch.no_grad():
+                self.store.view("mu").copy_(torch.from_numpy(np.asarray(mu, dtype=np.float32)))
+
+    # ---- training loop (gated_ccvae.py:313-419) ------------------------------------------------------------------------
+    @staticmethod
+    def epoch_schedule(perc_supervision, n_sup, n_unsup, batch_size):
+        """-> list of booleans, one per batch of an epoch: is this batch supervised?  (gated_ccvae.py:319-357:
+        `is_supervised = (i % period_sup_batches == 0) and ctr_sup < sup_batches`.)"""
+        if perc_supervision == 1.0:
+            sup_batches = batches = math.ceil(n_sup / batch_size)
+            period = 1
+        elif perc_supervision > 0.0:
+            sup_batches = math.ceil(n_sup / batch_size)
+            batches = sup_batches + math.ceil(n_unsup / batch_size)
+            period = int(batches / sup_batches)
+        elif perc_supervision == 0.0:
+            sup_batches, batches, period = 0, math.ceil(n_unsup / batch_size), None
+        else:
+            assert False, "Data frac not correct"
+        out, ctr = [], 0
+        for i in range(int(batches)):
+            sup = period is not None and (i % period == 0) and ctr < sup_batches
+            ctr += int(sup)
+            out.append(bool(sup))
+        return out
+
+    def train(self, data_loaders, param_dir, fig_path=None, on_batch=None):
+        """gated_ccvae.py:313-419: per epoch the supervised / unsupervised batches are interleaved by
+        `epoch_schedule`, every batch is one `train_step`, the epoch ends with the validation accuracy, a
+        best-model checkpoint, and (learnable gates) `gating_sampler_temp *= 0.99`; the last model is saved at the
+        end.  `data_loaders` = {'sup','unsup','valid'} objects with `.n_s` and `.step()` (utils_data.py).  A NaN in the
+        gate sample raises (the reference calls sys.exit(-1), :373-375).  Returns the per-epoch log."""
+        cfg = self.train_config
+        perc = cfg["perc_supervision"]
+        best_val_acc, history = -np.inf, []
+        for epoch in range(cfg["n_epochs"]):
+            n_sup = data_loaders["sup"].n_s if perc != 0.0 else 0
+            n_unsup = data_loaders["unsup"].n_s if perc != 1.0 else 0
+            schedule = self.epoch_schedule(perc, n_sup, n_unsup, cfg["batch_size"])
+            sup_iter = iter(data_loaders["sup"].step()) if perc != 0.0 else None
+            unsup_iter = iter(data_loaders["unsup"].step()) if perc != 1.0 else None
+            sup_loss = unsup_loss = None
+            c = None
+            for i, is_sup in enumerate(schedule):
+                xs, ys = next(sup_iter if is_sup else unsup_iter)
+                loss, c = self.train_step(xs, ys if is_sup else None, supervised=is_sup)
+                if is_sup:
+                    sup_loss = loss
+                else:
+                    unsup_loss = loss
+                if on_batch is not None:
+                    on_batch(epoch, i, is_sup, loss, c)
+            # one device->host read per epoch instead of per batch (the reference reads loss and c every batch for its
+            # progress bar): the NaN check on the gate sample keeps its meaning, it just fires at the epoch end
+            if c is not None and bool(torch.isnan(c).any()):
+                raise FloatingPointError("gate sample c contains NaN (gated_ccvae.py:373-375)")
+            val_acc = self.accuracy(data_loaders["valid"]) if perc else -np.inf
+            logger.info("[Epoch %03d] Val Acc %.3f" % (epoch, val_acc))
+            if val_acc > best_val_acc:
+                logger.info("Saving best model...")
+                best_val_acc = val_acc
+                self.save_model(param_dir, "best")
+            if cfg["gate_type"] == "learnable":
+                self.gating_sampler_temp *= 0.99
+                self._graphs.clear()      # graphs captured with the old temperature are never replayed again
+                self._graph_turn.clear()
+                logger.info("gating_sampler_temp decayed to: %.4f" % self.gating_sampler_temp)
+            history.append(dict(epoch=epoch, sup_loss=None if sup_loss is None else float(sup_loss),
+                                unsup_loss=None if unsup_loss is None else float(unsup_loss), val_acc=float(val_acc),
+                                n_sup=sum(schedule), n_unsup=len(schedule) - sum(schedule),
+                                gating_sampler_temp=float(self.gating_sampler_temp)))
+        logger.info("Saving last model...")
+        self.save_model(param_dir, "last")
+        return history
 
     # ---- data parallel ---------------------------------------------------------------------------------------------------
     def _allreduce_grads(self):

@@ -40,3 +40,25 @@ class GatingMatrixReader:
     def __init__(self, root, sup_frac, batch_size=None):
         self.root, self.sup_frac, self.batch_size = root, sup_frac, batch_size
         self.init_gating_prob = load_gating_matrix(root, sup_frac)
+
+
+class SyntheticReader:
+    """Stand-in for CelebAReader (utils_data.py:31-176) with the interface the Learner consumes: `.n_s` samples,
+    `.step()` yielding `(xs, ys)` batches forever (xs uint8 or fp32 [B,64,64,3], ys int64 [B,18] or None).  CelebA
+    itself is not available; images are seeded synthetic 8-bit pixels, labels Bernoulli(0.5)."""
+
+    def __init__(self, n_samples, batch_size, supervised=True, seed=0, dtype="uint8", y_dim=18):
+        import torch
+        self.n_s, self.batch_size, self.supervised = int(n_samples), int(batch_size), bool(supervised)
+        gen = torch.Generator().manual_seed(seed)
+        self.x = torch.randint(0, 256, (self.n_s, 64, 64, 3), generator=gen, dtype=torch.uint8)
+        if dtype != "uint8":
+            self.x = self.x.to(torch.float32) / 255.0
+        self.y = (torch.rand(self.n_s, y_dim, generator=gen) < 0.5).to(torch.int64)
+
+    def step(self):
+        i = 0
+        while True:
+            idx = [(i + j) % self.n_s for j in range(self.batch_size)]
+            i = (i + self.batch_size) % self.n_s
+            yield self.x[idx], (self.y[idx] if self.supervised else None)

@@ -1,0 +1,113 @@
+"""Keras-2.8 `.h5` weight files of the reference (gated_ccvae.py:146-165, 391-419) through the pure-Python HDF5
+subset reader, and the training-loop schedule (gated_ccvae.py:317-357).  Fixture = the reference's own trained
+checkpoint `models/params_0.2_learnable/*_best.*`, copied as data under tests/golden/models/."""
+import hashlib
+import math
+import os
+
+import numpy as np
+import pytest
+
+import gccvae_b200 as G
+from gccvae_b200.h5lite import H5Error, H5File, keras_weights
+from gccvae_b200.params import param_specs
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CKPT = os.path.join(HERE, "golden", "models", "params_0.2_learnable")
+
+# (file stem, number of tensors, float64 sum of all weights, sha256[:16] of the concatenated fp32 bytes) recorded from
+# the reference's files when the fixture was made
+KNOWN = [
+    ("classifier_best", 2, 0.7985251030768268, "6c11356777ef6223"),
+    ("cond_prior_best", 4, 1057.400958465302, "63e5e0fccbf679b3"),
+    ("decoder_model_best", 12, 549.6746476925755, "6fb13ac621c410a9"),
+    ("encoder_model_best", 14, 265.08541270720133, "ddd0924c66160c71"),
+]
+
+
+@pytest.mark.parametrize("stem,n,total,digest", KNOWN)
+def test_reader_returns_the_stored_tensors(stem, n, total, digest):
+    w = keras_weights(os.path.join(CKPT, stem + ".h5"))
+    assert len(w) == n
+    assert all(a.dtype == np.float32 for _, a in w)
+    assert float(sum(np.float64(a).sum() for _, a in w)) == pytest.approx(total, rel=0, abs=1e-9)
+    assert hashlib.sha256(b"".join(a.tobytes() for _, a in w)).hexdigest()[:16] == digest
+
+
+def test_keras_order_and_shapes_are_the_parameter_store_order():
+    specs = param_specs()
+    for stem, prefix in (("encoder_model", "enc."), ("decoder_model", "dec."), ("classifier", "cls."),
+                         ("cond_prior", "prior.")):
+        w = keras_weights(os.path.join(CKPT, stem + "_best.h5"))
+        mine = [(k, s) for k, s in specs if k.startswith(prefix)]
+        assert [tuple(a.shape) for _, a in w] == [tuple(s) for _, s in mine], stem
+        # kernel before bias inside every layer (Keras' weight_names order)
+        for (wn, _), (k, _) in zip(w, mine):
+            if k.endswith(".b"):
+                assert wn.endswith("bias:0"), (wn, k)
+            elif k.endswith(".w"):
+                assert wn.endswith("kernel:0"), (wn, k)
+
+
+def test_file_metadata_and_group_walk():
+    f = H5File(os.path.join(CKPT, "encoder_model_best.h5"))
+    a = f.attrs("/")
+    assert a["backend"] == b"tensorflow" and a["keras_version"] == b"2.8.0"
+    assert len(a["layer_names"]) == 8 and a["layer_names"][0].startswith(b"conv2d")   # 5 conv, flatten, 2 dense
+    assert len(f.visit("/")) == 14
+    assert f.is_group("/" + a["layer_names"][0].decode())
+    with pytest.raises(KeyError):
+        f["/nope/kernel:0"]
+
+
+def test_not_hdf5_is_a_loud_error(tmp_path):
+    p = tmp_path / "x.h5"
+    p.write_bytes(b"PK\x03\x04 not hdf5")
+    with pytest.raises(H5Error):
+        H5File(str(p))
+
+
+def test_learned_gating_csv_export_is_byte_exact(tmp_path):
+    """`save_model` writes learned_gating_matrix_*.csv as the reference's pandas `to_csv` does (gated_ccvae.py:399-403):
+    regenerated from the reference's .npy it must equal the reference's .csv byte for byte."""
+    mu = np.load(os.path.join(CKPT, "learned_gating_matrix_best.npy"))
+    want = open(os.path.join(CKPT, "learned_gating_matrix_best.csv")).read()
+    got = "," + ",".join(G.utils_data.CELEBA_EASY_LABELS) + "\n"
+    for i in range(mu.shape[0]):
+        got += "z{},".format(i + 1) + ",".join(str(t) for t in mu[i]) + "\n"
+    assert got == want
+
+
+def _reference_schedule(perc, n_sup, n_unsup, bs):
+    """the literal loop of gated_ccvae.py:319-357."""
+    if perc == 1.0:
+        batches_per_epoch = np.ceil(n_sup / bs)
+        period_sup_batches = 1
+        sup_batches = batches_per_epoch
+    elif perc > 0.0:
+        sup_batches = np.ceil(n_sup / bs)
+        unsup_batches = np.ceil(n_unsup / bs)
+        batches_per_epoch = sup_batches + unsup_batches
+        period_sup_batches = int(batches_per_epoch / sup_batches)
+    else:
+        sup_batches = 0.0
+        batches_per_epoch = np.ceil(n_unsup / bs)
+        period_sup_batches = np.inf
+    out, ctr_sup = [], 0
+    for i in range(int(batches_per_epoch)):
+        is_supervised = (i % period_sup_batches == 0) and ctr_sup < sup_batches
+        ctr_sup += int(is_supervised)
+        out.append(bool(is_supervised))
+    return out
+
+
+@pytest.mark.parametrize("perc,n_sup,n_unsup,bs", [
+    (0.2, 32554, 130216, 256),      # CelebA train split at 20 % labels, reference batch size (configs.py:17)
+    (0.2, 81536, 81536 * 4, 128),   # 637 supervised batches -> period 4... (1 sup : 3 unsup)
+    (0.5, 1000, 1000, 128), (1.0, 777, 0, 256), (0.0, 0, 500, 128), (0.1, 130, 4000, 64),
+])
+def test_epoch_schedule_is_the_reference_interleave(perc, n_sup, n_unsup, bs):
+    got = G.Learner.epoch_schedule(perc, n_sup, n_unsup, bs)
+    assert got == _reference_schedule(perc, n_sup, n_unsup, bs)
+    if 0.0 < perc < 1.0:
+        assert sum(got) == math.ceil(n_sup / bs)
