@@ -1251,6 +1251,13 @@ __device__ __forceinline__ float load_px<float>(const float* p, const float*) { 
 template <>
 __device__ __forceinline__ float load_px<uint8_t>(const uint8_t* p, const float* lut) { return lut[__ldg(p)]; }
 
+template <typename XT>
+__device__ __forceinline__ float px_value(XT raw, const float* lut);
+template <>
+__device__ __forceinline__ float px_value<float>(float raw, const float*) { return raw; }
+template <>
+__device__ __forceinline__ float px_value<uint8_t>(uint8_t raw, const float* lut) { return lut[raw]; }
+
 // one thread per block (n, i, j): 4 pixels x 3 channels in, 32 bytes out
 template <typename XT>
 __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, long long total, uint4* __restrict__ X2) {
@@ -1399,20 +1406,19 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
     const XT* xs = reinterpret_cast<const XT*>(p.x);
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
     // The image pixels of a block do not depend on the accumulator and come straight from HBM: they are fetched one
-    // tile AHEAD (register double buffer), so their latency hides behind the arithmetic of the current tile.
-    float xn[12];
-    auto fetch_x = [&](int tile, float (&xv)[12]) {
+    // tile AHEAD (register double buffer), so their latency hides behind the arithmetic of the current tile.  The
+    // prefetch keeps the RAW values (bytes for uint8 images) and is branch-free - coordinates clamped into the image,
+    // out-of-image pixels are masked by `ok` below - so that all 12 loads are in flight together; the uint8 -> float
+    // table lookup happens when the values are consumed (a lookup right behind its load would stall the warp for
+    // the full memory latency, four times per tile).
+    XT xn[12];
+    auto fetch_x = [&](int tile, XT (&xv)[12]) {
       const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
 #pragma unroll
       for (int qq = 0; qq < 4; ++qq) {
-        const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
-        const bool okq = row_ok && (unsigned)Y < 64u && (unsigned)X < 64u;
-        xv[3 * qq] = xv[3 * qq + 1] = xv[3 * qq + 2] = 0.0f;
-        if (okq) {
-          const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
-          xv[3 * qq] = load_px<XT>(px, s_lut); xv[3 * qq + 1] = load_px<XT>(px + 1, s_lut);
-          xv[3 * qq + 2] = load_px<XT>(px + 2, s_lut);
-        }
+        const int Y = min(max(2 * i - 1 + (qq >> 1), 0), 63), X = min(max(2 * j - 1 + (qq & 1), 0), 63);
+        const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
+        xv[3 * qq] = __ldg(px); xv[3 * qq + 1] = __ldg(px + 1); xv[3 * qq + 2] = __ldg(px + 2);
       }
     };
     if (tile_beg < tile_end) fetch_x(tile_beg, xn);
@@ -1421,7 +1427,7 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
       float xv[12];
 #pragma unroll
-      for (int k2 = 0; k2 < 12; ++k2) xv[k2] = xn[k2];
+      for (int k2 = 0; k2 < 12; ++k2) xv[k2] = px_value<XT>(xn[k2], s_lut);
       if (tile + 1 < tile_end) fetch_x(tile + 1, xn);
       bool ok[4];
 #pragma unroll

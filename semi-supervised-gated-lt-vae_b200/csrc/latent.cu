@@ -592,37 +592,20 @@ __global__ void __launch_bounds__(WARPS * 32) latent_bwd_kernel(gccvae_latent_bw
   }
 }
 
-// column-wise sum of the per-CTA partial rows -> one row (4 independent accumulators per thread)
-__global__ void __launch_bounds__(128) reduce_partials_kernel(const float* __restrict__ partials, int n_partials,
-                                                              float* __restrict__ out) {
-  pdl_prologue();
-  const int c = blockIdx.x * 128 + threadIdx.x;
-  if (c >= PT_TOTAL) return;
-  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-  int n = 0;
-  for (; n + 4 <= n_partials; n += 4) {
-    a0 += partials[(size_t)(n + 0) * PT_TOTAL + c];
-    a1 += partials[(size_t)(n + 1) * PT_TOTAL + c];
-    a2 += partials[(size_t)(n + 2) * PT_TOTAL + c];
-    a3 += partials[(size_t)(n + 3) * PT_TOTAL + c];
-  }
-  for (; n < n_partials; ++n) a0 += partials[(size_t)n * PT_TOTAL + c];
-  out[c] = (a0 + a1) + (a2 + a3);
-}
-
 // ---------------------------------------------------------------------------------------------
 // gate backward: reduce partials, un-gate, chain to mu, add L1.  One CTA.
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__ partials, int n_partials,
-                                                       const float* __restrict__ mu, const float* __restrict__ Wcls,
-                                                       const float* __restrict__ Wlt, const float* __restrict__ Wlf,
-                                                       const float* __restrict__ Wst, const float* __restrict__ Wsf,
-                                                       const float* __restrict__ ws, float gating_reg, float l1_scale,
-                                                       float* __restrict__ dWcls, float* __restrict__ dbcls,
-                                                       float* __restrict__ dWlt, float* __restrict__ dWlf,
-                                                       float* __restrict__ dWst, float* __restrict__ dWsf,
-                                                       float* __restrict__ dmu, float* __restrict__ loss_inout) {
-  pdl_prologue();
+// (partial rows are read with ld.global.cg: in the merged kernel below they were written by OTHER blocks of the same
+// grid, which a non-coherent / L1-cached load is not guaranteed to see)
+__device__ __forceinline__ void gate_bwd_body(const float* partials, int n_partials,
+                                              const float* __restrict__ mu, const float* __restrict__ Wcls,
+                                              const float* __restrict__ Wlt, const float* __restrict__ Wlf,
+                                              const float* __restrict__ Wst, const float* __restrict__ Wsf,
+                                              const float* __restrict__ ws, float gating_reg, float l1_scale,
+                                              float* __restrict__ dWcls, float* __restrict__ dbcls,
+                                              float* __restrict__ dWlt, float* __restrict__ dWlf,
+                                              float* __restrict__ dWst, float* __restrict__ dWsf,
+                                              float* __restrict__ dmu, float* __restrict__ loss_inout) {
   __shared__ float s_dc[NP];
   __shared__ float s_red[352 / 32];
   const int p = threadIdx.x;
@@ -635,7 +618,7 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
     for (int n = 0; n < n_partials; ++n) {
       const float* row = partials + (size_t)n * PT_TOTAL;
 #pragma unroll
-      for (int m = 0; m < 5; ++m) sum[m] += row[m * NP + p];
+      for (int m = 0; m < 5; ++m) sum[m] += __ldcg(row + m * NP + p);
     }
     const float c_ij = ws[GW_C + p];
     const float c_prior = ws[GW_C + i2 * Y + j2];
@@ -648,7 +631,7 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
   } else if (p - NP < Y && dbcls) {
     const int j = p - NP;
     float v = 0.0f;
-    for (int n = 0; n < n_partials; ++n) v += partials[(size_t)n * PT_TOTAL + PT_DB + j];
+    for (int n = 0; n < n_partials; ++n) v += __ldcg(partials + (size_t)n * PT_TOTAL + PT_DB + j);
     dbcls[j] = v;
   }
   __syncthreads();
@@ -664,7 +647,7 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
   // loss: sum of partial losses + L1
   float lossv = 0.0f;
   if (p == NP + Y) {
-    for (int n = 0; n < n_partials; ++n) lossv += partials[(size_t)n * PT_TOTAL + PT_LOSS];
+    for (int n = 0; n < n_partials; ++n) lossv += __ldcg(partials + (size_t)n * PT_TOTAL + PT_LOSS);
   }
   float tot = warp_sum(absmu);
   if ((p & 31) == 0) s_red[p >> 5] = tot;
@@ -675,6 +658,47 @@ __global__ void __launch_bounds__(352) gate_bwd_kernel(const float* __restrict__
     if (dmu == nullptr) l1 = 0.0f;
     if (loss_inout) loss_inout[0] = lossv + l1_scale * gating_reg * l1 / (float)NP;
   }
+}
+
+// Both steps in ONE launch (one dependent launch less on the step's critical path): every block reduces 352 columns
+// of the partial rows into `reduced` (4 independent accumulators per thread, fixed order: deterministic), takes a ticket, and the
+// block that draws the last ticket - all columns are then visible - runs the gate backward on the reduced row.
+// The ticket is slot GW_B + 31 of the gate workspace: gate_fwd zeroes it every step, the last block re-zeroes it.
+__global__ void __launch_bounds__(352) reduce_gate_bwd_kernel(const float* __restrict__ partials, int n_partials,
+                                                              float* reduced, unsigned int* ticket,
+                                                              const float* __restrict__ mu, const float* __restrict__ Wcls,
+                                                              const float* __restrict__ Wlt, const float* __restrict__ Wlf,
+                                                              const float* __restrict__ Wst, const float* __restrict__ Wsf,
+                                                              const float* __restrict__ ws, float gating_reg,
+                                                              float l1_scale, float* __restrict__ dWcls,
+                                                              float* __restrict__ dbcls, float* __restrict__ dWlt,
+                                                              float* __restrict__ dWlf, float* __restrict__ dWst,
+                                                              float* __restrict__ dWsf, float* __restrict__ dmu,
+                                                              float* __restrict__ loss_inout) {
+  pdl_prologue();
+  __shared__ int s_last;
+  const int c = blockIdx.x * 352 + threadIdx.x;
+  if (c < PT_TOTAL) {
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int n = 0;
+    for (; n + 4 <= n_partials; n += 4) {
+      a0 += partials[(size_t)(n + 0) * PT_TOTAL + c];
+      a1 += partials[(size_t)(n + 1) * PT_TOTAL + c];
+      a2 += partials[(size_t)(n + 2) * PT_TOTAL + c];
+      a3 += partials[(size_t)(n + 3) * PT_TOTAL + c];
+    }
+    for (; n < n_partials; ++n) a0 += partials[(size_t)n * PT_TOTAL + c];
+    reduced[c] = (a0 + a1) + (a2 + a3);
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) s_last = (atomicAdd(ticket, 1u) == gridDim.x - 1) ? 1 : 0;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (threadIdx.x == 0) *ticket = 0u;
+  gate_bwd_body(reduced, 1, mu, Wcls, Wlt, Wlf, Wst, Wsf, ws, gating_reg, l1_scale, dWcls, dbcls, dWlt, dWlf, dWst, dWsf,
+                dmu, loss_inout);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -893,15 +917,12 @@ extern "C" int gccvae_gate_bwd(float* partials, int n_partials, const float* mu,
               "gate_bwd: null pointer");
   // row n_partials of the buffer receives the column sums (the caller allocates n_partials + 1 rows)
   float* reduced = partials + (size_t)n_partials * PT_TOTAL;
-  GCC_CUDA(launch_pdl_k(reduce_partials_kernel, dim3((PT_TOTAL + 127) / 128), dim3(128), 0, (cudaStream_t)stream,
-                        (const float*)partials, n_partials, reduced));
-  GCC_CHECK_LAUNCH("reduce_partials");
-  partials = reduced;
-  n_partials = 1;
-  GCC_CUDA(launch_pdl_k(gate_bwd_kernel, dim3(1), dim3(352), 0, (cudaStream_t)stream, (const float*)partials, n_partials,
-                        mu, Wcls, Wlt, Wlf, Wst, Wsf, gate_ws,
-                                                       gating_reg, l1_scale, dWcls, dbcls, dWlt, dWlf, dWst, dWsf, dmu,
-                                                       loss_inout));
+  // block ticket of the merged kernel: a spare slot of the gate workspace (zeroed by every gate_fwd launch and by the
+  // kernel itself) - the workspace is caller-owned device memory, const only from the caller's point of view
+  unsigned int* ticket = reinterpret_cast<unsigned int*>(const_cast<float*>(gate_ws)) + GW_B + 31;
+  GCC_CUDA(launch_pdl_k(reduce_gate_bwd_kernel, dim3((PT_TOTAL + 351) / 352), dim3(352), 0, (cudaStream_t)stream,
+                        (const float*)partials, n_partials, reduced, ticket, mu, Wcls, Wlt, Wlf, Wst, Wsf, gate_ws,
+                        gating_reg, l1_scale, dWcls, dbcls, dWlt, dWlf, dWst, dWsf, dmu, loss_inout));
   GCC_CHECK_LAUNCH("gate_bwd");
   return GCCVAE_OK;
 }

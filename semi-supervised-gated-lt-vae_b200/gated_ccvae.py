@@ -128,17 +128,27 @@ class KerasAdam:
         self.store, self.n = store, n_params
         self.m = torch.zeros_like(store.flat)
         self.v = torch.zeros_like(store.flat)
-        self.step_dev = torch.zeros(1, dtype=torch.int32, device=store.device)  # t, bumped on device
+        # {t, block ticket}: t lives on the device (the kernels key their Philox streams on it and a captured graph
+        # of the step can be replayed); the update kernel itself advances it
+        self.step_dev = torch.zeros(2, dtype=torch.int32, device=store.device)
         self.lib = _lib.load()
 
     @property
     def iterations(self):
-        return int(self.step_dev.item())
+        return int(self.step_dev[0].item())
 
     def apply_gradients(self):
-        _lib.check(self.lib.gccvae_adam_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
-                                            self.n, self.lr, self.beta_1, self.beta_2, self.epsilon, 0,
-                                            ptr(self.step_dev), _stream()), "adam")
+        """one launch: t += 1, the Adam update of the trainable prefix, and the gradient buffer cleared for the next
+        backward pass (which accumulates into it).  Returns True if the gradient buffer was cleared."""
+        if os.environ.get("GCCVAE_ADAM", "fused") == "split":    # A/B switch: counter bump + update as two launches
+            _lib.check(self.lib.gccvae_adam_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
+                                                self.n, self.lr, self.beta_1, self.beta_2, self.epsilon, 0,
+                                                ptr(self.step_dev), _stream()), "adam")
+            return False
+        _lib.check(self.lib.gccvae_adam_fused_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
+                                                  self.n, self.store.total, self.lr, self.beta_1, self.beta_2,
+                                                  self.epsilon, ptr(self.step_dev), _stream()), "adam")
+        return True
 
 
 class Learner:
@@ -168,6 +178,7 @@ class Learner:
         self.use_graphs = bool(graphs)   # replay the whole train_step as ONE CUDA graph (Philox-noise steps only)
         self._graphs = {}
         self._graph_turn = {}
+        self._grads_clean = False        # True right after apply_gradients (it clears the gradient buffer)
         self._copy_stream = None
         self.last = {}
         self._lat = {}
@@ -280,7 +291,9 @@ class Learner:
         if hasattr(self.engine, "begin_step"):
             self.engine.begin_step(x, b, lb["log_pxz"])
         if backward:
-            self.engine.zero_grads()
+            if not self._grads_clean:    # otherwise the previous Adam launch left the buffer zeroed
+                self.engine.zero_grads()
+            self._grads_clean = False
         self._gate(n)
         mark("zero+gate", coarse=True)
         self.engine.encoder_fwd(x, b)
@@ -317,7 +330,7 @@ class Learner:
             # only Adam (and the returned loss): on the tensor-core engine they leave the dgrad chain for the second
             # side stream, which encoder_bwd joins at the end of the step
             on_side2 = getattr(self.engine, "_on_side2", None)
-            if on_side2 is not None and os.environ.get("GCCVAE_GATE_BWD_STREAM", "side") != "main":
+            if on_side2 is not None and os.environ.get("GCCVAE_GATE_BWD_STREAM", "main") != "main":
                 on_side2(gate_bwd)
             else:
                 gate_bwd()
@@ -369,7 +382,7 @@ class Learner:
             return self._train_step_graphed(x, y, supervised, k)
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
         self._allreduce_grads()
-        self.optimiser.apply_gradients()
+        self._grads_clean = self.optimiser.apply_gradients()
         return loss, c
 
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
@@ -408,13 +421,17 @@ class Learner:
             g["x"].copy_(x, non_blocking=True)
             if supervised:
                 g["y"].copy_(torch.as_tensor(y), non_blocking=True)
+        if self.world == 1 and g["clean"] and not self._grads_clean:
+            self.engine.zero_grads()   # this graph was captured without a memset: it relies on the previous Adam launch
         g["graph"].replay()
         g["done"] = torch.cuda.Event()
         g["done"].record(main)
         self.lib.gccvae_add_launch_count(g["launches"])
         if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
             self._allreduce_grads()
-            self.optimiser.apply_gradients()
+            self._grads_clean = self.optimiser.apply_gradients()
+        else:
+            self._grads_clean = g["clean"]
         return g["loss"], self._c
 
     def _capture(self, key):
@@ -427,7 +444,7 @@ class Learner:
                 self.engine.marks = []
             loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
             if self.world == 1:
-                self.optimiser.apply_gradients()
+                self._grads_clean = self.optimiser.apply_gradients()
                 getattr(self.engine, "mark", lambda *a, **k: None)("adam", coarse=True)
             return loss
 
@@ -448,7 +465,7 @@ class Learner:
         torch.cuda.synchronize(self.device)
         for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
             dst.copy_(src)
-        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None)
+        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None, clean=self._grads_clean)
 
     def classifier_accuracy(self, x, y, noise=None):
         """gated_ccvae.py:421-446."""
