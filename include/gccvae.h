@@ -291,12 +291,14 @@ int gccvae_recon_f32(const float* x, const float* xhat, int batch, int per_image
 int gccvae_adam_f32(float* param, const float* grad, float* m, float* v, long long n, float lr,
                     float beta1, float beta2, float eps, int step, int* step_dev, void* stream);
 
-/* The same update as ONE launch for the replayed step: t = step_state[0] + 1 is used and published to
- * step_state[0] when the kernel ends; grad[0..n_zero) is cleared behind the read (n_zero >= n), so the next backward
- * pass accumulates into a clean buffer without a memset.  step_state: 2 device ints {t, 0}; the second is the
- * kernel's block ticket and must be 0 on entry (it is left at 0). */
-int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long n, long long n_zero, float lr,
-                          float beta1, float beta2, float eps, int* step_state, void* stream);
+/* The same update as ONE launch for the replayed step: t = step_state[0] + 1 is used; grad[i0..n_zero) is cleared
+ * behind the read (n_zero >= n), so the next backward pass accumulates into a clean buffer without a memset.  Elements
+ * [i0, n) are updated.  publish != 0: step_state[0] = t when the kernel ends.  A step may therefore run the update in
+ * two launches over disjoint ranges - the second one publishing - e.g. everything but the first layer while the last
+ * dgrad is still running.  step_state: 2 device ints {t, 0}; the second is the block ticket of the publishing launch
+ * and must be 0 on entry (it is left at 0). */
+int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long i0, long long n, long long n_zero,
+                          float lr, float beta1, float beta2, float eps, int* step_state, int publish, void* stream);
 
 /* loss[0] = sum_b(-elbo_b)/batch_global (+ gating_reg*mean|mu| when mu != NULL): the forward-only
  * value of sup_loss / unsup_loss (gated_ccvae.py:225-230, 291-298). */

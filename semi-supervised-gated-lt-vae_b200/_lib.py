@@ -111,7 +111,7 @@ SIGNATURES = {
     "gccvae_gate_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_recon_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gccvae_adam_f32": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _P, _P]),
-    "gccvae_adam_fused_f32": (_I, [_P, _P, _P, _P, _LL, _LL, _F, _F, _F, _F, _P, _P]),
+    "gccvae_adam_fused_f32": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _F, _F, _F, _F, _P, _I, _P]),
     "gccvae_elbo_loss_f32": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P]),
     "gccvae_draw_noise_f32": (_I, [_I, _U64, _U64, _I, _I, _P, _P]),
     "gccvae_head_act_f32": (_I, [_P, _P, _LL, _P, _P, _P]),

@@ -2408,6 +2408,8 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
     p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_side = -g_colsum_mod;
     g_colsum = nullptr;
     GCC_REQUIRE(p.colsum_side == 1 && p.colsum_n > 0 && p.colsum_n <= CS, "tap4_wg: fused bias gradient: S side only");
+    // in x2 mode the epilogue warps build the A tile; the column-sum path of wgrad_kernel assumes they are idle
+    GCC_REQUIRE(env_tma, "tap4_wg: the fused bias gradient is not supported with the thread-built A tile");
   }
   const int groups = (batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
@@ -2467,7 +2469,16 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   p.x = x; p.x_u8 = x_u8; p.bias = bias; p.coef = coef; p.log_pxz = log_pxz; p.D2 = (uint4*)D2; p.xhat = xhat; p.db = db;
   p.batch = batch; p.total_tiles = batch * 9;
   p.timeline = g_timeline;
-  const int per_sm = 3;
+  // CTAs per SM: the kernel is bound by the latency of its per-tile chain (TMA -> MMA -> epilogue), not by a
+  // throughput: more resident CTAs = more tiles in flight.  Limits: 4 x 77 registers x 192 threads, 4 x 39 KB of shared
+  // memory (one A stage each), 4 x 64 TMEM columns.  GCCVAE_CTR_PER_SM overrides (A/B runs).
+  static int env_per_sm = -1;
+  if (env_per_sm < 0) {
+    const char* e = getenv("GCCVAE_CTR_PER_SM");
+    env_per_sm = e ? atoi(e) : 0;
+  }
+  int per_sm = env_per_sm > 0 ? env_per_sm : 4;   // measured on B200 (batch 1024): 2 -> 1.469, 3 -> 1.444, 4 -> 1.430 ms per step pair
+  if (per_sm > 4) per_sm = 4;
   int stages = (200 * 1024 / per_sm - 4096 - 4096) / (4 * 8192);
   if (stages > 4) stages = 4;
   GCC_REQUIRE(stages >= 1, "convt_recon: shared memory");

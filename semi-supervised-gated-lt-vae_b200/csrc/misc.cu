@@ -99,16 +99,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 }
 
 // The same update with the step bookkeeping inside: t = state[0] + 1 is used, the gradient buffer is cleared behind
-// the read (the next backward accumulates into it: no separate memset on the step's critical path), and the last
-// block to finish publishes state[0] = t (state[1] is the ticket counter, left at 0).  One launch instead of three.
+// the read (the next backward accumulates into it: no separate memset on the step's critical path), and - when
+// `publish` is set - the last block to finish publishes state[0] = t (state[1] is the ticket counter, left at 0).
+// The element range [i0, n) lets the step run the update in two parts: everything but the first layer's parameters
+// as soon as their gradients are complete (concurrently with the last dgrad), the rest at the very end (publishing).
 __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, float* __restrict__ g,
-                                                         float* __restrict__ m, float* __restrict__ v, long long n,
-                                                         long long n_zero, float lr, float b1, float b2, float eps,
-                                                         int* __restrict__ state) {
+                                                         float* __restrict__ m, float* __restrict__ v, long long i0,
+                                                         long long n, long long n_zero, float lr, float b1, float b2,
+                                                         float eps, int* __restrict__ state, int publish) {
   pdl_prologue();
   const int t = state[0] + 1;
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < n_zero; i += (long long)gridDim.x * 256) {
+  for (long long i = i0 + blockIdx.x * 256LL + threadIdx.x; i < n_zero; i += (long long)gridDim.x * 256) {
     if (i < n) {
       const float gi = g[i];
       const float mi = m[i] + (gi - m[i]) * (1.0f - b1);
@@ -119,6 +121,7 @@ __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, 
     }
     g[i] = 0.0f;
   }
+  if (!publish) return;
   __syncthreads();                      // every thread of this block has read state[0]
   if (threadIdx.x == 0) {
     __threadfence();
@@ -261,13 +264,14 @@ extern "C" int gccvae_adam_f32(float* param, const float* grad, float* m, float*
   return GCCVAE_OK;
 }
 
-extern "C" int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long n, long long n_zero,
-                                     float lr, float beta1, float beta2, float eps, int* step_state, void* stream) {
-  GCC_REQUIRE(param && grad && m && v && n > 0 && n_zero >= n && step_state, "adam_fused: bad args");
-  long long blocks = (n_zero + 255) / 256;
+extern "C" int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long i0, long long n,
+                                     long long n_zero, float lr, float beta1, float beta2, float eps, int* step_state,
+                                     int publish, void* stream) {
+  GCC_REQUIRE(param && grad && m && v && i0 >= 0 && n > i0 && n_zero >= n && step_state, "adam_fused: bad args");
+  long long blocks = (n_zero - i0 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
-  GCC_CUDA(launch_pdl_k(adam_fused_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, n,
-                        n_zero, lr, beta1, beta2, eps, step_state));
+  GCC_CUDA(launch_pdl_k(adam_fused_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, i0,
+                        n, n_zero, lr, beta1, beta2, eps, step_state, publish));
   GCC_CHECK_LAUNCH("adam_fused");
   return GCCVAE_OK;
 }

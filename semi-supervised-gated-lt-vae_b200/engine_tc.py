@@ -93,6 +93,8 @@ class EngineTC(Engine):
         self.side2 = (torch.cuda.Stream(device=dev)
                       if self.side is not None and os.environ.get("GCCVAE_BGRAD_STREAM", "side") != "main" else None)
         self.bias_in_wgrad = os.environ.get("GCCVAE_BIAS_IN_WGRAD", "0") != "0"
+        # ... or for selected layers only (comma-separated names)
+        self.bias_in_wgrad_layers = set(filter(None, os.environ.get("GCCVAE_BIAS_IN_WGRAD_LAYERS", "").split(",")))
         self.wg_rr = os.environ.get("GCCVAE_WG_RR", "0") != "0"   # weight gradients alternate between both side streams
         # bias gradients fused into the epilogue of the dgrad that produces the layer's pre-activation gradient
         # (column sums of what it stores): no separate pass over the tensor.  Off: column-sum kernels on side2.
@@ -103,6 +105,11 @@ class EngineTC(Engine):
         self._rr = 0
         self._deferred_bias = []
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
+        # called once per backward pass when every gradient except the first layer's is complete or queued: the
+        # Learner hangs the bulk of the Adam update here, so that only the first layer's update follows the last dgrad
+        self.tail_hook = None
+        self.side3 = None          # its own stream: the first layer's weight / bias gradients must not queue behind it
+        self._side3_used = False
         # debug timeline (GCCVAE_MARKERS=1: a globaltimer marker kernel after every op, 2: only at segment ends)
         self.mark_level = int(os.environ.get("GCCVAE_MARKERS", "0"))
         self.mark_buf = torch.zeros(1024, dtype=torch.int64, device=dev) if self.mark_level else None
@@ -289,6 +296,9 @@ class EngineTC(Engine):
             torch.cuda.current_stream().wait_stream(self.side)
             if self.side2 is not None:
                 torch.cuda.current_stream().wait_stream(self.side2)
+            if self._side3_used:
+                torch.cuda.current_stream().wait_stream(self.side3)
+                self._side3_used = False
 
     def _fuse_bias(self, name, n, mod=0):
         """the NEXT dgrad launch (main stream) also accumulates the bias gradient of layer `name` in its epilogue."""
@@ -307,7 +317,9 @@ class EngineTC(Engine):
         stream.  GCCVAE_BIAS_IN_WGRAD=1: the next wgrad launch produces it from its staged operand tiles (side 1:
         S operand, 2: L operand) with its idle epilogue warps - one pass less over dout, but measured 1 % slower
         end to end on B200 (the stage release waits for the column sums), so it is off by default."""
-        if self.bias_in_wgrad and not (self.s2d and side == 2):   # (the s2d wgrad sums the S operand only)
+        x2_layer = self.x2 and name in ("enc.conv1", "dec.conv5t")    # their wgrad's epilogue warps build the A tile
+        if ((self.bias_in_wgrad or name in self.bias_in_wgrad_layers) and not x2_layer
+                and not (self.s2d and side == 2)):   # (the s2d wgrad sums the S operand only)
             self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, -side)
         elif dout is not None:
             self._deferred_bias.append((dout, name, n))
@@ -525,9 +537,27 @@ class EngineTC(Engine):
                     self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
                         C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
             self._side(wg)
+            hook = self.tail_hook if name == TC_ENC[0] else None
+            ev = None
+            if hook is not None and self.side is not None and self.side2 is not None:
+                ev = torch.cuda.Event()
+                ev.record(torch.cuda.current_stream())     # everything the main stream has produced so far
             # this dgrad's output is pn's pre-activation gradient; the dense conv5 dgrad emits (kh,kw,cl) columns
             self._fuse_bias(pn, _ENC[pn][3][2], mod=(_ENC[pn][3][2] if name == "enc.conv5" else 0))
             self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad", mask_s2d=s2d_l)
+            if hook is not None:
+                self.tail_hook = None
+                if ev is not None:     # under the last dgrad: after all earlier weight / bias gradients, not after it
+                    if self.side3 is None:
+                        self.side3 = torch.cuda.Stream(device=self.device)
+                    self.side3.wait_event(ev)
+                    self.side3.wait_stream(self.side)
+                    self.side3.wait_stream(self.side2)
+                    with torch.cuda.stream(self.side3):
+                        hook()
+                    self._side3_used = True
+                else:
+                    hook()
         dh1 = b["enc.conv1.dout"]
         def wg1():
             self._arm_wgrad_bias("enc.conv1", 32, 1, dh1)

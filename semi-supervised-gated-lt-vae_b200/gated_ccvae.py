@@ -137,18 +137,22 @@ class KerasAdam:
     def iterations(self):
         return int(self.step_dev[0].item())
 
-    def apply_gradients(self):
-        """one launch: t += 1, the Adam update of the trainable prefix, and the gradient buffer cleared for the next
-        backward pass (which accumulates into it).  Returns True if the gradient buffer was cleared."""
+    def apply_gradients(self, lo=0, hi=None, publish=True):
+        """one launch: the Adam update of parameters [lo, hi) of the trainable prefix with t = iterations + 1, the
+        gradient buffer cleared behind the read (the next backward pass accumulates into it), and - `publish` - the
+        step counter advanced.  Returns True if the gradient buffer is clean afterwards."""
         if os.environ.get("GCCVAE_ADAM", "fused") == "split":    # A/B switch: counter bump + update as two launches
+            assert lo == 0 and hi is None
             _lib.check(self.lib.gccvae_adam_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
                                                 self.n, self.lr, self.beta_1, self.beta_2, self.epsilon, 0,
                                                 ptr(self.step_dev), _stream()), "adam")
             return False
+        n = self.n if hi is None else min(int(hi), self.n)
+        zero_hi = self.store.total if hi is None else n
         _lib.check(self.lib.gccvae_adam_fused_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
-                                                  self.n, self.store.total, self.lr, self.beta_1, self.beta_2,
-                                                  self.epsilon, ptr(self.step_dev), _stream()), "adam")
-        return True
+                                                  int(lo), n, zero_hi, self.lr, self.beta_1, self.beta_2, self.epsilon,
+                                                  ptr(self.step_dev), int(bool(publish)), _stream()), "adam")
+        return bool(publish)
 
 
 class Learner:
@@ -179,6 +183,10 @@ class Learner:
         self._graphs = {}
         self._graph_turn = {}
         self._grads_clean = False        # True right after apply_gradients (it clears the gradient buffer)
+        # single GPU, tensor-core engine: Adam runs in two parts - everything but the first layer's parameters as soon
+        # as their gradients are complete (on a side stream, under the last dgrad), the first layer at the very end
+        self._adam_cut = self.store.offsets["enc.conv2.w"][0]
+        self._adam_head_done = False
         self._copy_stream = None
         self.last = {}
         self._lat = {}
@@ -380,9 +388,27 @@ class Learner:
         """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update."""
         if self.use_graphs and noise is None:
             return self._train_step_graphed(x, y, supervised, k)
+        return self._step_body(x, y, supervised, noise, k)
+
+    def _adam_head(self):
+        self.optimiser.apply_gradients(lo=self._adam_cut, hi=None, publish=False)
+        self._adam_head_done = True
+
+    def _step_body(self, x, y, supervised, noise, k):
+        """forward + backward + (all-reduce) + Adam, as issued eagerly or captured into the step's graph."""
+        split = (self.world == 1 and hasattr(self.engine, "tail_hook")
+                 and os.environ.get("GCCVAE_ADAM_TAIL", "1") != "0" and os.environ.get("GCCVAE_ADAM", "fused") != "split")
+        self._adam_head_done = False
+        if split:
+            self.engine.tail_hook = self._adam_head
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
-        self._allreduce_grads()
-        self._grads_clean = self.optimiser.apply_gradients()
+        if split:
+            self.engine.tail_hook = None
+        if self._adam_head_done:
+            self._grads_clean = self.optimiser.apply_gradients(lo=0, hi=self._adam_cut, publish=True)
+        else:
+            self._allreduce_grads()
+            self._grads_clean = self.optimiser.apply_gradients()
         return loss, c
 
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
@@ -442,10 +468,11 @@ class Learner:
         def body():
             if getattr(self.engine, "marks", None) is not None:
                 self.engine.marks = []
-            loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
             if self.world == 1:
-                self._grads_clean = self.optimiser.apply_gradients()
+                loss, _ = self._step_body(xs, ys, supervised, None, k)
                 getattr(self.engine, "mark", lambda *a, **k: None)("adam", coarse=True)
+            else:       # NCCL stays outside the graph: the all-reduce and Adam follow the replay
+                loss, _ = self._elbo(xs, ys, supervised, None, backward=True, k=k)
             return loss
 
         # warm-up on a side stream (first-use attribute calls, buffer allocation), state restored afterwards
