@@ -7,7 +7,7 @@ one() { ( cd "$1" && env $2 timeout 120 python bench.py --no-cpu-baseline --step
 for i in $(seq $R); do
   for arm in "$@"; do
     case "$arm" in
-      base) echo "base: $(one _ab/base GCCVAE_GATE_BWD_STREAM=main)";;
+      base) echo "base: $(one _ab/base AB_DUMMY=1)";;
       -) echo "new: $(one . AB_DUMMY=1)";;
       *) echo "new[$arm]: $(one . "${arm//,/ }")";;
     esac

@@ -1,7 +1,10 @@
-"""Debug probe: per-item pipeline timeline of block 0 of a tap-GEMM launch (clock64 ticks -> ns)."""
+"""Debug probe: per-item pipeline timeline of block 0 of a tap-GEMM launch (clock64 ticks -> ns).
+Needs the instrumented build: `GCCVAE_TIMELINE=1 python semi-supervised-gated-lt-vae_b200/build.py` -> csrc/libgccvae_tl.so
+(the hooks are compiled out of the production library: they cost ~25 % of the c3conv epilogue even when idle)."""
 import ctypes as C
 import sys
 import os
+os.environ.setdefault("GCCVAE_LIB", "libgccvae_tl.so")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 import gccvae_b200._lib as L

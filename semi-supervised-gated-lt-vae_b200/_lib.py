@@ -7,7 +7,8 @@ import os
 import threading
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libgccvae.so")
+# GCCVAE_LIB selects another build of the same library in csrc/ (libgccvae_tl.so: timeline hooks compiled in)
+LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("GCCVAE_LIB", "libgccvae.so"))
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ACCUMULATE = 0, 1, 2, 0x100
 OUT_S2D, MASK_S2D = 0x10, 0x20   # layout flags OR-ed into `act` (include/gccvae.h)

@@ -12,12 +12,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 INCLUDE = os.path.join(ROOT, "include")
-LIB = os.path.join(CSRC, "libgccvae.so")
+# GCCVAE_TIMELINE=1 builds the instrumented variant (pipeline timeline hooks of scripts/timeline_probe.py compiled in)
+TIMELINE = os.environ.get("GCCVAE_TIMELINE", "0") not in ("", "0")
+LIB = os.path.join(CSRC, "libgccvae_tl.so" if TIMELINE else "libgccvae.so")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE, "-I", CSRC,
-]
+] + (["-DGCCVAE_TIMELINE"] if TIMELINE else [])
 
 
 def _nvcc() -> str:
@@ -44,7 +46,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     nvcc = _nvcc()
-    objdir = os.path.join(CSRC, "build")
+    objdir = os.path.join(CSRC, "build_tl" if TIMELINE else "build")
     os.makedirs(objdir, exist_ok=True)
 
     def compile_one(src):

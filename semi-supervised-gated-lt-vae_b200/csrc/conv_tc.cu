@@ -66,11 +66,24 @@ struct alignas(64) TapGemmParams {
   int out_s2d, mask_s2d;   // the output / the mask tensor is stored in s2d block form (bf16 only)
 };
 
+// Pipeline timeline (scripts/timeline_probe.py).  Compiled in only with -DGCCVAE_TIMELINE (libgccvae_tl.so): even with
+// a NULL buffer the hooks cost a constant-bank load, a special-register read and a predicate chain per event, which
+// the ncu source view showed as ~25 % of the stall samples of the (epilogue-bound) c3conv epilogue.
+#ifdef GCCVAE_TIMELINE
+#define TL_ON(p) ((p).timeline != nullptr)
 #define TL(item_local, slot)                                                              \
   do {                                                                                    \
     if (p.timeline != nullptr && blockIdx.x == 0 && (item_local) < 32)                    \
       p.timeline[(item_local) * 8 + (slot)] = clock64();                                  \
   } while (0)
+#define C3_DBG(p) ((p).dbg)      // GCCVAE_C3_DBG bit switches of c3conv (skip stores / loads / relaxed waits)
+#else
+#define TL_ON(p) false
+#define C3_DBG(p) 0
+#define TL(item_local, slot) \
+  do {                       \
+  } while (0)
+#endif
 
 constexpr int TG_THREADS = 192;
 
@@ -159,7 +172,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   pdl_wait();   // everything above overlapped the predecessor's tail; its outputs are needed from here on
-  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+  if (TL_ON(p) && threadIdx.x == 0 && blockIdx.x < 1024) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.timeline[40 * 8 + 2 * blockIdx.x] = (long long)gt;
@@ -181,9 +194,9 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
         const int aw = p.a_scale * w0, ah = p.a_scale * h0, brow = p.b_row0[phase_id] + slab * p.N;
         int t = 0, c = 0;
         for (int it = 0; it < k_iters; it += p.tps) {
-          const long long tw0 = p.timeline ? clock64() : 0;
+          const long long tw0 = TL_ON(p) ? clock64() : 0;
           mbar_wait(&empty[stage], ph ^ 1);
-          if (p.timeline) prod_wait += clock64() - tw0;
+          if (TL_ON(p)) prod_wait += clock64() - tw0;
           if (it == 0) TL(item - item_beg, 0);
           mbar_expect_tx(&full[stage], stage_tx);
           uint8_t* a_dst = sA + stage * stage_stride;
@@ -199,7 +212,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
-      if (p.timeline != nullptr && blockIdx.x == 0) {
+      if (TL_ON(p) && blockIdx.x == 0) {
         p.timeline[32 * 8 + 0] = prod_wait;
         p.timeline[32 * 8 + 1] = clock64() - tp0;
       }
@@ -221,16 +234,16 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const long long tm0 = clock64();
       for (int item = item_beg; item < item_end; ++item) {
         const int li = item - item_beg, as = li & 1;
-        const long long ta0 = p.timeline ? clock64() : 0;
+        const long long ta0 = TL_ON(p) ? clock64() : 0;
         mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
-        if (p.timeline) acc_wait += clock64() - ta0;
+        if (TL_ON(p)) acc_wait += clock64() - ta0;
         tc_fence_after();
         TL(li, 2);
         const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols;
         for (int it = 0; it < k_iters; it += p.tps) {
-          const long long tw0 = p.timeline ? clock64() : 0;
+          const long long tw0 = TL_ON(p) ? clock64() : 0;
           mbar_wait(&full[stage], ph);
-          if (p.timeline) mma_wait += clock64() - tw0;
+          if (TL_ON(p)) mma_wait += clock64() - tw0;
           tc_fence_after();
           if (it + p.tps >= k_iters) TL(li, 3);
           uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * st_step);
@@ -247,7 +260,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
-      if (p.timeline != nullptr && blockIdx.x == 0) {
+      if (TL_ON(p) && blockIdx.x == 0) {
         p.timeline[32 * 8 + 2] = mma_wait;
         p.timeline[32 * 8 + 3] = acc_wait;
         p.timeline[32 * 8 + 4] = clock64() - tm0;
@@ -435,7 +448,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
     tc_fence_before();
   }
   __syncthreads();
-  if (p.timeline != nullptr && threadIdx.x == 0 && blockIdx.x < 1024) {
+  if (TL_ON(p) && threadIdx.x == 0 && blockIdx.x < 1024) {
     unsigned long long gt;
     asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
     p.timeline[40 * 8 + 2 * blockIdx.x + 1] = (long long)gt;
@@ -1581,13 +1594,13 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int n = tile >> 3, h0 = (tile & 7) * 4;
       const uint4* src = p.in2 + (((size_t)n * 33 + (h0 + dy)) * 33 + dx) * 2;
-      if (p.dbg & 4) mbar_wait(&empty[stage], ph ^ 1);
+      if (C3_DBG(p) & 4) mbar_wait(&empty[stage], ph ^ 1);
       else mbar_wait_relaxed(&empty[stage], ph ^ 1);
       if (m == 0) TL(tile - tile_beg, 0);
       const uint32_t dst = smem_u32(sA + stage * A_TILE) + row_off;
 #pragma unroll
       for (int t = 0; t < 4; ++t) {
-        if (p.dbg & 2) break;
+        if (C3_DBG(p) & 2) break;
         const uint4* sp = src + ((t >> 1) * 33 + (t & 1)) * 2;
 #pragma unroll
         for (int h = 0; h < 2; ++h)
@@ -1705,7 +1718,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
         uint32_t w[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        if (!(p.dbg & 1)) st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.N + c0, w);
+        if (!(C3_DBG(p) & 1)) st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + opix * p.N + c0, w);
       }
       if (threadIdx.x == 160) TL(li, 6);
     }
@@ -2479,6 +2492,8 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   }
   int per_sm = env_per_sm > 0 ? env_per_sm : 4;   // measured on B200 (batch 1024): 2 -> 1.469, 3 -> 1.444, 4 -> 1.430 ms per step pair
   if (per_sm > 4) per_sm = 4;
+  // (3 CTAs x 2 stages fit as well - 224 KB / 3 - but measured slower than 4 x 1: the kernel is bound by the TMA
+  // row rate, profiles/r01c_timeline_probe.txt)
   int stages = (200 * 1024 / per_sm - 4096 - 4096) / (4 * 8192);
   if (stages > 4) stages = 4;
   GCC_REQUIRE(stages >= 1, "convt_recon: shared memory");
