@@ -320,10 +320,11 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       // bias index of this slab's first channel: host guarantees bias_mod % N == 0 or bias_mod >= n_store,
       // so no per-element modulo is needed
       const int bias_base = slab0 % p.bias_mod;
+      const uint32_t s_bias_u32 = smem_u32(s_bias);
       for (int c0 = 0; c0 < p.N; c0 += 16) {
         const int cg = slab0 + c0;  // global output channel of this chunk
         // bias_base + c0 + i < 256 always: bias_mod <= 256 wraps it, otherwise n_store <= 256
-        const float* bsrc = s_bias + ((bias_base + c0) & 255);
+        const uint32_t bsrc = s_bias_u32 + (uint32_t)(((bias_base + c0) & 255) * 4);
         uint32_t r[16];
         tmem_ld16(tacc + (uint32_t)c0, r);
         tmem_ld_wait();
@@ -336,7 +337,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
         float v[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(bsrc + 4 * i);
+          const float4 t = lds_f4(bsrc + 16u * i);
           v[4 * i] = __uint_as_float(r[4 * i]) + t.x;
           v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + t.y;
           v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + t.z;
@@ -509,7 +510,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   uint64_t* tempty = tfull + 2;
   uint64_t* bfull = tempty + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bfull + 1);
-  float* s_bias = reinterpret_cast<float*>(tmem_slot + 4);   // [256]
+  float* s_bias = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(tmem_slot + 4) + 15) & ~(uintptr_t)15);   // [256], 16-byte aligned (ld.shared.v4)
   float* s_col = s_bias + 256;                                // [256] per-CTA column sums
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -606,6 +607,7 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
   } else {
     // ===== epilogue: 8 warps; warp pair (q, q+4) shares TMEM lane quadrant q, each takes 2 phases =====
     const int ew = warp - 2, q = warp & 3, half = ew >> 2;
+    const uint32_t s_bias_u32 = smem_u32(s_bias);
     const int m = q * 32 + lane;
     const int dy = m / p.BW, dx = m % p.BW;
     float cacc[COLSUM ? 4 : 1][16];   // running column sums of this thread's rows (bias gradient)
@@ -653,7 +655,13 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
           if (c0 >= p.n_store) continue;
           float v[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]) + s_bias[c0 + i];
+          for (int i = 0; i < 4; ++i) {
+            const float4 t = lds_f4(s_bias_u32 + (uint32_t)(c0 + 4 * i) * 4u);
+            v[4 * i] = __uint_as_float(r[4 * i]) + t.x;
+            v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + t.y;
+            v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + t.z;
+            v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + t.w;
+          }
           if (p.act == GCCVAE_ACT_RELU) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
@@ -1653,6 +1661,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
       }
       asm volatile("bar.sync 1, 128;" ::: "memory");
     }
+    const uint32_t s_bias_u32 = smem_u32(s_bias);
     // the ReLU mask does not depend on the accumulator: it is fetched one tile ahead (register double buffer)
     const bool use_mask = p.mask != nullptr;
     uint32_t mnext[NCH][8];
@@ -1695,7 +1704,7 @@ __global__ void __launch_bounds__(C3_THREADS, 2) c3conv_kernel(const __grid_cons
         float v[16];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          const float4 t = *reinterpret_cast<const float4*>(s_bias + c0 + 4 * i);
+          const float4 t = lds_f4(s_bias_u32 + (uint32_t)(c0 + 4 * i) * 4u);
           v[4 * i] = __uint_as_float(r[c][4 * i]) + t.x;
           v[4 * i + 1] = __uint_as_float(r[c][4 * i + 1]) + t.y;
           v[4 * i + 2] = __uint_as_float(r[c][4 * i + 2]) + t.z;

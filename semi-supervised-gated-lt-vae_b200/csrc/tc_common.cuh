@@ -12,6 +12,14 @@ namespace gccvae {
 namespace tc {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+// 16-byte shared-memory load through the shared window (ld.shared, short scoreboard).  A float4 dereference of a
+// pointer derived from the dynamic shared-memory base compiles to a GENERIC load (LD.E.128, long scoreboard): in
+// the epilogues that put ~15 % of the kernel's stall samples on the bias add (profiles/r01d_*).
+__device__ __forceinline__ float4 lds_f4(uint32_t smem_addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(smem_addr));
+  return v;
+}
 
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
