@@ -45,7 +45,8 @@ def parse():
     ap.add_argument("--precision", default=os.environ.get("GCCVAE_PRECISION", "auto"))
     ap.add_argument("--batch", type=int, default=1024)
     ap.add_argument("--ref-batch", type=int, default=256)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=3)
+    ap.add_argument("--cpu-baseline-steps", type=int, default=60,
+                    help="timed oracle steps of the cpu_baseline leg (60 x ~175 ms = ~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     # the other BASELINE.json configs (parity / study cases, not the headline line)
@@ -274,7 +275,7 @@ def run_ours(args, rank, world, local_rank):
                 "bytes_per_launch": nbytes, "ms_per_launch": ms, "launches_per_step": n,
                 "share_of_profiled_step": ms * n / tot, "traffic": None}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01b_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
             roof["traffic"] = traffic.get(name)
         except Exception:
             pass
