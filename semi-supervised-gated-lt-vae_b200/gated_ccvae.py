@@ -447,8 +447,8 @@ class Learner:
             g["x"].copy_(x, non_blocking=True)
             if supervised:
                 g["y"].copy_(torch.as_tensor(y), non_blocking=True)
-        if self.world == 1 and g["clean"] and not self._grads_clean:
-            self.engine.zero_grads()   # this graph was captured without a memset: it relies on the previous Adam launch
+        if g["clean"] and not self._grads_clean:
+            self.engine.zero_grads()   # the graph was captured without a memset: it relies on the previous Adam launch
         g["graph"].replay()
         self.lib.gccvae_add_launch_count(g["launches"])
         if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
@@ -490,13 +490,22 @@ class Learner:
         torch.cuda.synchronize(self.device)
         graph = torch.cuda.CUDAGraph()
         n0 = self.lib.gccvae_launch_count()
+        # the captured step carries no gradient memset: every replay starts from the buffer the (fused) Adam launch of
+        # the previous step cleared - inside the graph on one GPU, after the all-reduce in data-parallel runs
+        fused = os.environ.get("GCCVAE_ADAM", "fused") != "split"
+        if fused:
+            if not self._grads_clean:
+                self.engine.zero_grads()
+            self._grads_clean = True
         with torch.cuda.graph(graph):
             loss = body()
         launches = self.lib.gccvae_launch_count() - n0
         torch.cuda.synchronize(self.device)
         for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
             dst.copy_(src)
-        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None, clean=self._grads_clean)
+        if fused:
+            self._grads_clean = True     # nothing ran during the capture: the buffer is as clean as before it
+        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None, clean=fused)
 
     def classifier_accuracy(self, x, y, noise=None):
         """gated_ccvae.py:421-446."""
