@@ -16,7 +16,7 @@ cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True)
 x = torch.rand(B, 64, 64, 3, device="cuda")
 y = (torch.rand(B, 18, device="cuda") < 0.5).long()
-for sup in (True,):
+for sup in (True, False):
     for _ in range(5):
         lrn.train_step(x, y if sup else None, sup)
     torch.cuda.synchronize()

@@ -1902,6 +1902,19 @@ static int pick_tile(int H, int W, int* bw, int* bh, int* bn) {
 
 static bool g_pdl = true;   // programmatic dependent launch for the tensor-core kernels (GCCVAE_PDL=0 disables)
 
+// CTAs per SM of the weight-gradient kernels and their shared-memory budget per CTA (KB).  They run on a side stream
+// UNDER the dgrad chain: what they occupy is not available to the critical path's persistent CTAs.
+static int wg_per_sm() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GCCVAE_WG_PER_SM"); v = e ? atoi(e) : 2; if (v < 1) v = 1; if (v > 2) v = 2; }
+  return v;
+}
+static int wg_smem_kb() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("GCCVAE_WG_SMEM_KB"); v = e ? atoi(e) : 100; if (v < 40) v = 40; if (v > 190) v = 190; }
+  return v;
+}
+
 template <class Params>
 static cudaError_t launch_pdl(void (*kernel)(const Params), dim3 grid, int threads, size_t smem, cudaStream_t st,
                               const Params& p) {
@@ -2435,12 +2448,12 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   }
   const int groups = (batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
-  int splits = 148 * 2;
+  int splits = 148 * wg_per_sm();
   if (splits > p.tiles_total) splits = p.tiles_total;
   p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
-  int stages = (100 * 1024) / stage_bytes;   // two CTAs per SM
+  int stages = (wg_smem_kb() * 1024) / stage_bytes;   // default 100 KB: two CTAs per SM
   if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
@@ -2617,13 +2630,13 @@ extern "C" int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void*
   const int groups = (batch + bn - 1) / bn;
   p.tiles_total = groups * p.tiles_w * p.tiles_h;
   const int mtiles = (16 * CL) / 128;
-  int splits = (148 * 2 + mtiles - 1) / mtiles;
+  int splits = (148 * wg_per_sm() + mtiles - 1) / mtiles;
   if (splits > p.tiles_total) splits = p.tiles_total;
   if (splits < 1) splits = 1;
   p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
   const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
-  int stages = (100 * 1024) / stage_bytes;   // two CTAs per SM
+  int stages = (wg_smem_kb() * 1024) / stage_bytes;   // default 100 KB: two CTAs per SM
   if (stages > 4) stages = 4;
   if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
   if (stages < 1) stages = 1;
