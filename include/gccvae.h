@@ -271,7 +271,10 @@ int gccvae_latent_bwd(const gccvae_latent_bwd_args* a, void* stream);
 
 /* reduce the partials; chain through c to mu (clip / pow / ratio of gated_ccvae.py:103-109) and
  * add the L1 term gating_reg*mean|mu| (gated_ccvae.py:229-230,297-298) scaled by l1_scale
- * (1/world in data parallel).  d* may be NULL when the tensor is frozen. */
+ * (1/world in data parallel).  d* may be NULL when the tensor is frozen.
+ * One launch: every block reduces a slice of the partial rows, the block that draws the last ticket forms the
+ * gradients.  The ticket is float slot 2*324 + 31 of gate_ws (a spare slot of the bias row): gccvae_gate_fwd zeroes it
+ * on every launch and this kernel leaves it at zero, so gate_ws must come from gccvae_gate_fwd (or be zero-filled). */
 int gccvae_gate_bwd(float* partials /* [n_partials + 1 rows]: the last row is scratch */, int n_partials, const float* mu, const float* Wcls,
                     const float* Wlt, const float* Wlf, const float* Wst, const float* Wsf,
                     const float* gate_ws, float gating_reg, float l1_scale, float* dWcls, float* dbcls,

@@ -1,17 +1,20 @@
 """bf16 tensor-core executor of the ELBO step (tcgen05 / TMEM / TMA kernels of csrc/conv_tc.cu).
 
-Activations between the convolutions are bf16 NHWC; accumulation, biases, the latent stage, the
-losses and all gradients of parameters are fp32.  Layer -> kernel map:
+Activations between the convolutions are bf16; accumulation, biases, the latent stage, the losses and all gradients
+of parameters are fp32.  Layer -> kernel map of the default (x2 + s2d) mode, DESIGN.md "Data layout in HBM":
 
-  enc.conv1   x fp32 -> K=64 im2col matrix X64 (bf16) -> dense tcgen05 GEMM; wgrad from X64
-  enc.conv2-4 tap-GEMM (16 taps, stride-2 TMA boxes); dgrad = 4-phase tap-GEMM; wgrad = MN-major GEMM
-  enc.conv5   dense tcgen05 GEMM [B,2048]x[2048,256]
-  heads, dec.fc1, dec.conv1t   45-wide dense layers, operands zero-padded to 64 / 96: dense tcgen05 GEMMs
-  dec.conv2t-4t  4-phase tap-GEMM; dgrad = 16-tap tap-GEMM; wgrad = MN-major GEMM
-  dec.conv5t  4-phase tap-GEMM, N=16 (3 real channels), float4 image output; the reconstruction
-              log-likelihood kernel emits its gradient directly as the im2col matrix G64, from which
-              dgrad and wgrad are dense GEMMs
-Packed bf16 weight operands are refreshed from the fp32 master parameters at the start of every step.
+  image            fp32 or uint8 [B,64,64,3] -> x2 blocks [B,33,33,16] (prep_x2; u8/255 through an exact table)
+  enc.conv1        c3conv (thread-built im2col tile from x2 blocks, K = 64); wgrad tap4_wg from the same blocks
+  enc.conv2-4      tap-GEMM over the s2d form of the input (4 taps x 4 C_L); dgrad = halo kernel (conv2, conv3) or
+                   4-phase tap-GEMM; wgrad = wg_s2d (MN-major operands straight from TMA boxes, split-K)
+  enc.conv5, heads, dec.fc1, dec.conv1t   dense tcgen05 GEMMs (45-wide operands zero-padded to 64 / 96)
+  dec.conv2t-4t    forward = 4-phase tap-GEMM / halo kernel (conv3t, conv4t); dgrad = tap-GEMM over the s2d form of the
+                   output gradient; wgrad = wg_s2d
+  dec.conv5t       forward fused with sigmoid + Laplace log-likelihood + dLoss/dlogit in x2 block form (convt_recon);
+                   dgrad = c3conv over those blocks, wgrad = tap4_wg
+Weight gradients run on a side stream, bias gradients (column sums) on a second one, the bulk of Adam on a third; packed
+bf16 weight operands are refreshed from the fp32 master parameters at the start of every step (one launch).
+GCCVAE_X2=0 / GCCVAE_S2D=0 select the older im2col / NHWC formulations (kept for A/B runs and as a cross-check).
 """
 from __future__ import annotations
 
