@@ -561,15 +561,37 @@ class Learner:
                 self.store.view("mu").copy_(torch.from_numpy(np.asarray(mu_init, dtype=np.float32)))
             logging.info("Loaded learned mu")
 
+    # Keras layer names of a fresh build of the four models (first instances; `load_weights` matches by order and
+    # shape, not by name): (file stem, model name, [(layer name, number of weight tensors)])
+    _H5_LAYOUT = (
+        ("encoder_model", "encoder", [("conv2d", 2), ("conv2d_1", 2), ("conv2d_2", 2), ("conv2d_3", 2), ("conv2d_4", 2),
+                                      ("flatten", 0), ("dense", 2), ("dense_1", 2)]),
+        ("decoder_model", "decoder", [("dense_2", 2), ("reshape", 0), ("conv2d_transpose", 2), ("conv2d_transpose_1", 2),
+                                      ("conv2d_transpose_2", 2), ("conv2d_transpose_3", 2), ("conv2d_transpose_4", 2)]),
+        ("classifier", "classifier", [("my_inference_layer", 2)]),
+        ("cond_prior", "conditional__prior", [("my_cond_generation_layer", 1), ("my_cond_generation_layer_1", 1),
+                                              ("my_cond_generation_layer_2", 1), ("my_cond_generation_layer_3", 1)]),
+    )
+
     def save_model(self, param_dir, model_id):
-        """gated_ccvae.py:391-419.  The reference writes four Keras .h5 files; there is no HDF5 writer here, so the
-        same tensors go to `{stem}_{model_id}.npz` under their parameter names (load with `load_model_npz`).  The
-        learned gating matrix is written exactly as the reference does: `.npy` (+ `.csv`, z1..z18 x label names)."""
+        """gated_ccvae.py:391-419: the four `save_weights` files `{encoder_model,decoder_model,classifier,cond_prior}_
+        {model_id}.h5` in Keras' HDF5 layout (`h5lite.write_keras_weights`: layer_names / weight_names attributes,
+        `<model>/<layer>/kernel:0|bias:0` datasets - readable by `load_model` here; written to the format of the
+        reference's own files but not verified against libhdf5, which is not available), and in learnable mode the
+        gating matrix exactly as the reference writes it: `.npy` and `.csv` (z1..z18 x label names)."""
+        from .h5lite import write_keras_weights
         os.makedirs(param_dir, exist_ok=True)
         d = {k: v.cpu().numpy() for k, v in self.store.to_dict().items()}
-        for stem, prefix in self._H5_FILES:
-            np.savez(os.path.join(param_dir, "{}_{}.npz".format(stem, model_id)),
-                     **{k: v for k, v in d.items() if k.startswith(prefix)})
+        for (stem, model, layout), (_, prefix) in zip(self._H5_LAYOUT, self._H5_FILES):
+            tensors = [d[n] for n in self.store.names() if n.startswith(prefix)]
+            layers, i = [], 0
+            for lname, n in layout:
+                kinds = ("kernel:0", "bias:0")[:n]
+                layers.append((lname, [("{}/{}/{}".format(model, lname, kind), tensors[i + j])
+                                       for j, kind in enumerate(kinds)]))
+                i += n
+            assert i == len(tensors), (stem, i, len(tensors))
+            write_keras_weights(os.path.join(param_dir, "{}_{}.h5".format(stem, model_id)), layers)
         if self.train_config["gate_type"] == "learnable":
             mu = d["mu"]
             np.save(os.path.join(param_dir, "learned_gating_matrix_{}.npy".format(model_id)), mu)
@@ -577,15 +599,6 @@ class Learner:
                 fh.write("," + ",".join(CELEBA_EASY_LABELS) + "\n")
                 for i in range(mu.shape[0]):
                     fh.write("z{},".format(i + 1) + ",".join(str(t) for t in mu[i]) + "\n")   # shortest fp32 repr
-
-    def load_model_npz(self, param_dir, model_id):
-        for stem, _ in self._H5_FILES:
-            with np.load(os.path.join(param_dir, "{}_{}.npz".format(stem, model_id))) as z:
-                self.store.load_dict({k: z[k] for k in z.files})
-        if self.train_config["gate_type"] == "learnable":
-            mu = load_learned_gating_matrix(param_dir, model_id)
-            with torch.no_grad():
-                self.store.view("mu").copy_(torch.from_numpy(np.asarray(mu, dtype=np.float32)))
 
     # ---- training loop (gated_ccvae.py:313-419) ------------------------------------------------------------------------
     @staticmethod

@@ -319,3 +319,163 @@ def keras_weights(path):
             wn = wn.decode("utf8")
             out.append((wn, f["/" + lname + "/" + wn]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# writer: the same subset, laid out the way libhdf5 1.12 / h5py lays out the reference's files
+# ---------------------------------------------------------------------------------------------------------------------
+_LEAF_K, _INT_K = 4, 16                      # group leaf / internal node K of the reference's superblocks
+_TREE_BYTES = 24 + (2 * _INT_K + 1) * 8 + 2 * _INT_K * 8      # 544
+_SNOD_BYTES = 8 + 2 * _LEAF_K * 40                            # 328
+_FREE_NULL = 1                               # H5HL_FREE_NULL: "no free block" in a local heap
+
+
+def _pad8(b: bytes) -> bytes:
+    return b + b"\0" * (-len(b) % 8)
+
+
+def _msg(mtype: int, body: bytes, flags: int = 0) -> bytes:
+    body = _pad8(body)
+    return struct.pack("<HHB3x", mtype, len(body), flags) + body
+
+
+def _dataspace_v1(shape) -> bytes:
+    # version 1, rank, flags (0: no max dims), 5 reserved bytes, then the dimensions
+    return struct.pack("<BBB5x", 1, len(shape), 0) + b"".join(struct.pack("<Q", int(d)) for d in shape)
+
+
+_F32_TYPE = bytes.fromhex("11201f000400000000002000170800177f000000")     # IEEE little-endian binary32 (as in the files)
+
+
+def _string_type(size: int) -> bytes:
+    # class 3 (string), version 1, null-padded ASCII - what h5py writes for numpy 'S' data
+    return struct.pack("<BBBBI", 0x13, 0x01, 0, 0, max(1, size))
+
+
+def _attribute_v1(name: str, dtype_msg: bytes, shape, data: bytes) -> bytes:
+    nm = name.encode("utf8") + b"\0"
+    ds = _dataspace_v1(shape)
+    return (struct.pack("<BxHHH", 1, len(nm), len(dtype_msg), len(ds)) + _pad8(nm) + _pad8(dtype_msg) + _pad8(ds) + data)
+
+
+def _string_attr(name: str, value) -> bytes:
+    """scalar bytes or list of bytes -> attribute message body with a fixed-length string type."""
+    if isinstance(value, (bytes, str)):
+        v = value.encode("utf8") if isinstance(value, str) else value
+        return _attribute_v1(name, _string_type(len(v)), (), v.ljust(max(1, len(v)), b"\0"))
+    vals = [v.encode("utf8") if isinstance(v, str) else v for v in value]
+    width = max([len(v) for v in vals] + [1])
+    return _attribute_v1(name, _string_type(width), (len(vals),), b"".join(v.ljust(width, b"\0") for v in vals))
+
+
+class _Writer:
+    def __init__(self):
+        self.buf = bytearray(96)             # superblock + root symbol-table entry, filled in at the end
+
+    def alloc(self, data: bytes) -> int:
+        self.buf += b"\0" * (-len(self.buf) % 8)
+        addr = len(self.buf)
+        self.buf += data
+        return addr
+
+    def object_header(self, messages) -> int:
+        body = b"".join(messages)
+        # version 1 prefix: version, reserved, message count, reference count, header size, 4 bytes of alignment
+        return self.alloc(struct.pack("<BxHII4x", 1, len(messages), 1, len(body)) + body)
+
+    def dataset(self, arr: np.ndarray) -> int:
+        arr = np.ascontiguousarray(arr, dtype="<f4")
+        data_addr = self.alloc(arr.tobytes())
+        msgs = [
+            _msg(0x0001, struct.pack("<BBB5x", 1, arr.ndim, 1) + b"".join(struct.pack("<Q", d) for d in arr.shape) * 2),
+            _msg(0x0003, _F32_TYPE, flags=1),
+            _msg(0x0005, bytes.fromhex("0202020100000000"), flags=1),      # fill value v2: none defined
+            _msg(0x0008, struct.pack("<BBQQ", 3, 1, data_addr, arr.nbytes)),
+        ]
+        return self.object_header(msgs)
+
+    def group(self, children, attrs=()):
+        """children: {name: (object header address, btree, heap)} (btree/heap None for datasets).
+        -> (object header address, btree address, heap address)"""
+        names = sorted(children, key=lambda s: s.encode("utf8"))
+        heap = bytearray(8)                  # offset 0: the empty string (B-tree key 0, root entry name)
+        off = {}
+        for n in names:
+            off[n] = len(heap)
+            heap += _pad8(n.encode("utf8") + b"\0")
+        heap_data = self.alloc(bytes(heap))
+        heap_addr = self.alloc(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap), _FREE_NULL, heap_data))
+        # symbol nodes of up to 2 * leaf K entries, in name order
+        per = 2 * _LEAF_K
+        chunks = [names[i:i + per] for i in range(0, len(names), per)]
+        if len(chunks) > 2 * _INT_K:
+            raise H5Error("group with more than {} entries".format(2 * _INT_K * per))
+        keys, kids = [0], []
+        for ch in chunks:
+            body = b"SNOD" + struct.pack("<BxH", 1, len(ch))
+            for n in ch:
+                addr, bt, hp = children[n]
+                if bt is None:
+                    body += struct.pack("<QQII16x", off[n], addr, 0, 0)
+                else:
+                    body += struct.pack("<QQIIQQ", off[n], addr, 1, 0, bt, hp)
+            kids.append(self.alloc(body.ljust(_SNOD_BYTES, b"\0")))
+            keys.append(off[ch[-1]])
+        tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, len(kids), UNDEF, UNDEF)
+        for i, kid in enumerate(kids):
+            tree += struct.pack("<QQ", keys[i], kid)
+        tree += struct.pack("<Q", keys[len(kids)])
+        btree_addr = self.alloc(tree.ljust(_TREE_BYTES, b"\0"))
+        msgs = [_msg(0x0011, struct.pack("<QQ", btree_addr, heap_addr))] + [_msg(0x000C, a) for a in attrs]
+        return self.object_header(msgs), btree_addr, heap_addr
+
+    def finish(self, root) -> bytes:
+        addr, bt, hp = root
+        sb = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBxBBBxHHI", 0, 0, 0, 0, 8, 8, _LEAF_K, _INT_K, 0)
+        sb += struct.pack("<QQQQ", 0, UNDEF, len(self.buf), UNDEF)
+        sb += struct.pack("<QQIIQQ", 0, addr, 1, 0, bt, hp)
+        assert len(sb) == 96
+        self.buf[:96] = sb
+        return bytes(self.buf)
+
+
+def write_keras_weights(path, layers, backend=b"tensorflow", keras_version=b"2.8.0"):
+    """Write a Keras-2.8 style `save_weights` HDF5 file.  `layers` = [(layer_name, [(weight_name, ndarray), ...])] in
+    model order; a weight name is the dataset path below its layer group (e.g. "encoder/conv2d/kernel:0").  Same
+    structures as the reference's files (superblock 0, version-1 object headers, symbol-table groups, contiguous
+    float32 datasets); string attributes are fixed-length (as Keras <= 2.2 / h5py write numpy 'S' data) instead of
+    variable-length, which `load_weights` accepts as well.  Checked against this module's reader and against the
+    byte layout of the reference's files; NOT checked against libhdf5 (not available here)."""
+    w = _Writer()
+
+    def build(tree, attrs=()):
+        kids = {}
+        for name, node in tree.items():
+            if isinstance(node, dict):
+                kids[name] = build(node)
+            else:
+                kids[name] = (w.dataset(node), None, None)
+        return w.group(kids, attrs)
+
+    root = {}
+    for lname, weights in layers:
+        tree = {}
+        for wname, arr in weights:
+            node = tree
+            parts = wname.split("/")
+            for p in parts[:-1]:
+                node = node.setdefault(p, {})
+            node[parts[-1]] = np.asarray(arr)
+        root[lname] = (tree, [wn for wn, _ in weights])
+    kids = {}
+    for lname, (tree, wnames) in root.items():
+        sub = {}
+        for name, node in tree.items():
+            sub[name] = build(node) if isinstance(node, dict) else (w.dataset(node), None, None)
+        kids[lname] = w.group(sub, [_string_attr("weight_names", wnames)])
+    kids["top_level_model_weights"] = w.group({}, [_string_attr("weight_names", [])])
+    attrs = [_string_attr("layer_names", [ln for ln, _ in layers]), _string_attr("backend", backend),
+             _string_attr("keras_version", keras_version)]
+    data = w.finish(w.group(kids, attrs))
+    with open(path, "wb") as fh:
+        fh.write(data)

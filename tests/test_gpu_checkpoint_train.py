@@ -104,10 +104,10 @@ def test_train_loop_schedule_checkpoints_and_temperature(tmp_path, precision, gr
     assert not torch.equal(before, lrn.store.flat) and bool(torch.isfinite(lrn.store.flat).all())
     for mid in ("best", "last"):
         for stem in ("encoder_model", "decoder_model", "classifier", "cond_prior"):
-            assert os.path.exists(os.path.join(str(tmp_path), "{}_{}.npz".format(stem, mid)))
+            assert os.path.exists(os.path.join(str(tmp_path), "{}_{}.h5".format(stem, mid)))
         assert os.path.exists(os.path.join(str(tmp_path), "learned_gating_matrix_{}.npy".format(mid)))
         assert os.path.exists(os.path.join(str(tmp_path), "learned_gating_matrix_{}.csv".format(mid)))
     # the saved "last" model restores the exact parameters
     other = G.Learner((64, 64, 3), 45, 18, 18, 200, 0.2, cfg, precision=precision)
-    other.load_model_npz(str(tmp_path), "last")
+    other.load_model(str(tmp_path), "last")
     assert torch.equal(other.store.flat, lrn.store.flat)

@@ -111,3 +111,74 @@ def test_epoch_schedule_is_the_reference_interleave(perc, n_sup, n_unsup, bs):
     assert got == _reference_schedule(perc, n_sup, n_unsup, bs)
     if 0.0 < perc < 1.0:
         assert sum(got) == math.ceil(n_sup / bs)
+
+
+# ---- writer -----------------------------------------------------------------------------------------------------------
+def _layers_of(path):
+    f = H5File(path)
+    out = []
+    for ln in f.attrs("/")["layer_names"]:
+        ln = ln.decode()
+        wn = f.attrs("/" + ln).get("weight_names")
+        out.append((ln, [(n.decode(), f["/" + ln + "/" + n.decode()]) for n in wn] if isinstance(wn, list) else []))
+    return out
+
+
+@pytest.mark.parametrize("stem", ["encoder_model_best", "decoder_model_best", "classifier_best", "cond_prior_best"])
+def test_writer_round_trips_the_reference_checkpoint(tmp_path, stem):
+    """re-write the reference's file with `write_keras_weights` and read it back: same layer_names, weight_names (in
+    Keras' order), shapes and bits; same group tree."""
+    from gccvae_b200.h5lite import write_keras_weights
+    src = os.path.join(CKPT, stem + ".h5")
+    out = str(tmp_path / (stem + ".h5"))
+    write_keras_weights(out, _layers_of(src))
+    a, b = keras_weights(src), keras_weights(out)
+    assert [n for n, _ in a] == [n for n, _ in b]
+    for (_, x), (_, y) in zip(a, b):
+        assert x.dtype == y.dtype and x.shape == y.shape and x.tobytes() == y.tobytes()
+    fa, fb = H5File(src), H5File(out)
+    assert fa.attrs("/")["layer_names"] == fb.attrs("/")["layer_names"]
+    assert fb.attrs("/")["backend"] == b"tensorflow" and fb.attrs("/")["keras_version"] == b"2.8.0"
+    assert fa.visit("/") == fb.visit("/") and fa.keys("/") == fb.keys("/")
+
+
+def test_written_file_has_the_reference_files_on_disk_structure(tmp_path):
+    """superblock fields, node sizes and signatures equal those of the reference's files (what libhdf5 wrote)."""
+    import struct
+    from gccvae_b200.h5lite import write_keras_weights
+    src = os.path.join(CKPT, "encoder_model_best.h5")
+    out = str(tmp_path / "enc.h5")
+    write_keras_weights(out, _layers_of(src))
+    a, b = open(src, "rb").read(), open(out, "rb").read()
+    assert a[:24] == b[:24]                                      # signature, versions, sizes, group K's, flags
+    assert struct.unpack_from("<Q", b, 40)[0] == len(b)          # end-of-file address
+    assert struct.unpack_from("<QQ", b, 24) == (0, 0xFFFFFFFFFFFFFFFF)      # base address, no free-space info
+    root_bt, root_heap = struct.unpack_from("<QQ", b, 56 + 24)
+    assert b[root_bt:root_bt + 4] == b"TREE" and b[root_heap:root_heap + 4] == b"HEAP"
+    # the encoder's root group has 9 entries -> two symbol nodes of <= 8 entries under one B-tree node, keys in order
+    used = struct.unpack_from("<H", b, root_bt + 6)[0]
+    assert used == 2
+    kids = [struct.unpack_from("<Q", b, root_bt + 24 + 8 + 16 * i)[0] for i in range(used)]
+    counts = [struct.unpack_from("<H", b, k + 6)[0] for k in kids]
+    assert all(b[k:k + 4] == b"SNOD" for k in kids) and counts == [8, 1]
+    for n_tree in (a.count(b"TREE"), b.count(b"TREE")):
+        assert n_tree >= 9
+
+
+def test_writer_rejects_what_it_cannot_represent(tmp_path):
+    from gccvae_b200.h5lite import write_keras_weights
+    many = [("l", [("m/l/w{}:0".format(i), np.zeros(1, np.float32)) for i in range(300)])]
+    with pytest.raises(H5Error):
+        write_keras_weights(str(tmp_path / "x.h5"), many)
+
+
+def test_many_entries_in_one_group_round_trip(tmp_path):
+    from gccvae_b200.h5lite import write_keras_weights
+    rng = np.random.default_rng(0)
+    layers = [("layer_{:02d}".format(i), [("m/layer_{:02d}/kernel:0".format(i), rng.standard_normal((3, i + 1)).astype(np.float32))])
+              for i in range(40)]                               # 41 root entries: 6 symbol nodes
+    out = str(tmp_path / "many.h5")
+    write_keras_weights(out, layers)
+    back = keras_weights(out)
+    assert [n for n, _ in back] == [w[0][0] for _, w in layers]
+    assert all(np.array_equal(a, w[0][1]) for (_, a), (_, w) in zip(back, layers))
