@@ -32,7 +32,7 @@ from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, LatentBwdArgs, LatentFw
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
 from .params import ParamStore, keras_default_init
-from .utils_data import CELEBA_EASY_LABELS, load_learned_gating_matrix
+from .utils_data import gating_matrix_csv, load_learned_gating_matrix
 
 logger = logging.getLogger(__name__)
 
@@ -596,9 +596,7 @@ class Learner:
             mu = d["mu"]
             np.save(os.path.join(param_dir, "learned_gating_matrix_{}.npy".format(model_id)), mu)
             with open(os.path.join(param_dir, "learned_gating_matrix_{}.csv".format(model_id)), "w") as fh:
-                fh.write("," + ",".join(CELEBA_EASY_LABELS) + "\n")
-                for i in range(mu.shape[0]):
-                    fh.write("z{},".format(i + 1) + ",".join(str(t) for t in mu[i]) + "\n")   # shortest fp32 repr
+                fh.write(gating_matrix_csv(mu))
 
     # ---- training loop (gated_ccvae.py:313-419) ------------------------------------------------------------------------
     @staticmethod

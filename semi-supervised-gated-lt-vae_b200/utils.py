@@ -33,3 +33,4 @@ def get_gaussian_kl_div(locs_q, scale_q, locs_p=None, scale_p=None):
     out = torch.empty(B, dtype=torch.float32, device=dev)
     _lib.check(lib.gccvae_gaussian_kl_f32(ptr(lq), ptr(sq), ptr(lp), ptr(sp), B, D, ptr(out), _stream()), "kl")
     return out
+from .utils_data import create_gating_matrix  # noqa: F401,E402  (utils.py:132-149 lives next to the data module here)

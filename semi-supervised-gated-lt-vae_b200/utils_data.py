@@ -34,12 +34,80 @@ def load_learned_gating_matrix(param_dir, model_id):
     return np.load(os.path.join(param_dir, "learned_gating_matrix_{}.npy".format(model_id)))
 
 
-class GatingMatrixReader:
-    """The slice of CelebAReader the Learner consumes: `.init_gating_prob` (gated_ccvae.py:506)."""
+def grouped_indices_from_labels(data):
+    """rows of a binary label matrix [N, n_labels] -> list of the positive label indices of every row that has at
+    least one (utils_data.py:163-165: np.nonzero + cut at row changes; rows without a positive label form no group)."""
+    data = np.asarray(data)
+    where_one_x, where_one_y = np.nonzero(data)
+    cut_idx = np.flatnonzero(np.r_[True, where_one_x[1:] != where_one_x[:-1], True])
+    return [where_one_y[i:j] for i, j in zip(cut_idx[:-1], cut_idx[1:])]
 
-    def __init__(self, root, sup_frac, batch_size=None):
+
+def cooccurrence_counts(data):
+    """C[i, j] = number of rows with labels i and j both positive, 0 on the diagonal; n = rows with any positive label.
+    The double loop of utils.py:137-144 as one integer matrix product (exact)."""
+    y = (np.asarray(data) != 0).astype(np.int64)
+    counts = y.T @ y
+    np.fill_diagonal(counts, 0)
+    return counts, int((y.sum(axis=1) > 0).sum())
+
+
+def create_gating_matrix(grouped_indices, n_labels):
+    """utils.py:132-149: co-occurrence counts of the label groups / number of groups, diagonal set to 1 (float64)."""
+    n_elems = len(grouped_indices)
+    y = np.zeros((n_elems, n_labels), dtype=np.int64)
+    for r, group in enumerate(grouped_indices):
+        y[r, np.asarray(group, dtype=np.int64)] = 1
+    counts = y.T @ y
+    np.fill_diagonal(counts, 0)
+    gating_matrix = counts.astype(np.float64) / n_elems
+    np.fill_diagonal(gating_matrix, 1)
+    return gating_matrix
+
+
+def initial_gating_matrix(sup_frac, sup_labels=None, valid_labels=None, n_labels=len(CELEBA_EASY_LABELS)):
+    """the generate branch of CelebAReader.set_gating_prob (utils_data.py:153-168): 0.5 off the diagonal when there
+    is no supervision, else the co-occurrence statistics of the supervised + validation label rows."""
+    if sup_frac == 0.0:
+        mu = np.ones((n_labels, n_labels)) / 2.0
+        np.fill_diagonal(mu, 1.)
+        return mu
+    data = np.concatenate((np.asarray(sup_labels), np.asarray(valid_labels)), axis=0)
+    return create_gating_matrix(grouped_indices_from_labels(data), n_labels)
+
+
+def gating_matrix_csv(mu, columns=CELEBA_EASY_LABELS):
+    """text of `pd.DataFrame(mu, index=z1.., columns=labels).to_csv()` (utils_data.py:172-174, gated_ccvae.py:399-403):
+    shortest round-trip repr of every entry in the array's own precision."""
+    mu = np.asarray(mu)
+    lines = ["," + ",".join(columns)]
+    for i in range(mu.shape[0]):
+        lines.append("z{},".format(i + 1) + ",".join(str(t) for t in mu[i]))
+    return "\n".join(lines) + "\n"
+
+
+class GatingMatrixReader:
+    """The slice of CelebAReader the Learner consumes: `.init_gating_prob` (gated_ccvae.py:506), loaded from
+    `root/gating_matrix_{sup_frac}.npy` if it exists, else generated from label rows and saved as `.npy` + `.csv`
+    (utils_data.py:147-176)."""
+
+    def __init__(self, root, sup_frac, batch_size=None, sup_labels=None, valid_labels=None):
         self.root, self.sup_frac, self.batch_size = root, sup_frac, batch_size
-        self.init_gating_prob = load_gating_matrix(root, sup_frac)
+        self.set_gating_prob(sup_labels, valid_labels)
+
+    def set_gating_prob(self, sup_labels=None, valid_labels=None):
+        path = gating_matrix_path(self.root, self.sup_frac)
+        if os.path.exists(path):
+            self.init_gating_prob = load_gating_matrix(self.root, self.sup_frac)
+            return
+        if self.sup_frac != 0.0 and (sup_labels is None or valid_labels is None):
+            raise FileNotFoundError("No gating matrix found at {} and no label rows to generate it from".format(path))
+        mu = initial_gating_matrix(self.sup_frac, sup_labels, valid_labels)
+        self.init_gating_prob = mu
+        os.makedirs(self.root, exist_ok=True)
+        np.save(path, mu)
+        with open(os.path.join(self.root, "gating_matrix_{}.csv".format(self.sup_frac)), "w") as fh:
+            fh.write(gating_matrix_csv(mu))
 
 
 class SyntheticReader:
