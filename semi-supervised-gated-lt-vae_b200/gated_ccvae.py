@@ -621,6 +621,12 @@ class Learner:
             out.append(bool(sup))
         return out
 
+    @staticmethod
+    def next_gating_temperature(t):
+        """gated_ccvae.py:404-406: the per-epoch decay of the gate sampler's temperature (host float, as there)."""
+        t *= 0.99
+        return t
+
     def train(self, data_loaders, param_dir, fig_path=None, on_batch=None):
         """gated_ccvae.py:313-419: per epoch the supervised / unsupervised batches are interleaved by
         `epoch_schedule`, every batch is one `train_step`, the epoch ends with the validation accuracy, a
@@ -658,7 +664,7 @@ class Learner:
                 best_val_acc = val_acc
                 self.save_model(param_dir, "best")
             if cfg["gate_type"] == "learnable":
-                self.gating_sampler_temp *= 0.99
+                self.gating_sampler_temp = self.next_gating_temperature(self.gating_sampler_temp)
                 self._graphs.clear()      # graphs captured with the old temperature are never replayed again
                 self._graph_turn.clear()
                 logger.info("gating_sampler_temp decayed to: %.4f" % self.gating_sampler_temp)

@@ -179,3 +179,13 @@ def test_many_entries_in_one_group_round_trip(tmp_path):
     back = keras_weights(out)
     assert [n for n, _ in back] == [w[0][0] for _, w in layers]
     assert all(np.array_equal(a, w[0][1]) for (_, a), (_, w) in zip(back, layers))
+
+
+def test_temperature_decay_reproduces_the_reference_training_log():
+    """`gating_sampler_temp decayed to: %.4f` lines of models/params_1.0_learnable/logs (75 epochs from T = 1.0)."""
+    logged = open(os.path.join(HERE, "golden", "logs", "gating_sampler_temp_params_1.0_learnable.txt")).read().split()
+    assert len(logged) == 75
+    t = 1.0
+    for want in logged:
+        t = G.Learner.next_gating_temperature(t)
+        assert "%.4f" % t == want
