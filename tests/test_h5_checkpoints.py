@@ -189,3 +189,24 @@ def test_temperature_decay_reproduces_the_reference_training_log():
     for want in logged:
         t = G.Learner.next_gating_temperature(t)
         assert "%.4f" % t == want
+
+
+def test_one_one_checkpoint_shows_the_gating_semantics_in_the_reference_outputs():
+    """The reference's own model trained 100 epochs with fixed one-one gates (models/params_1.0_fixed_one-one): the
+    conditional prior's OFF-diagonal kernel entries are exactly at their initial values (0 for the two loc kernels, 1 for
+    the two scale kernels, networks.py:113-116) and the classifier kernel's off-diagonal entries still look like their
+    N(0, 0.05) initialiser (networks.py:69-70): with c = I every gated product c[i,j]*W[i,j] has a gradient that is
+    exactly zero off the diagonal, and Adam leaves a zero-gradient entry untouched.  These are the semantics the
+    known-answer test 1 of SURVEY 8c states and the kernels implement (tests/test_oracle_known_answers.py,
+    tests/test_gpu_parity_fp32.py) - here read off real reference outputs."""
+    d = os.path.join(HERE, "golden", "models", "params_1.0_fixed_one-one")
+    off = ~np.eye(18, dtype=bool)
+    prior = keras_weights(os.path.join(d, "cond_prior_best.h5"))
+    assert len(prior) == 4
+    for i, (_, a) in enumerate(prior):
+        init = 0.0 if i < 2 else 1.0                      # loc_true, loc_false | scale_true, scale_false
+        assert np.all(a[off] == init)
+        assert np.abs(np.diag(a) - init).max() > 1e-1     # the diagonal did train
+    (_, w), (_, b) = keras_weights(os.path.join(d, "classifier_best.h5"))
+    assert 0.04 < float(w[off].std()) < 0.06 and abs(float(w[off].mean())) < 0.01
+    assert float(np.abs(b).max()) > 0.05                  # the bias (initialised to zeros) did train
