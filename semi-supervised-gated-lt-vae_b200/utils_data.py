@@ -130,3 +130,128 @@ class SyntheticReader:
             idx = [(i + j) % self.n_s for j in range(self.batch_size)]
             i = (i + self.batch_size) % self.n_s
             yield self.x[idx], (self.y[idx] if self.supervised else None)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# CelebA input pipeline (utils_data.py:31-198).  Host side of the path: it produces what `Learner.train_step` consumes.
+# The image blobs are not part of the reference checkout, so this is exercised on a synthetic directory of the same
+# layout (tests/test_celeba_reader.py).  One addition: `dtype="uint8"` hands the resized 8-bit pixels through unchanged -
+# the tensor-core engine normalises u8 / 255 on the device, bit-exactly as `np.float32(img) / 255.0` (:57-59) does, and
+# the batch that crosses PCIe is 4x smaller.
+# ---------------------------------------------------------------------------------------------------------------------
+CELEBA_LABELS = ['5_o_Clock_Shadow', 'Arched_Eyebrows', 'Attractive', 'Bags_Under_Eyes', 'Bald', 'Bangs', 'Big_Lips',
+                 'Big_Nose', 'Black_Hair', 'Blond_Hair', 'Blurry', 'Brown_Hair', 'Bushy_Eyebrows', 'Chubby', 'Double_Chin',
+                 'Eyeglasses', 'Goatee', 'Gray_Hair', 'Heavy_Makeup', 'High_Cheekbones', 'Male', 'Mouth_Slightly_Open',
+                 'Mustache', 'Narrow_Eyes', 'No_Beard', 'Oval_Face', 'Pale_Skin', 'Pointy_Nose', 'Receding_Hairline',
+                 'Rosy_Cheeks', 'Sideburns', 'Smiling', 'Straight_Hair', 'Wavy_Hair', 'Wearing_Earrings', 'Wearing_Hat',
+                 'Wearing_Lipstick', 'Wearing_Necklace', 'Wearing_Necktie', 'Young']
+CELEBA_SPLIT = {"train": 162770, "valid": 19867, "test": 19962}
+
+
+class LabelTable:
+    """image file names + their binary label rows (the reference's CSV namedtuple: header, index, data)."""
+
+    def __init__(self, header, index, data):
+        self.header, self.index, self.data = list(header), list(index), np.asarray(data)
+
+    def rows(self, lo, hi=None):
+        return LabelTable(self.header, self.index[lo:hi], self.data[lo:hi])
+
+    def __len__(self):
+        return len(self.index)
+
+
+class DataLoader:
+    """utils_data.py:31-88: endless batches of (images [B,64,64,3], labels [B,18]) in a (shuffled) fixed order that wraps
+    around; `.n_s` samples; `.step()` yields the batch read last and reads the next one; `.reset()` rewinds."""
+
+    def __init__(self, data_dir, cached_data, batch_size, shuffle=True, dtype="float32", rng=None):
+        self.data_dir, self.cached_data, self.bs = data_dir, cached_data, int(batch_size)
+        self.n_s = len(cached_data.data)
+        self.dtype = dtype
+        self.idxs = list(range(self.n_s))
+        if shuffle:
+            (rng if rng is not None else np.random).shuffle(self.idxs)
+        self.start = 0
+        self.Xs, self.ys = self.read_data(self.get_batch())
+
+    def read_data(self, idxs, normalise=True):
+        from PIL import Image
+        out = np.empty((len(idxs), 64, 64, 3), dtype=np.uint8)
+        for r, i in enumerate(idxs):
+            with Image.open(os.path.join(self.data_dir, self.cached_data.index[i])) as img:
+                out[r] = np.asarray(img.convert("RGB").resize((64, 64)))      # PIL's default resampling, as :54-56
+        labels = self.cached_data.data[idxs]
+        if self.dtype == "uint8":
+            return out, labels
+        X = out.astype(np.float32)
+        return (X / 255.0 if normalise else X), labels
+
+    def get_batch(self):
+        n, s = self.n_s, self.start
+        if s + self.bs < n:
+            batch = self.idxs[s:s + self.bs]
+            self.start = s + self.bs
+        else:           # wrap around: the tail of the order followed by its head
+            batch = self.idxs[s:] + self.idxs[:self.bs - (n - s)]
+            self.start = (s + self.bs) % n
+        return batch
+
+    def step(self):
+        while True:
+            yield self.Xs, self.ys
+            self.Xs, self.ys = self.read_data(self.get_batch())
+
+    def reset(self):
+        self.start = 0
+
+
+class CelebAReader(GatingMatrixReader):
+    """utils_data.py:91-198: `list_attr_celeba.csv` (40 attributes, -1 / 1) -> the 18 easy labels (0 / 1); train / valid /
+    test by position; the first `sup_frac` of the training rows are the supervised set; loaders over
+    `root/img_align_celeba`; `init_gating_prob` loaded or generated from the supervised + validation label rows."""
+
+    def __init__(self, root, sup_frac, batch_size, split_map=None, dtype="float32"):
+        self.root, self.sup_frac, self.batch_size, self.dtype = root, sup_frac, batch_size, dtype
+        self.split_map = dict(split_map or CELEBA_SPLIT)
+        self.sub_label_inds = [i for i, name in enumerate(CELEBA_LABELS) if name in CELEBA_EASY_LABELS]
+        self.attr = self._load_csv("list_attr_celeba.csv", header=0)
+        self.init_gating_prob = None
+
+    def _load_csv(self, filename, header=None):
+        import csv
+        with open(os.path.join(self.root, filename)) as fh:
+            rows = [r for r in csv.reader(fh) if r]
+        if header is not None:
+            rows = rows[header + 1:]
+        index = [r[0] for r in rows]
+        data = np.array([[int(v) for v in r[1:]] for r in rows], dtype=np.int64).reshape(len(rows), -1)
+        data = (data == 1).astype(np.int64)[:, self.sub_label_inds]           # -1 -> 0, 1 -> 1, easy labels only
+        return LabelTable(["image_id"] + CELEBA_EASY_LABELS, index, data)
+
+    def load_split_data(self):
+        n_train, n_valid = self.split_map["train"], self.split_map["valid"]
+        train = self.attr.rows(0, n_train)
+        cached = {"train": train}
+        if self.sup_frac == 0.0:
+            cached["unsup"] = train
+        elif self.sup_frac == 1.0:
+            cached["sup"] = train
+        else:
+            n_sup = int(n_train * self.sup_frac)
+            cached["sup"], cached["unsup"] = train.rows(0, n_sup), train.rows(n_sup)
+        cached["valid"] = self.attr.rows(n_train, n_train + n_valid)
+        cached["test"] = self.attr.rows(n_train + n_valid)
+        return cached
+
+    def setup_data_loaders(self, shuffle=True, rng=None):
+        if self.sup_frac == 0.0:
+            modes = ["unsup", "test"]
+        elif self.sup_frac == 1.0:
+            modes = ["sup", "test", "valid"]
+        else:
+            modes = ["unsup", "test", "sup", "valid"]
+        cached = self.load_split_data()
+        self.set_gating_prob(cached["sup"].data if "sup" in cached else None, cached["valid"].data)
+        img_dir = os.path.join(self.root, "img_align_celeba")
+        return {m: DataLoader(img_dir, cached[m], self.batch_size, shuffle=shuffle, dtype=self.dtype, rng=rng) for m in modes}

@@ -1,0 +1,74 @@
+"""CelebA input pipeline (utils_data.py:31-198) on a synthetic directory of the dataset's layout: label mapping, splits,
+supervised fraction, batch order with wrap-around, resize, uint8 / float32 outputs, gating matrix generated and saved."""
+import os
+
+import numpy as np
+import pytest
+
+import gccvae_b200 as G
+from gccvae_b200 import utils_data as UD
+
+N, SPLIT = 40, {"train": 24, "valid": 8, "test": 8}
+
+
+@pytest.fixture(scope="module")
+def root(tmp_path_factory):
+    from PIL import Image
+    d = tmp_path_factory.mktemp("celeba")
+    os.makedirs(d / "img_align_celeba")
+    rng = np.random.default_rng(0)
+    attrs = np.where(rng.random((N, 40)) < 0.35, 1, -1)
+    with open(d / "list_attr_celeba.csv", "w") as fh:
+        fh.write("image_id," + ",".join(UD.CELEBA_LABELS) + "\n")
+        for i in range(N):
+            name = "%06d.png" % (i + 1)
+            fh.write(name + "," + ",".join(str(v) for v in attrs[i]) + "\n")
+            Image.fromarray(rng.integers(0, 256, (109, 89, 3), dtype=np.uint8)).save(d / "img_align_celeba" / name)
+    return str(d), attrs
+
+
+def test_label_mapping_and_splits(root):
+    path, attrs = root
+    rdr = G.utils_data.CelebAReader(path, 0.25, 4, split_map=SPLIT)
+    easy = [UD.CELEBA_LABELS.index(n) for n in UD.CELEBA_EASY_LABELS]
+    assert rdr.sub_label_inds == easy and len(easy) == 18
+    assert np.array_equal(rdr.attr.data, (attrs[:, easy] == 1).astype(np.int64))
+    c = rdr.load_split_data()
+    assert (len(c["train"]), len(c["sup"]), len(c["unsup"]), len(c["valid"]), len(c["test"])) == (24, 6, 18, 8, 8)
+    assert c["sup"].index == ["%06d.png" % i for i in range(1, 7)] and c["test"].index[0] == "000033.png"
+    assert set(G.utils_data.CelebAReader(path, 0.0, 4, split_map=SPLIT).load_split_data()) == {"train", "unsup", "valid", "test"}
+    assert len(G.utils_data.CelebAReader(path, 1.0, 4, split_map=SPLIT).load_split_data()["sup"]) == 24
+
+
+def test_loaders_batches_and_gating_matrix(root):
+    from PIL import Image
+    path, attrs = root
+    for f in os.listdir(path):
+        if f.startswith("gating_matrix"):
+            os.remove(os.path.join(path, f))
+    rdr = G.utils_data.CelebAReader(path, 0.25, 4, split_map=SPLIT, dtype="uint8")
+    loaders = rdr.setup_data_loaders(shuffle=False)
+    assert set(loaders) == {"unsup", "test", "sup", "valid"} and loaders["sup"].n_s == 6
+    # gating matrix from the supervised + validation rows, saved next to the data
+    c = rdr.load_split_data()
+    want = UD.create_gating_matrix(UD.grouped_indices_from_labels(np.concatenate((c["sup"].data, c["valid"].data))), 18)
+    assert rdr.init_gating_prob.tobytes() == want.tobytes()
+    assert os.path.exists(os.path.join(path, "gating_matrix_0.25.npy")) and os.path.exists(os.path.join(path, "gating_matrix_0.25.csv"))
+    # batch order of 6 samples in batches of 4, unshuffled: the reference's wrap-around rule
+    it = iter(loaders["sup"].step())
+    seen = [next(it) for _ in range(4)]
+    idx = [[0, 1, 2, 3], [4, 5, 0, 1], [2, 3, 4, 5], [0, 1, 2, 3]]
+    for (X, y), want_idx in zip(seen, idx):
+        assert X.dtype == np.uint8 and X.shape == (4, 64, 64, 3) and y.shape == (4, 18)
+        assert np.array_equal(y, c["sup"].data[want_idx])
+        for r, i in enumerate(want_idx):
+            ref = np.array(Image.open(os.path.join(path, "img_align_celeba", c["sup"].index[i])).resize((64, 64)))
+            assert np.array_equal(X[r], ref)
+    # float32 loaders give exactly uint8 / 255 in fp32 (what the device-side normalisation reproduces bit for bit)
+    f32 = G.utils_data.CelebAReader(path, 0.25, 4, split_map=SPLIT).setup_data_loaders(shuffle=False)
+    Xf, yf = next(iter(f32["sup"].step()))
+    assert Xf.dtype == np.float32 and np.array_equal(Xf, seen[0][0].astype(np.float32) / 255.0) and np.array_equal(yf, seen[0][1])
+    # shuffled loaders visit every sample once per pass
+    rng = np.random.default_rng(3)
+    sh = G.utils_data.CelebAReader(path, 0.25, 3, split_map=SPLIT, dtype="uint8").setup_data_loaders(shuffle=True, rng=rng)
+    assert sorted(sh["unsup"].idxs) == list(range(18)) and sh["unsup"].idxs != list(range(18))
