@@ -72,3 +72,57 @@ def test_loaders_batches_and_gating_matrix(root):
     rng = np.random.default_rng(3)
     sh = G.utils_data.CelebAReader(path, 0.25, 3, split_map=SPLIT, dtype="uint8").setup_data_loaders(shuffle=True, rng=rng)
     assert sorted(sh["unsup"].idxs) == list(range(18)) and sh["unsup"].idxs != list(range(18))
+
+
+def test_prefetching_loader_yields_the_same_batches_in_the_same_order(root):
+    path, _ = root
+    mk = lambda: G.utils_data.CelebAReader(path, 0.25, 5, split_map=SPLIT, dtype="uint8").setup_data_loaders(
+        shuffle=True, rng=np.random.default_rng(7))["unsup"]
+    plain, wrapped = mk(), UD.PrefetchLoader(mk(), workers=4, depth=3)
+    assert wrapped.n_s == plain.n_s == 18
+    a, b = iter(plain.step()), iter(wrapped.step())
+    for _ in range(9):                       # 45 samples: wraps around the 18-sample order twice
+        (xa, ya), (xb, yb) = next(a), next(b)
+        assert xb.dtype == np.uint8 and np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    wrapped.close()
+    f32 = UD.PrefetchLoader(G.utils_data.CelebAReader(path, 0.25, 5, split_map=SPLIT).setup_data_loaders(
+        shuffle=True, rng=np.random.default_rng(7))["unsup"], workers=2, depth=1)
+    it = iter(f32.step())
+    next(it)
+    xf, _ = next(it)
+    assert xf.dtype == np.float32 and float(xf.max()) <= 1.0
+    f32.close()
+
+
+def test_cached_loader_decodes_once_and_serves_identical_batches(root, tmp_path):
+    import shutil
+    path, _ = root
+    work = str(tmp_path / "copy")
+    shutil.copytree(path, work)
+    mk = lambda: G.utils_data.CelebAReader(work, 0.25, 5, split_map=SPLIT, dtype="uint8").setup_data_loaders(
+        shuffle=True, rng=np.random.default_rng(11))["unsup"]
+    plain = mk()
+    cache = os.path.join(work, "unsup_64x64_u8.npy")
+    cached = UD.CachedLoader(mk(), cache_path=cache, workers=3)
+    assert os.path.exists(cache) and cached.pixels.shape == (18, 64, 64, 3) and cached.pixels.dtype == np.uint8
+    a, b = iter(plain.step()), iter(cached.step())
+    seen = []
+    for _ in range(9):                       # 45 samples: wraps around the 18-sample order twice
+        (xa, ya), (xb, yb) = next(a), next(b)
+        assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+        seen.append((xa, ya))
+    # a second construction reads the cache: it works with the images gone (only the wrapped loader's own first batch
+    # is decoded by its constructor, so those files stay)
+    again_src = mk()
+    keep = {again_src.cached_data.index[i] for i in again_src.idxs[:5]}
+    for f in os.listdir(os.path.join(work, "img_align_celeba")):
+        if f not in keep:
+            os.remove(os.path.join(work, "img_align_celeba", f))
+    again = UD.CachedLoader(again_src, cache_path=cache)
+    it = iter(again.step())
+    for xa, ya in seen[:6]:
+        xd, yd = next(it)
+        assert np.array_equal(xa, xd) and np.array_equal(ya, yd)
+    np.save(cache, np.zeros((3, 64, 64, 3), np.uint8))
+    with pytest.raises(ValueError):
+        UD.CachedLoader(again_src, cache_path=cache)
