@@ -44,9 +44,10 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("GCCVAE_PRECISION", "auto"))
     ap.add_argument("--batch", type=int, default=1024)
-    ap.add_argument("--ref-batch", type=int, default=256)
-    ap.add_argument("--cpu-baseline-steps", type=int, default=60,
-                    help="timed oracle steps of the cpu_baseline leg (60 x ~175 ms = ~10 s of CPU work)")
+    ap.add_argument("--ref-batch", type=int, default=None,
+                    help="batch of the CPU arm (default: --batch, i.e. the same configuration as the GPU arm)")
+    ap.add_argument("--cpu-baseline-steps", type=int, default=15,
+                    help="timed oracle steps of the cpu_baseline leg (15 x ~0.7 s at batch 1024 = ~10 s of CPU work)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
     # the other BASELINE.json configs (parity / study cases, not the headline line)
@@ -55,11 +56,14 @@ def parse():
     ap.add_argument("--unsup-per-sup", type=int, default=1, help="unsupervised train_steps per supervised one")
     ap.add_argument("--e2e-input", default="uint8", choices=["uint8", "fp32"],
                     help="host image dtype of the headline e2e run (the other one is reported as e2e_alt)")
-    return ap.parse_args()
+    args = ap.parse_args()
+    if args.ref_batch is None:
+        args.ref_batch = args.batch
+    return args
 
 
 def train_cfg(gate="inferred", frac="0.2"):
-    mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_{}.npy".format(frac)))
+    mu = np.load(os.path.join(ROOT, "data", "gating_matrix_{}.npy".format(frac)))
     base = dict(mu_init=mu, gating_reg=0.2, lr=1e-4, batch_size=1024, init_temp=0.1)
     if gate == "learnable":
         return dict(base, gate_type="learnable", gate_subtype=None, gating_init_temp=1.0)
@@ -93,16 +97,19 @@ def cpu_oracle_rate(batch, steps, warmup, gate="inferred", frac="0.2"):
 def run_reference(args, rank):
     if rank != 0:
         return
-    rate, ms = cpu_oracle_rate(args.ref_batch, max(1, args.steps), max(1, args.warmup), args.gate, args.frac)
+    # bounded: one oracle step pair at batch 1024 takes ~0.7 s on 16 cores; at most ~3 minutes of it are timed
+    steps = max(1, min(args.steps, int(180 * 1500 / max(1, args.ref_batch)) or 1))
+    warmup = max(1, min(args.warmup, 5))
+    rate, ms = cpu_oracle_rate(args.ref_batch, steps, warmup, args.gate, args.frac)
     cores = os.cpu_count() or 1
-    sample = "oracle (PyTorch-CPU restatement of the TF reference), sup+unsup step on batch {} per step".format(
-        args.ref_batch)
+    sample = ("oracle (PyTorch-CPU restatement of the TF reference), sup+unsup step on batch {} per step, {} timed "
+              "steps after {} warm-up".format(args.ref_batch, steps, warmup))
     line = {
-        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+        "warmup": warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD.format(gate=args.gate, frac=args.frac, b=args.batch),
-                   "reference_sample_batch": args.ref_batch},
+                   "reference_sample_batch": args.ref_batch, "same_config": args.ref_batch == args.batch},
         "cpu_baseline": {"value": rate, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
@@ -316,6 +323,18 @@ def run_ours(args, rank, world, local_rank):
             pk, src = (6650.0 if roof["bound"] == "hbm" else 1590.0), "fallback"
         roof["peak"], roof["peak_source"] = pk, src
         roof["frac"] = roof["achieved"] / pk
+        # the step as a whole against both bounds of the layer-by-layer model (1.21 MB of activation
+        # traffic and 120.24 MFLOP per image and training step; one GPU's share of `value`)
+        per_gpu = value / world
+        hbm_pk = peaks.get("hbm_gbs", 6650.0)
+        tc_pk = peaks.get("bf16_tflops_sustained", 1590.0)
+        roof["step"] = {
+            "images_per_s_per_gpu": per_gpu,
+            "hbm": {"bytes_per_image": 1.21e6, "achieved_GBps": per_gpu * 1.21e6 / 1e9, "peak_GBps": hbm_pk,
+                    "frac": per_gpu * 1.21e6 / 1e9 / hbm_pk},
+            "tensor": {"flop_per_image": 120.24e6, "achieved_TFLOPs": per_gpu * 120.24e6 / 1e12, "peak_TFLOPs": tc_pk,
+                       "frac": per_gpu * 120.24e6 / 1e12 / tc_pk},
+        }
         line["roofline"] = roof
         line["top_ops"] = top
     if not args.no_cpu_baseline:

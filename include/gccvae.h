@@ -299,9 +299,15 @@ int gccvae_adam_f32(float* param, const float* grad, float* m, float* v, long lo
  * [i0, n) are updated.  publish != 0: step_state[0] = t when the kernel ends.  A step may therefore run the update in
  * two launches over disjoint ranges - the second one publishing - e.g. everything but the first layer while the last
  * dgrad is still running.  step_state: 2 device ints {t, 0}; the second is the block ticket of the publishing launch
- * and must be 0 on entry (it is left at 0). */
+ * and must be 0 on entry (it is left at 0).
+ * result_ring (optional, with publish): ring_slots rows of GCCVAE_RESULT_SLOT_FLOATS floats; the publishing launch
+ * copies {result_loss[0], result_c[0..324)} into row (t - 1) % ring_slots, so that what train_step hands back
+ * (gated_ccvae.py:311 returns fresh tensors) is not overwritten by the next replay of the same captured step. */
+#define GCCVAE_RESULT_SLOT_FLOATS 328
 int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long i0, long long n, long long n_zero,
-                          float lr, float beta1, float beta2, float eps, int* step_state, int publish, void* stream);
+                          float lr, float beta1, float beta2, float eps, int* step_state, int publish,
+                          const float* result_loss, const float* result_c, float* result_ring, int ring_slots,
+                          void* stream);
 
 /* loss[0] = sum_b(-elbo_b)/batch_global (+ gating_reg*mean|mu| when mu != NULL): the forward-only
  * value of sup_loss / unsup_loss (gated_ccvae.py:225-230, 291-298). */

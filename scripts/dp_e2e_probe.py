@@ -14,7 +14,7 @@ dev = torch.device("cuda", lr_)
 if world > 1:
     dist.init_process_group("nccl", device_id=dev)
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.2.npy"))
+mu = np.load(os.path.join(ROOT, "data", "gating_matrix_0.2.npy"))
 cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=0.3,
            batch_size=1024, init_temp=0.1)
 B = int(os.environ.get("PROBE_B", "1024"))

@@ -23,7 +23,7 @@ assert world == 2, "run with --nproc-per-node 2"
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
-mu0 = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.5.npy"))
+mu0 = np.load(os.path.join(ROOT, "data", "gating_matrix_0.5.npy"))
 cfg = dict(gate_type="learnable", gate_subtype=None, mu_init=mu0, gating_reg=0.2, lr=1e-3, gating_init_temp=1.0,
            batch_size=16, init_temp=0.1)
 BL, K = 8, 10

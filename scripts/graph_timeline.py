@@ -10,7 +10,7 @@ import gccvae_b200 as G
 
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 1024
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_0.2.npy"))
+mu = np.load(os.path.join(ROOT, "data", "gating_matrix_0.2.npy"))
 cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=0.3,
            batch_size=B, init_temp=0.1)
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True)

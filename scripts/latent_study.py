@@ -13,7 +13,7 @@ from gccvae_b200._lib import ptr
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 B = int(sys.argv[1]) if len(sys.argv) > 1 else 8192
 K = 100
-mu = np.load(os.path.join(ROOT, "tests", "golden", "data", "gating_matrix_1.0.npy"))
+mu = np.load(os.path.join(ROOT, "data", "gating_matrix_1.0.npy"))
 cfg = dict(gate_type="learnable", gate_subtype=None, mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=1.0,
            batch_size=B, init_temp=0.1)
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 1.0, cfg, precision="fp32")

@@ -14,6 +14,7 @@ ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ACCUMULATE = 0, 1, 2, 0x100
 OUT_S2D, MASK_S2D = 0x10, 0x20   # layout flags OR-ed into `act` (include/gccvae.h)
 GATE_WS_FLOATS = 7 * 324 + 32
 LATENT_PARTIAL_FLOATS = 5 * 324 + 32
+RESULT_SLOT_FLOATS = 328
 
 
 class Geom(C.Structure):
@@ -112,7 +113,7 @@ SIGNATURES = {
     "gccvae_gate_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_recon_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gccvae_adam_f32": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _P, _P]),
-    "gccvae_adam_fused_f32": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _F, _F, _F, _F, _P, _I, _P]),
+    "gccvae_adam_fused_f32": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P]),
     "gccvae_elbo_loss_f32": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P]),
     "gccvae_draw_noise_f32": (_I, [_I, _U64, _U64, _I, _I, _P, _P]),
     "gccvae_head_act_f32": (_I, [_P, _P, _LL, _P, _P, _P]),
@@ -141,6 +142,9 @@ def load():
             raise GccvaeError(
                 "libgccvae.so is not built ({}).  Run `python __graft_entry__.py build` (needs nvcc). "
                 "There is no CPU or PyTorch fallback for the Gated-CCVAE kernels.".format(LIB_PATH))
+        # the library links the CUDA runtime dynamically (libcudart.so.12): import torch first, so that the loader
+        # binds it to the runtime torch has already mapped instead of bringing a second one into the process
+        import torch  # noqa: F401
         lib = C.CDLL(LIB_PATH)
         for name, (res, args) in SIGNATURES.items():
             try:

@@ -3,6 +3,7 @@ library is a plain C-ABI shared object (include/gccvae.h) loaded with ctypes."""
 from __future__ import annotations
 
 import concurrent.futures as cf
+import hashlib
 import os
 import shutil
 import subprocess
@@ -33,13 +34,32 @@ def sources():
     return sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
 
 
-def _stale() -> bool:
-    if not os.path.exists(LIB):
-        return True
-    t = os.path.getmtime(LIB)
+def _deps():
     deps = sources() + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cuh", ".h"))]
-    deps += [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)]
-    return any(os.path.getmtime(d) > t for d in deps)
+    return sorted(deps + [os.path.join(INCLUDE, f) for f in os.listdir(INCLUDE)])
+
+
+def source_hash() -> str:
+    """sha256 over the names and contents of every source / header and the compiler flags: the library is rebuilt when
+    this changes, whatever the file times say (the .so travels to the GPU box with the snapshot, file times do not
+    survive that reliably)."""
+    h = hashlib.sha256(" ".join(f for f in NVCC_FLAGS if not f.startswith("/")).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode() + b"\0")
+        with open(d, "rb") as fh:
+            h.update(fh.read())
+    return h.hexdigest()
+
+
+def _stamp_path() -> str:
+    return LIB + ".sha256"
+
+
+def _stale() -> bool:
+    if not os.path.exists(LIB) or not os.path.exists(_stamp_path()):
+        return True
+    with open(_stamp_path()) as fh:
+        return fh.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -61,10 +81,14 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
     with cf.ThreadPoolExecutor(max_workers=min(8, os.cpu_count() or 1)) as ex:
         objs = list(ex.map(compile_one, sources()))
-    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-Xcompiler", "-fPIC", "-o", LIB, *objs]
+    # -cudart shared: the runtime is the process's libcudart (torch has loaded one already), not a second static copy
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-shared", "-cudart", "shared", "-Xcompiler", "-fPIC",
+           "-o", LIB, *objs]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n{}\n{}".format(r.stdout, r.stderr))
+    with open(_stamp_path(), "w") as fh:
+        fh.write(source_hash() + "\n")
     return LIB
 
 

@@ -106,9 +106,19 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
 __global__ void __launch_bounds__(256) adam_fused_kernel(float* __restrict__ p, float* __restrict__ g,
                                                          float* __restrict__ m, float* __restrict__ v, long long i0,
                                                          long long n, long long n_zero, float lr, float b1, float b2,
-                                                         float eps, int* __restrict__ state, int publish) {
+                                                         float eps, int* __restrict__ state, int publish,
+                                                         const float* __restrict__ res_loss,
+                                                         const float* __restrict__ res_c, float* __restrict__ ring,
+                                                         int ring_slots) {
   pdl_prologue();
   const int t = state[0] + 1;
+  // the step's results (loss, gate sample c) are copied into slot (t - 1) % ring_slots of a caller-owned ring by the
+  // publishing launch: what train_step returns stays valid for ring_slots further steps although the step itself
+  // (a replayed graph) always writes the same addresses
+  if (publish && ring != nullptr && blockIdx.x == 0) {
+    float* dst = ring + (size_t)((t - 1) % ring_slots) * GCCVAE_RESULT_SLOT_FLOATS;
+    for (int i = threadIdx.x; i < 1 + GCCVAE_ZC * GCCVAE_Y; i += 256) dst[i] = i == 0 ? res_loss[0] : res_c[i - 1];
+  }
   const float lr_t = (float)((double)lr * sqrt(1.0 - pow((double)b2, (double)t)) / (1.0 - pow((double)b1, (double)t)));
   for (long long i = i0 + blockIdx.x * 256LL + threadIdx.x; i < n_zero; i += (long long)gridDim.x * 256) {
     if (i < n) {
@@ -266,12 +276,15 @@ extern "C" int gccvae_adam_f32(float* param, const float* grad, float* m, float*
 
 extern "C" int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long long i0, long long n,
                                      long long n_zero, float lr, float beta1, float beta2, float eps, int* step_state,
-                                     int publish, void* stream) {
+                                     int publish, const float* result_loss, const float* result_c, float* result_ring,
+                                     int ring_slots, void* stream) {
   GCC_REQUIRE(param && grad && m && v && i0 >= 0 && n > i0 && n_zero >= n && step_state, "adam_fused: bad args");
+  GCC_REQUIRE(result_ring == nullptr || (result_loss && result_c && ring_slots > 0), "adam_fused: bad result ring");
   long long blocks = (n_zero - i0 + 255) / 256;
   if (blocks > 148 * 8) blocks = 148 * 8;
   GCC_CUDA(launch_pdl_k(adam_fused_kernel, dim3((int)blocks), dim3(256), 0, (cudaStream_t)stream, param, grad, m, v, i0,
-                        n, n_zero, lr, beta1, beta2, eps, step_state, publish));
+                        n, n_zero, lr, beta1, beta2, eps, step_state, publish, result_loss, result_c, result_ring,
+                        ring_slots));
   GCC_CHECK_LAUNCH("adam_fused");
   return GCCVAE_OK;
 }

@@ -5,8 +5,6 @@ only exchange is one all-reduce(sum) of the flat gradient buffer; the gate sampl
 by all ranks, per-image noise from a per-rank seed; the L1 term on mu is added once (each rank adds 1/world)."""
 from __future__ import annotations
 
-import os
-
 import torch
 
 
@@ -41,8 +39,6 @@ def data_seed(seed: int, rank: int) -> int:
 def allreduce_sum_(dist, flat: torch.Tensor, n: int):
     """in-place sum over ranks of the first n elements of a flat buffer (the trainable prefix)."""
     if dist is not None and dist.get_world_size() > 1:
-        if os.environ.get("GCCVAE_DEBUG_SKIP_ALLREDUCE") == "1":    # timing diagnosis only: WRONG results
-            return flat
         dist.all_reduce(flat[:n], op=dist.ReduceOp.SUM)
     return flat
 

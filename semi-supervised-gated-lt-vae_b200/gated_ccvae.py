@@ -28,7 +28,7 @@ import numpy as np
 import torch
 
 from . import _lib, dp
-from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, LatentBwdArgs, LatentFwdArgs, ptr
+from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, RESULT_SLOT_FLOATS, LatentBwdArgs, LatentFwdArgs, ptr
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
 from .params import ParamStore, keras_default_init
@@ -137,21 +137,18 @@ class KerasAdam:
     def iterations(self):
         return int(self.step_dev[0].item())
 
-    def apply_gradients(self, lo=0, hi=None, publish=True):
+    def apply_gradients(self, lo=0, hi=None, publish=True, result=None):
         """one launch: the Adam update of parameters [lo, hi) of the trainable prefix with t = iterations + 1, the
         gradient buffer cleared behind the read (the next backward pass accumulates into it), and - `publish` - the
-        step counter advanced.  Returns True if the gradient buffer is clean afterwards."""
-        if os.environ.get("GCCVAE_ADAM", "fused") == "split":    # A/B switch: counter bump + update as two launches
-            assert lo == 0 and hi is None
-            _lib.check(self.lib.gccvae_adam_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
-                                                self.n, self.lr, self.beta_1, self.beta_2, self.epsilon, 0,
-                                                ptr(self.step_dev), _stream()), "adam")
-            return False
+        step counter advanced and `result` = (loss, c, ring) copied into ring[(t - 1) % len(ring)].  Returns True if the
+        gradient buffer is clean afterwards."""
         n = self.n if hi is None else min(int(hi), self.n)
         zero_hi = self.store.total if hi is None else n
+        loss, c, ring = result if (result is not None and publish) else (None, None, None)
         _lib.check(self.lib.gccvae_adam_fused_f32(ptr(self.store.flat), ptr(self.store.grad), ptr(self.m), ptr(self.v),
                                                   int(lo), n, zero_hi, self.lr, self.beta_1, self.beta_2, self.epsilon,
-                                                  ptr(self.step_dev), int(bool(publish)), _stream()), "adam")
+                                                  ptr(self.step_dev), int(bool(publish)), ptr(loss), ptr(c), ptr(ring),
+                                                  0 if ring is None else int(ring.shape[0]), _stream()), "adam")
         return bool(publish)
 
 
@@ -159,7 +156,7 @@ class Learner:
     """gated_ccvae.py:114-311, 421-455."""
 
     def __init__(self, ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config, device=None,
-                 precision="fp32", seed=1234, init_seed=0, graphs=False):
+                 precision="fp32", seed=1234, init_seed=0, graphs=False, adam_tail=True):
         if tuple(ip_shape) != (64, 64, 3):
             raise ValueError("the kernels are specialised for 64x64x3 inputs (gated_ccvae.py:481)")
         self.train_config = train_config
@@ -187,6 +184,12 @@ class Learner:
         # as their gradients are complete (on a side stream, under the last dgrad), the first layer at the very end
         self._adam_cut = self.store.offsets["enc.conv2.w"][0]
         self._adam_head_done = False
+        self.adam_tail = bool(adam_tail)
+        # what train_step returns: the publishing Adam launch copies (loss, c) into slot (t - 1) % RING of this ring, so
+        # the tensors handed back stay valid for RING further steps (the replayed graph always writes the same addresses)
+        self.RING = 8
+        self._ring = torch.zeros(self.RING, RESULT_SLOT_FLOATS, dtype=torch.float32, device=self.device)
+        self._t_host = None              # host mirror of optimiser.step_dev[0]; read from the device on first use
         self._copy_stream = None
         self.last = {}
         self._lat = {}
@@ -334,14 +337,7 @@ class Learner:
                     ptr(self.store.loss_slot), _stream()), "gate_bwd")
                 mark("gate bwd", coarse=True)
 
-            # the reduction of the per-block partial sums and the gate / classifier / prior parameter gradients feed
-            # only Adam (and the returned loss): on the tensor-core engine they leave the dgrad chain for the second
-            # side stream, which encoder_bwd joins at the end of the step
-            on_side2 = getattr(self.engine, "_on_side2", None)
-            if on_side2 is not None and os.environ.get("GCCVAE_GATE_BWD_STREAM", "main") != "main":
-                on_side2(gate_bwd)
-            else:
-                gate_bwd()
+            gate_bwd()
             self.engine.encoder_bwd(x, b)
             mark("encoder bwd + join", coarse=True)
         else:
@@ -385,19 +381,28 @@ class Learner:
         return loss.clone(), c.clone()
 
     def train_step(self, x, y, supervised, noise=None, k=100):
-        """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update."""
+        """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update -> (loss, c), both fresh
+        for the next RING steps (rows of the result ring the publishing Adam launch fills)."""
+        if self._t_host is None:
+            self._t_host = self.optimiser.iterations
+        slot = self._ring[self._t_host % self.RING]
         if self.use_graphs and noise is None:
-            return self._train_step_graphed(x, y, supervised, k)
-        return self._step_body(x, y, supervised, noise, k)
+            self._train_step_graphed(x, y, supervised, k)
+        else:
+            self._step_body(x, y, supervised, noise, k)
+        self._t_host += 1
+        return slot[0], slot[1:1 + 324].view(18, 18)
 
     def _adam_head(self):
         self.optimiser.apply_gradients(lo=self._adam_cut, hi=None, publish=False)
         self._adam_head_done = True
 
+    def _result(self):
+        return (self.store.loss_slot, self._c, self._ring)
+
     def _step_body(self, x, y, supervised, noise, k):
         """forward + backward + (all-reduce) + Adam, as issued eagerly or captured into the step's graph."""
-        split = (self.world == 1 and hasattr(self.engine, "tail_hook")
-                 and os.environ.get("GCCVAE_ADAM_TAIL", "1") != "0" and os.environ.get("GCCVAE_ADAM", "fused") != "split")
+        split = self.world == 1 and hasattr(self.engine, "tail_hook") and self.adam_tail
         self._adam_head_done = False
         if split:
             self.engine.tail_hook = self._adam_head
@@ -405,10 +410,11 @@ class Learner:
         if split:
             self.engine.tail_hook = None
         if self._adam_head_done:
-            self._grads_clean = self.optimiser.apply_gradients(lo=0, hi=self._adam_cut, publish=True)
+            self._grads_clean = self.optimiser.apply_gradients(lo=0, hi=self._adam_cut, publish=True,
+                                                               result=self._result())
         else:
             self._allreduce_grads()
-            self._grads_clean = self.optimiser.apply_gradients()
+            self._grads_clean = self.optimiser.apply_gradients(result=self._result())
         return loss, c
 
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
@@ -453,7 +459,7 @@ class Learner:
         self.lib.gccvae_add_launch_count(g["launches"])
         if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
             self._allreduce_grads()
-            self._grads_clean = self.optimiser.apply_gradients()
+            self._grads_clean = self.optimiser.apply_gradients(result=self._result())
         else:
             self._grads_clean = g["clean"]
         # the next host->device copy into this variant's inputs may start once this event fires.  Recorded AFTER the
@@ -492,19 +498,17 @@ class Learner:
         n0 = self.lib.gccvae_launch_count()
         # the captured step carries no gradient memset: every replay starts from the buffer the (fused) Adam launch of
         # the previous step cleared - inside the graph on one GPU, after the all-reduce in data-parallel runs
-        fused = os.environ.get("GCCVAE_ADAM", "fused") != "split"
-        if fused:
-            if not self._grads_clean:
-                self.engine.zero_grads()
-            self._grads_clean = True
+        fused = True
+        if not self._grads_clean:
+            self.engine.zero_grads()
+        self._grads_clean = True
         with torch.cuda.graph(graph):
             loss = body()
         launches = self.lib.gccvae_launch_count() - n0
         torch.cuda.synchronize(self.device)
         for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
             dst.copy_(src)
-        if fused:
-            self._grads_clean = True     # nothing ran during the capture: the buffer is as clean as before it
+        self._grads_clean = True         # nothing ran during the capture: the buffer is as clean as before it
         return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None, clean=fused)
 
     def classifier_accuracy(self, x, y, noise=None):
@@ -644,13 +648,16 @@ class Learner:
             unsup_iter = iter(data_loaders["unsup"].step()) if perc != 1.0 else None
             sup_loss = unsup_loss = None
             c = None
+            last = torch.zeros(2, dtype=torch.float32, device=self.device)   # last sup / unsup loss of the epoch
             for i, is_sup in enumerate(schedule):
                 xs, ys = next(sup_iter if is_sup else unsup_iter)
                 loss, c = self.train_step(xs, ys if is_sup else None, supervised=is_sup)
+                # train_step's results live in a ring of RING steps: keep the epoch's last losses in their own buffer
+                last[0 if is_sup else 1].copy_(loss)
                 if is_sup:
-                    sup_loss = loss
+                    sup_loss = last[0]
                 else:
-                    unsup_loss = loss
+                    unsup_loss = last[1]
                 if on_batch is not None:
                     on_batch(epoch, i, is_sup, loss, c)
             # one device->host read per epoch instead of per batch (the reference reads loss and c every batch for its

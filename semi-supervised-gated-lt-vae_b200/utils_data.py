@@ -268,6 +268,9 @@ class PrefetchLoader:
         import concurrent.futures as cf
         self.loader, self.n_s, self.depth, self.pin = loader, loader.n_s, max(1, int(depth)), bool(pin)
         self.pool = cf.ThreadPoolExecutor(max_workers=max(1, int(workers)))
+        from collections import deque
+        self.queue = deque()             # decode jobs submitted ahead, in the wrapped loader's order
+        self.Xs = self.ys = None         # the batch handed out last (DataLoader.Xs / .ys)
 
     def _decode_one(self, name):
         from PIL import Image
@@ -289,20 +292,32 @@ class PrefetchLoader:
         return X, labels
 
     def step(self):
-        """the wrapped loader's sequence: its already-read first batch, then `get_batch()` after `get_batch()`."""
-        from collections import deque
-        first = (self.loader.Xs, self.loader.ys)
-        if self.pin:
-            import torch
-            first = (torch.from_numpy(np.ascontiguousarray(first[0])).pin_memory(), first[1])
-        yield first
-        queue = deque(self._submit(self.loader.get_batch()) for _ in range(self.depth))
+        """the wrapped loader's sequence, with the wrapped loader's `step()` semantics (utils_data.py:77-80): every call
+        first yields the batch read LAST (the loader's constructor batch on the first call, the batch the previous
+        `step()` iterator handed out last afterwards) and then continues with `get_batch()` after `get_batch()`.  The
+        read-ahead queue and the last batch live on this object, so batches submitted ahead by one iterator are served
+        by the next one instead of being dropped."""
+        if self.Xs is None:
+            first = (self.loader.Xs, self.loader.ys)
+            if self.pin:
+                import torch
+                first = (torch.from_numpy(np.ascontiguousarray(first[0])).pin_memory(), first[1])
+            self.Xs, self.ys = first
         while True:
-            job = queue.popleft()
-            queue.append(self._submit(self.loader.get_batch()))
-            yield self._finish(job)
+            yield self.Xs, self.ys
+            while len(self.queue) < self.depth:
+                self.queue.append(self._submit(self.loader.get_batch()))
+            job = self.queue.popleft()
+            self.queue.append(self._submit(self.loader.get_batch()))
+            self.Xs, self.ys = self._finish(job)
 
     def reset(self):
+        """utils_data.py:86-87 rewinds the read position only; batches already submitted ahead are discarded so that the
+        next read is the first batch of the order, as it is for the wrapped loader."""
+        for futures, _ in self.queue:
+            for f in futures:
+                f.cancel()
+        self.queue.clear()
         self.loader.reset()
 
     def close(self):
@@ -341,6 +356,7 @@ class CachedLoader:
             self.pixels = torch.from_numpy(pixels).to(device)
         else:
             self.pixels = pixels
+        self.Xs = self.ys = None         # the batch handed out last (DataLoader.Xs / .ys)
 
     def _gather(self, idxs):
         if self.device is not None:
@@ -353,12 +369,15 @@ class CachedLoader:
         return x, self.labels[idxs]
 
     def step(self):
-        # the wrapped loader drew its first batch in its constructor: indices order[0 : bs] (start was 0)
-        order, bs = self.loader.idxs, self.loader.bs
-        first = order[:bs] if bs < self.n_s else order[:] + order[:bs - self.n_s]
-        yield self._gather(first)
+        """`DataLoader.step()` semantics (utils_data.py:77-80): yield the batch read last, then read on.  The first
+        batch is the one the wrapped loader drew in its constructor: indices order[0 : bs] (its start was 0)."""
+        if self.Xs is None:
+            order, bs = self.loader.idxs, self.loader.bs
+            first = order[:bs] if bs < self.n_s else order[:] + order[:bs - self.n_s]
+            self.Xs, self.ys = self._gather(first)
         while True:
-            yield self._gather(self.loader.get_batch())
+            yield self.Xs, self.ys
+            self.Xs, self.ys = self._gather(self.loader.get_batch())
 
     def reset(self):
         self.loader.reset()

@@ -7,6 +7,8 @@ HERE=$(cd "$(dirname "$0")" && pwd)
 mkdir -p "$HERE/data" "$HERE/learned" "$HERE/logs" "$HERE/models/params_0.2_learnable" "$HERE/models/params_1.0_fixed_one-one"
 # initial gating matrices (utils_data.py:147-176) with their pandas CSV exports, and the full-data co-occurrence table
 cp "$REF"/data/gating_matrix_*.npy "$REF"/data/gating_matrix_*.csv "$REF"/data/label_cooccurance_matrix.csv "$HERE/data/"
+# the same five .npy files also live in <repo>/data/ (the reference's own location, utils_data.py:149): bench.py, smoke() and scripts/ read them there
+mkdir -p "$HERE/../../data" && cp "$REF"/data/gating_matrix_*.npy "$HERE/../../data/"
 # learned gating matrices (gated_ccvae.py:396-403)
 for f in 0.2 0.5 1.0; do for m in best last; do
   cp "$REF/models/params_${f}_learnable/learned_gating_matrix_${m}.npy" "$HERE/learned/learned_gating_matrix_${f}_${m}.npy"

@@ -94,6 +94,48 @@ def test_prefetching_loader_yields_the_same_batches_in_the_same_order(root):
     f32.close()
 
 
+def test_wrapped_loaders_resume_like_the_plain_loader_across_step_calls(root, tmp_path):
+    """Learner.train() / accuracy() call .step() afresh every epoch: the reference's generator (utils_data.py:77-80) then
+    re-yields the batch it read last and reads on.  The wrappers must serve the same sequence over several step() calls
+    (and must not drop the batches they decoded ahead)."""
+    path, _ = root
+    mk = lambda: G.utils_data.CelebAReader(path, 0.25, 4, split_map=SPLIT, dtype="uint8").setup_data_loaders(
+        shuffle=True, rng=np.random.default_rng(5))["unsup"]
+
+    def epochs(loader, n_epochs=3, per_epoch=3):
+        out = []
+        for _ in range(n_epochs):
+            it = iter(loader.step())
+            out.append([next(it) for _ in range(per_epoch)])
+        return out
+
+    want = epochs(mk())
+    # the plain loader repeats the last batch of an epoch as the first of the next one
+    assert np.array_equal(want[0][-1][0], want[1][0][0]) and not np.array_equal(want[1][0][0], want[1][1][0])
+    pre = UD.PrefetchLoader(mk(), workers=3, depth=2)
+    cached = UD.CachedLoader(mk(), cache_path=str(tmp_path / "c.npy"), workers=2)
+    for got in (epochs(pre), epochs(cached)):
+        for ew, eg in zip(want, got):
+            for (xa, ya), (xb, yb) in zip(ew, eg):
+                assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    pre.close()
+
+    # reset() rewinds the read position for all three in the same way (the batch read last is still yielded first)
+    def with_reset(loader):
+        it = iter(loader.step())
+        out = [next(it) for _ in range(2)]
+        loader.reset()
+        it = iter(loader.step())
+        return out + [next(it) for _ in range(3)]
+
+    want = with_reset(mk())
+    pre = UD.PrefetchLoader(mk(), workers=3, depth=2)
+    for got in (with_reset(pre), with_reset(UD.CachedLoader(mk(), cache_path=str(tmp_path / "c.npy")))):
+        for (xa, ya), (xb, yb) in zip(want, got):
+            assert np.array_equal(xa, xb) and np.array_equal(ya, yb)
+    pre.close()
+
+
 def test_cached_loader_decodes_once_and_serves_identical_batches(root, tmp_path):
     import shutil
     path, _ = root

@@ -2,8 +2,6 @@
 relies on the previous update having cleared the buffer; a forward/backward call in between (dirty gradients) must not
 leak into the next train_step; the two-part update (bulk under the last dgrad + first layer at the end) and the plain
 two-launch update give bit-identical parameters."""
-import os
-
 import pytest
 import torch
 
@@ -55,26 +53,35 @@ def test_dirty_gradients_do_not_leak_into_the_next_step(graphs):
 
 
 def test_two_part_update_equals_the_plain_update():
+    import gccvae_b200 as G
     x, y = _data()
     outs = []
-    for env in ({"GCCVAE_ADAM_TAIL": "1"}, {"GCCVAE_ADAM_TAIL": "0"}, {"GCCVAE_ADAM": "split"}):
-        old = {k: os.environ.get(k) for k in ("GCCVAE_ADAM_TAIL", "GCCVAE_ADAM")}
-        os.environ.update(env)
-        try:
-            lrn = _learner(False)
-            noise = None
-            for _ in range(2):
-                lrn.train_step(x, y, True, noise=noise)
-                lrn.train_step(x, None, False, noise=noise)
-            torch.cuda.synchronize()
-            outs.append((lrn.store.flat.clone(), lrn.optimiser.m.clone(), lrn.optimiser.iterations))
-        finally:
-            for k, v in old.items():
-                if v is None:
-                    os.environ.pop(k, None)
-                else:
-                    os.environ[k] = v
-    assert outs[0][2] == outs[1][2] == outs[2][2] == 4
-    for o in outs[1:]:
-        differs = ((o[0] - outs[0][0]).abs() > 2e-6).float().mean().item()
-        assert differs < 0.01, differs
+    for tail in (True, False):
+        cfg = dict(cfg_for("learnable", "0.5"), batch_size=32)
+        lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=False, seed=5, adam_tail=tail)
+        lrn.store.load_dict(O.init_params(0, trained_like=True))
+        for _ in range(2):
+            lrn.train_step(x, y, True)
+            lrn.train_step(x, None, False)
+        torch.cuda.synchronize()
+        outs.append((lrn.store.flat.clone(), lrn.optimiser.m.clone(), lrn.optimiser.iterations))
+    assert outs[0][2] == outs[1][2] == 4
+    differs = ((outs[1][0] - outs[0][0]).abs() > 2e-6).float().mean().item()
+    assert differs < 0.01, differs
+
+
+@pytest.mark.parametrize("graphs", [False, True])
+def test_train_step_results_are_not_overwritten_by_the_next_steps(graphs):
+    """gated_ccvae.py:311 returns fresh tensors; here the publishing Adam launch copies (loss, c) into a ring, so what
+    train_step handed back must still hold its own step's values after the following steps ran."""
+    x, y = _data()
+    lrn = _learner(graphs)
+    kept, values = [], []
+    for i in range(6):
+        loss, c = lrn.train_step(x, y if i % 2 == 0 else None, i % 2 == 0)
+        torch.cuda.synchronize()
+        kept.append((loss, c))
+        values.append((float(loss), c.clone()))
+    assert len({round(v, 4) for v, _ in values}) > 2          # the steps really differ
+    for (loss, c), (v, cv) in zip(kept, values):
+        assert float(loss) == v and torch.equal(c, cv)
