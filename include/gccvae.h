@@ -281,6 +281,82 @@ int gccvae_gate_bwd(float* partials /* [n_partials + 1 rows]: the last row is sc
                     float* dWlt, float* dWlf, float* dWst, float* dWsf, float* dmu, float* loss_inout,
                     void* stream);
 
+/* ---- fused dense chain (bf16 engine): everything between the encoder's last convolution and the decoder's first
+ * transposed convolution is row-local, so ONE launch each way carries groups of gccvae_chain_rows(batch) images
+ * through it (csrc/chain.cu):
+ *   forward:  h5 -> heads (networks.py:17-18,31-34) -> the whole of gccvae_latent_fwd -> fc1 + ReLU (networks.py:43,52)
+ *             -> conv1t + ReLU (networks.py:45,54);
+ *   backward: conv1t dgrad -> ReLU mask -> fc1 dgrad -> the whole of gccvae_latent_bwd -> heads dgrad -> ReLU mask,
+ *             plus the bias gradients of conv1t / fc1 / the heads / conv5 (accumulated with atomics: the buffers must
+ *             be zero or hold partial sums) and the per-CTA partial rows gccvae_gate_bwd reduces.
+ * Weight operands are the packed bf16 matrices of gccvae_pack_jobs_bf16 ([out feature][k], k contiguous, zero padded);
+ * activations between the layers are bf16 as on the tensor-core path, everything else fp32.  Noise, seeds, `terms`,
+ * `partials` as for the latent kernels; n_partials must equal gccvae_chain_partials(batch). */
+typedef struct {
+  int batch, batch_global, supervised, K;
+  int rows_per_cta;          /* set by the library */
+  int pad_;
+  const void* h5;            /* bf16 [B,256] conv5 output (after ReLU) */
+  const void* w_heads;       /* bf16 [96][256]: rows 0..44 locs, 48..92 std */
+  const float* b_heads;      /* [96] (same row layout, pads zero) */
+  const void* w_fc1;         /* bf16 [64][64]  [out][in] */
+  const float* b_fc1;        /* [45] */
+  const void* w_conv1t;      /* bf16 [2048][64] [(kh,kw,co)][ci] */
+  const float* b_conv1t;     /* [128] */
+  const long long* y;        /* [B,18] int64 labels (sup) */
+  const float* eps;          /* [B,45] or NULL -> Philox */
+  const float* eps_k;        /* [K,B,18] or NULL -> Philox */
+  const float* U_y;          /* [B,18] or NULL -> Philox */
+  uint64_t seed, offset;
+  const int* step_dev;
+  const float* gate_ws;
+  float* pre;                /* [B,96] heads' pre-activations: locs at 0..44, std at 48..92 */
+  float* loc;                /* [B,45] */
+  float* scale;              /* [B,45] */
+  float* z;                  /* [B,45] */
+  float* terms;              /* [6,B] */
+  float* logits;             /* [B,18] */
+  int* y_out;                /* [B,18] or NULL */
+  void* z16;                 /* bf16 [B,64] */
+  void* g0;                  /* bf16 [B,64]  fc1 output (45 real columns) */
+  void* g1;                  /* bf16 [B,2048] conv1t output = [B,4,4,128] */
+} gccvae_chain_fwd_args;
+int gccvae_chain_rows(int batch);
+int gccvae_chain_partials(int batch);
+int gccvae_chain_fwd(const gccvae_chain_fwd_args* a, void* stream);
+
+typedef struct {
+  int batch, batch_global, supervised, K;
+  int rows_per_cta;          /* set by the library */
+  int n_partials;
+  const void* dg1;           /* bf16 [B,2048] gradient of conv1t's pre-activation */
+  const void* g0;            /* bf16 [B,64] fc1 output */
+  const void* h5;            /* bf16 [B,256] conv5 output */
+  const float* pre;          /* [B,96] from the forward */
+  const int* y;              /* [B,18] labels used by the forward (y_out) */
+  const float* eps;
+  const float* eps_k;
+  uint64_t seed, offset;
+  const int* step_dev;
+  const float* gate_ws;
+  const float* terms;        /* [6,B] from the forward */
+  const float* log_pxz;      /* [B] */
+  const void* w_conv1t_t;    /* bf16 [64][2048]  [ci][(kh,kw,co)] */
+  const void* w_fc1_t;       /* bf16 [64][64]  [in][out] */
+  const void* w_heads_t;     /* bf16 [256][96] */
+  void* dg0;                 /* bf16 [B,64] gradient of fc1's pre-activation */
+  void* dpre16;              /* bf16 [B,96] gradient of the heads' pre-activations */
+  void* dh5;                 /* bf16 [B,256] gradient of conv5's pre-activation */
+  float* partials;           /* [n_partials + 1, GCCVAE_LATENT_PARTIAL_FLOATS] */
+  float* db_loc;             /* [45] += (optional, with db_scale) */
+  float* db_scale;
+  float* db_fc1;             /* [45] += (optional) */
+  float* db_conv1t;          /* [128] += (optional) */
+  float* db_conv5;           /* [256] += (optional) */
+} gccvae_chain_bwd_args;
+int gccvae_chain_bwd(const gccvae_chain_bwd_args* a, void* stream);
+
+
 /* ---- reconstruction log-likelihood (utils.py:101-105) ---------------------------------------------
  * log_pxz[b] = -sum|x - xhat| - 12288 ln2; optionally also the gradient w.r.t. the decoder's
  * pre-sigmoid logits, dlogit = coef[b] * sign(x - xhat) * xhat (1 - xhat). */

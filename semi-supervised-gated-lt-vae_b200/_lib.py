@@ -47,6 +47,35 @@ class LatentBwdArgs(C.Structure):
     ]
 
 
+class ChainFwdArgs(C.Structure):
+    """gccvae_chain_fwd_args (include/gccvae.h)."""
+    _fields_ = [
+        ("batch", C.c_int), ("batch_global", C.c_int), ("supervised", C.c_int), ("K", C.c_int),
+        ("rows_per_cta", C.c_int), ("pad_", C.c_int),
+        ("h5", C.c_void_p), ("w_heads", C.c_void_p), ("b_heads", C.c_void_p), ("w_fc1", C.c_void_p),
+        ("b_fc1", C.c_void_p), ("w_conv1t", C.c_void_p), ("b_conv1t", C.c_void_p),
+        ("y", C.c_void_p), ("eps", C.c_void_p), ("eps_k", C.c_void_p), ("U_y", C.c_void_p),
+        ("seed", C.c_uint64), ("offset", C.c_uint64), ("step_dev", C.c_void_p), ("gate_ws", C.c_void_p),
+        ("pre", C.c_void_p), ("loc", C.c_void_p), ("scale", C.c_void_p), ("z", C.c_void_p), ("terms", C.c_void_p),
+        ("logits", C.c_void_p), ("y_out", C.c_void_p), ("z16", C.c_void_p), ("g0", C.c_void_p), ("g1", C.c_void_p),
+    ]
+
+
+class ChainBwdArgs(C.Structure):
+    """gccvae_chain_bwd_args (include/gccvae.h)."""
+    _fields_ = [
+        ("batch", C.c_int), ("batch_global", C.c_int), ("supervised", C.c_int), ("K", C.c_int),
+        ("rows_per_cta", C.c_int), ("n_partials", C.c_int),
+        ("dg1", C.c_void_p), ("g0", C.c_void_p), ("h5", C.c_void_p), ("pre", C.c_void_p), ("y", C.c_void_p),
+        ("eps", C.c_void_p), ("eps_k", C.c_void_p), ("seed", C.c_uint64), ("offset", C.c_uint64),
+        ("step_dev", C.c_void_p), ("gate_ws", C.c_void_p), ("terms", C.c_void_p), ("log_pxz", C.c_void_p),
+        ("w_conv1t_t", C.c_void_p), ("w_fc1_t", C.c_void_p), ("w_heads_t", C.c_void_p),
+        ("dg0", C.c_void_p), ("dpre16", C.c_void_p), ("dh5", C.c_void_p), ("partials", C.c_void_p),
+        ("db_loc", C.c_void_p), ("db_scale", C.c_void_p), ("db_fc1", C.c_void_p), ("db_conv1t", C.c_void_p),
+        ("db_conv5", C.c_void_p),
+    ]
+
+
 class PackJob(C.Structure):
     _fields_ = [("kind", C.c_int), ("taps", C.c_int), ("CL", C.c_int), ("CS", C.c_int), ("W", C.c_void_p),
                 ("out", C.c_void_p), ("sr", C.c_int), ("sk", C.c_int), ("ld_out", C.c_int), ("row_off", C.c_int),
@@ -110,6 +139,10 @@ SIGNATURES = {
     "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),
     "gccvae_latent_bwd_partials": (_I, [_I]),
     "gccvae_latent_bwd": (_I, [C.POINTER(LatentBwdArgs), _P]),
+    "gccvae_chain_rows": (_I, [_I]),
+    "gccvae_chain_partials": (_I, [_I]),
+    "gccvae_chain_fwd": (_I, [C.POINTER(ChainFwdArgs), _P]),
+    "gccvae_chain_bwd": (_I, [C.POINTER(ChainBwdArgs), _P]),
     "gccvae_gate_bwd": (_I, [_P, _I, _P, _P, _P, _P, _P, _P, _P, _F, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_recon_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gccvae_adam_f32": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _P, _P]),

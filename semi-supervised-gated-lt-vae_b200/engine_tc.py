@@ -45,8 +45,11 @@ def _dense64_geom(rows, cs):
 class EngineTC(Engine):
     precision = "bf16"
 
-    def __init__(self, store):
+    def __init__(self, store, fused_chain=True):
         super().__init__(store)
+        # conv5 -> heads -> latent -> fc1 -> conv1t (and the reverse) as ONE launch each way (csrc/chain.cu); False keeps
+        # the layer-by-layer kernels (A/B runs, cross-check in tests/test_gpu_chain.py)
+        self.chain = bool(fused_chain)
         dev = self.device
         lib = self.lib
         z16 = lambda *shape: torch.zeros(*shape, dtype=BF16, device=dev)
@@ -202,6 +205,16 @@ class EngineTC(Engine):
                     ld_dz=64, dloc_pre=None, dscale_pre=None, dpre16=ptr(b["dpre16"]), db_loc=ptr(g_("enc.locs.b")),
                     db_scale=ptr(g_("enc.std.b")))
 
+    def chain_io(self, b):
+        """buffers and packed operands the fused chain kernels (gccvae_chain_fwd / _bwd) read and write."""
+        v, g_, wp = self.store.view, self.store.g, self.wp
+        return dict(h5=b["enc.conv5.out"], pre=b["pre96"], z16=b["z16"], g0=b["dec.fc1.out"], g1=b["dec.conv1t.out"],
+                    dg1=b["dec.conv1t.dout"], dg0=b["dec.fc1.dout"], dpre16=b["dpre16"], dh5=b["enc.conv5.dout"],
+                    w_heads=wp["heads.ls"], b_heads=wp["heads.bias"], w_fc1=wp["fc1.ls"], b_fc1=v("dec.fc1.b"),
+                    w_conv1t=wp["conv1t.sl"], b_conv1t=v("dec.conv1t.b"), w_conv1t_t=wp["conv1t.ls"],
+                    w_fc1_t=wp["fc1.sl"], w_heads_t=wp["heads.sl"], db_loc=g_("enc.locs.b"), db_scale=g_("enc.std.b"),
+                    db_fc1=g_("dec.fc1.b"), db_conv1t=g_("dec.conv1t.b"), db_conv5=g_("enc.conv5.b"))
+
     # ---- helpers --------------------------------------------------------------------------------------------
     def _run(self, what, tensors, rc_fn):
         """issue one C-ABI call; with self.prof set, bracket it with CUDA events on the launching stream and
@@ -310,6 +323,8 @@ class EngineTC(Engine):
             self._bias_fused.add(name)
 
     def _arm_wgrad_bias(self, name, n, side, dout=None):
+        if name in getattr(self, "_chain_bias", ()):      # produced by the fused chain kernel
+            return
         if name in self._bias_fused:      # already produced by the dgrad epilogue
             self._bias_fused.discard(name)
             return
@@ -352,7 +367,7 @@ class EngineTC(Engine):
         self._begun = True
         self._log_pxz_ready = log_pxz is not None
 
-    def encoder_fwd(self, x, b):
+    def encoder_fwd(self, x, b, heads=True):
         B = x.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
         begun, self._begun = getattr(self, "_begun", False), False
@@ -394,19 +409,21 @@ class EngineTC(Engine):
                           C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU, None,
                           ptr(b[name + ".out"]), 0, st))
             h = b[name + ".out"]
-        self._gemm(B, 256, 96, h, self.wp["heads.ls"], self.wp["heads.bias"], 96, 0, ACT_NONE, None, b["pre96"], 1,
-                   "enc.heads fwd")
+        if heads:      # (inside the ELBO step the fused chain kernel computes them)
+            self._gemm(B, 256, 96, h, self.wp["heads.ls"], self.wp["heads.bias"], 96, 0, ACT_NONE, None, b["pre96"], 1,
+                       "enc.heads fwd")
         return b["pre96"][:, 0:45], b["pre96"][:, 48:93]
 
-    def decoder_fwd(self, z, b, z16_ready=False, fused_recon=False, batch=None):
+    def decoder_fwd(self, z, b, z16_ready=False, fused_recon=False, batch=None, head=True):
         B = z.shape[0] if batch is None else batch
         lib, st, v = self.lib, _stream(), self.store.view
         if not z16_ready:          # standalone Decoder(z) call; inside the step the latent kernel writes z16
             b["z16"][:, :45].copy_(z)
-        self._gemm(B, 64, 64, b["z16"], self.wp["fc1.ls"], v("dec.fc1.b"), 45, 0, ACT_RELU, None, b["dec.fc1.out"], 0,
-                   "dec.fc1 fwd")
-        self._gemm(B, 64, 2048, b["dec.fc1.out"], self.wp["conv1t.sl"], v("dec.conv1t.b"), 2048, 128, ACT_RELU, None,
-                   b["dec.conv1t.out"], 0, "dec.conv1t fwd")
+        if head:                   # (inside the ELBO step the fused chain kernel has produced dec.conv1t.out)
+            self._gemm(B, 64, 64, b["z16"], self.wp["fc1.ls"], v("dec.fc1.b"), 45, 0, ACT_RELU, None, b["dec.fc1.out"], 0,
+                       "dec.fc1 fwd")
+            self._gemm(B, 64, 2048, b["dec.fc1.out"], self.wp["conv1t.sl"], v("dec.conv1t.b"), 2048, 128, ACT_RELU, None,
+                       b["dec.conv1t.out"], 0, "dec.conv1t fwd")
         h = b["dec.conv1t.out"]
         for name in TC_DEC:
             g = make_geom(_DEC[name], B)
@@ -419,10 +436,10 @@ class EngineTC(Engine):
         self._sl("dec.conv5t", g, h, v("dec.conv5t.b"), ACT_SIGMOID, None, xh4, 2, "dec.conv5t fwd")
         return xh4[..., :3]
 
-    def decoder_fwd_recon(self, x, b, coef, log_pxz, backward, want_recon):
+    def decoder_fwd_recon(self, x, b, coef, log_pxz, backward, want_recon, head=True):
         """decoder forward with conv5t + sigmoid + Laplace log-likelihood (+ dLoss/dlogit in x2 block form) fused."""
         B = x.shape[0]
-        self.decoder_fwd(None, b, z16_ready=True, fused_recon=True, batch=B)
+        self.decoder_fwd(None, b, z16_ready=True, fused_recon=True, batch=B, head=head)
         xhat = None
         if want_recon:
             if b["xhat3"] is None:
@@ -450,7 +467,8 @@ class EngineTC(Engine):
         return b["xhat4"][..., :3]
 
     # ---- backward -----------------------------------------------------------------------------------------------
-    def decoder_bwd(self, z, b, want_dz=True):
+    def decoder_bwd(self, z, b, want_dz=True, tail=True):
+        """`tail=False`: stop after conv2t's dgrad (the fused chain kernel continues from dec.conv1t.dout)."""
         B = z.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
         g4 = b["dec.conv4t.out"]
@@ -499,6 +517,8 @@ class EngineTC(Engine):
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
                                          "dec.conv1t wgrad"))
+        if not tail:
+            return None
         if "dec.conv1t" in self._bias_fused:
             self._bias_fused.discard("dec.conv1t")
         else:
@@ -513,16 +533,25 @@ class EngineTC(Engine):
             self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "dec.fc1 dgrad")
         return b["dz64"][:, :45]
 
-    def encoder_bwd(self, x, b):
+    def heads_wgrad(self, b, B):
+        """weight gradients of both [256,45] head kernels in one GEMM (bias gradients come from the latent stage)."""
+        g_ = self.store.g
+        self._gemm_tn(B, 256, 96, b["enc.conv5.out"], b["dpre16"],
+                      [(0, 45, 45, g_("enc.locs.w")), (48, 45, 45, g_("enc.std.w"))], 256, "enc.heads wgrad")
+
+    def fc1_wgrad(self, b, B):
+        self._gemm_tn(B, 64, 64, b["z16"], b["dec.fc1.dout"], [(0, 45, 45, self.store.g("dec.fc1.w"))], 45, "dec.fc1 wgrad")
+
+    def encoder_bwd(self, x, b, heads=True):
+        """`heads=False`: enc.conv5.dout is already there (fused chain kernel), start at conv5's own backward."""
         B = x.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
         h5, dh5, dpre = b["enc.conv5.out"], b["enc.conv5.dout"], b["dpre16"]
-        # heads: weight gradients of both [256,45] kernels in one GEMM; bias gradients come from the latent kernel
-        self._side(lambda: self._gemm_tn(B, 256, 96, h5, dpre,
-                                         [(0, 45, 45, g_("enc.locs.w")), (48, 45, 45, g_("enc.std.w"))], 256,
-                                         "enc.heads wgrad"))
-        self._fuse_bias("enc.conv5", 256)
-        self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "enc.heads dgrad")
+        if heads:
+            self._side(lambda: self.heads_wgrad(b, B))
+            self._fuse_bias("enc.conv5", 256)
+            self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "enc.heads dgrad")
+        self._chain_bias = {"enc.conv5"} if not heads else set()
         prev_of = {"enc.conv5": "enc.conv4", "enc.conv4": "enc.conv3", "enc.conv3": "enc.conv2",
                    "enc.conv2": "enc.conv1"}
         for name in reversed(TC_ENC):

@@ -28,7 +28,8 @@ import numpy as np
 import torch
 
 from . import _lib, dp
-from ._lib import GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, RESULT_SLOT_FLOATS, LatentBwdArgs, LatentFwdArgs, ptr
+from ._lib import (GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, RESULT_SLOT_FLOATS, ChainBwdArgs, ChainFwdArgs, LatentBwdArgs,
+                   LatentFwdArgs, ptr)
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
 from .params import ParamStore, keras_default_init
@@ -40,7 +41,8 @@ logger = logging.getLogger(__name__)
 class CCVAE:
     """gated_ccvae.py:23-111."""
 
-    def __init__(self, z_dim, z_classify, y_dim, train_config, device=None, precision="fp32", init_seed=0):
+    def __init__(self, z_dim, z_classify, y_dim, train_config, device=None, precision="fp32", init_seed=0,
+                 engine_options=None):
         if (z_dim, z_classify, y_dim) != (45, 18, 18):
             raise ValueError("the sm_100a kernels are specialised for z_dim=45, z_classify=y_dim=18")
         self.z_dim = z_dim
@@ -50,7 +52,7 @@ class CCVAE:
         self.device = torch.device(device) if device is not None else _default_device()
         self.store = ParamStore(self.device)
         keras_default_init(self.store, init_seed)
-        self.engine = make_engine(self.store, precision)
+        self.engine = make_engine(self.store, precision, **(engine_options or {}))
         self.lib = self.engine.lib
         kw = dict(store=self.store, engine=self.engine)
         self.encoder = Encoder(z_dim, **kw)
@@ -110,12 +112,14 @@ class CCVAE:
         return c
 
 
-def make_engine(store, precision):
+def make_engine(store, precision, **options):
     if precision == "fp32":
+        if options:
+            raise ValueError("the fp32 engine has no options (got {})".format(sorted(options)))
         return Engine(store)
     if precision == "bf16":
         from .engine_tc import EngineTC
-        return EngineTC(store)
+        return EngineTC(store, **options)
     raise ValueError("precision must be 'fp32' or 'bf16', got {!r}".format(precision))
 
 
@@ -156,7 +160,7 @@ class Learner:
     """gated_ccvae.py:114-311, 421-455."""
 
     def __init__(self, ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config, device=None,
-                 precision="fp32", seed=1234, init_seed=0, graphs=False, adam_tail=True):
+                 precision="fp32", seed=1234, init_seed=0, graphs=False, adam_tail=True, engine_options=None):
         if tuple(ip_shape) != (64, 64, 3):
             raise ValueError("the kernels are specialised for 64x64x3 inputs (gated_ccvae.py:481)")
         self.train_config = train_config
@@ -169,7 +173,7 @@ class Learner:
         self.latent_sampler_temp = train_config.get("init_temp", 0.1)
         self.gating_sampler_temp = train_config["gating_init_temp"]
         self.model = CCVAE(z_dim, z_classify, y_dim, train_config, device=device, precision=precision,
-                           init_seed=init_seed)
+                           init_seed=init_seed, engine_options=engine_options)
         self.device = self.model.device
         self.p_Y = torch.full((1, y_dim), 0.5, dtype=torch.float32, device=self.device)  # gated_ccvae.py:141
         self.store, self.engine, self.lib = self.model.store, self.model.engine, self.model.lib
@@ -206,7 +210,8 @@ class Learner:
         lb = self._lat.get(B)
         if lb is None:
             e = lambda *s, dt=torch.float32: torch.empty(*s, dtype=dt, device=self.device)
-            npart = self.lib.gccvae_latent_bwd_partials(B)
+            npart = (self.lib.gccvae_chain_partials(B) if getattr(self.engine, "chain", False)
+                     else self.lib.gccvae_latent_bwd_partials(B))
             lb = dict(loc=e(B, 45), scale=e(B, 45), z=e(B, 45), terms=e(6, B), logits=e(B, 18),
                       y_i32=e(B, 18, dt=torch.int32), log_pxz=e(B), partials=e(npart + 1, LATENT_PARTIAL_FLOATS),
                       npart=npart)
@@ -290,6 +295,34 @@ class Learner:
         a.partials, a.n_partials, a.loss_out = ptr(lb["partials"]), lb["npart"], None
         _lib.check(self.lib.gccvae_latent_bwd(C.byref(a), _stream()), "latent_bwd")
 
+    def _chain_fwd(self, B, lb, b, y, n, supervised, K):
+        """conv5 output -> heads -> latent forward -> fc1 -> conv1t in one launch (bf16 engine, csrc/chain.cu)."""
+        a, io = ChainFwdArgs(), self.engine.chain_io(b)
+        a.batch, a.batch_global, a.supervised, a.K = B, dp.batch_global(B, self.world), int(supervised), K
+        for k_ in ("h5", "w_heads", "b_heads", "w_fc1", "b_fc1", "w_conv1t", "b_conv1t", "pre", "z16", "g0", "g1"):
+            setattr(a, k_, ptr(io[k_]))
+        a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
+        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), 0, ptr(self.optimiser.step_dev)
+        a.gate_ws = ptr(self._gate_ws)
+        a.loc, a.scale, a.z, a.terms, a.logits, a.y_out = (ptr(lb["loc"]), ptr(lb["scale"]), ptr(lb["z"]),
+                                                           ptr(lb["terms"]), ptr(lb["logits"]), ptr(lb["y_i32"]))
+        self.engine._run("chain fwd", (io["h5"], io["w_heads"], io["w_conv1t"], io["g1"]),
+                         lambda: self.lib.gccvae_chain_fwd(C.byref(a), _stream()))
+
+    def _chain_bwd(self, B, lb, b, n, supervised, K):
+        """dec.conv1t.dout -> conv1t / fc1 dgrad -> latent backward -> heads dgrad -> enc.conv5.dout in one launch."""
+        a, io = ChainBwdArgs(), self.engine.chain_io(b)
+        a.batch, a.batch_global, a.supervised, a.K = B, dp.batch_global(B, self.world), int(supervised), K
+        a.n_partials = lb["npart"]
+        for k_ in ("dg1", "g0", "h5", "pre", "w_conv1t_t", "w_fc1_t", "w_heads_t", "dg0", "dpre16", "dh5", "db_loc",
+                   "db_scale", "db_fc1", "db_conv1t", "db_conv5"):
+            setattr(a, k_, ptr(io[k_]))
+        a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
+        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), 0, ptr(self.optimiser.step_dev)
+        a.gate_ws, a.terms, a.log_pxz, a.partials = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"]), ptr(lb["partials"])
+        self.engine._run("chain bwd", (io["dg1"], io["w_conv1t_t"], io["w_heads_t"], io["dh5"]),
+                         lambda: self.lib.gccvae_chain_bwd(C.byref(a), _stream()))
+
     def _elbo(self, x, y, supervised, noise=None, backward=False, k=100):
         x, y = self._prep_inputs(x, y if supervised else None)
         B = x.shape[0]
@@ -305,13 +338,24 @@ class Learner:
             if not self._grads_clean:    # otherwise the previous Adam launch left the buffer zeroed
                 self.engine.zero_grads()
             self._grads_clean = False
+        chain = getattr(self.engine, "chain", False) and getattr(self.engine, "x2", False)
         self._gate(n)
         mark("zero+gate", coarse=True)
-        self.engine.encoder_fwd(x, b)
-        mark("encoder fwd", coarse=True)
-        self._latent_fwd(B, lb, b, y, n, supervised, k)
-        mark("latent fwd", coarse=True)
-        if getattr(self.engine, "x2", False):
+        if chain:
+            self.engine.encoder_fwd(x, b, heads=False)
+            mark("encoder fwd", coarse=True)
+            self._chain_fwd(B, lb, b, y, n, supervised, k)
+            mark("chain fwd", coarse=True)
+        else:
+            self.engine.encoder_fwd(x, b)
+            mark("encoder fwd", coarse=True)
+            self._latent_fwd(B, lb, b, y, n, supervised, k)
+            mark("latent fwd", coarse=True)
+        if chain:
+            xhat = self.engine.decoder_fwd_recon(x, b, lb["terms"][5], lb["log_pxz"], backward,
+                                                 want_recon=not torch.cuda.is_current_stream_capturing(), head=False)
+            mark("decoder fwd + recon", coarse=True)
+        elif getattr(self.engine, "x2", False):
             xhat = self.engine.decoder_fwd_recon(x, b, lb["terms"][5], lb["log_pxz"], backward,
                                                  want_recon=not torch.cuda.is_current_stream_capturing())
             mark("decoder fwd + recon", coarse=True)
@@ -321,10 +365,17 @@ class Learner:
             xhat = self.engine.recon(x, b, lb["terms"][5], lb["log_pxz"], backward)
             mark("recon", coarse=True)
         if backward:
-            self.engine.decoder_bwd(lb["z"], b)
+            if chain:
+                self.engine.decoder_bwd(lb["z"], b, tail=False)
+            else:
+                self.engine.decoder_bwd(lb["z"], b)
             mark("decoder bwd (main)", coarse=True)
-            self._latent_bwd(B, lb, b, n, supervised, k)
-            mark("latent bwd", coarse=True)
+            if chain:
+                self._chain_bwd(B, lb, b, n, supervised, k)
+                mark("chain bwd", coarse=True)
+            else:
+                self._latent_bwd(B, lb, b, n, supervised, k)
+                mark("latent bwd", coarse=True)
             v, g = self.store.view, self.store.g
 
             def gate_bwd():
@@ -337,8 +388,19 @@ class Learner:
                     ptr(self.store.loss_slot), _stream()), "gate_bwd")
                 mark("gate bwd", coarse=True)
 
-            gate_bwd()
-            self.engine.encoder_bwd(x, b)
+            if chain:
+                # the weight gradients that read the chain kernel's outputs, and the reduction of its partial rows into
+                # the gate / classifier / prior gradients (they feed only Adam and the returned loss), go to the
+                # weight-gradient stream: nothing of them is left on the dgrad chain
+                def after_chain():
+                    self.engine.fc1_wgrad(b, B)
+                    self.engine.heads_wgrad(b, B)
+                    gate_bwd()
+                self.engine._side(after_chain)
+                self.engine.encoder_bwd(x, b, heads=False)
+            else:
+                gate_bwd()
+                self.engine.encoder_bwd(x, b)
             mark("encoder bwd + join", coarse=True)
         else:
             _lib.check(self.lib.gccvae_elbo_loss_f32(ptr(lb["terms"]), ptr(lb["log_pxz"]), B,
