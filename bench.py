@@ -54,6 +54,9 @@ def parse():
     ap.add_argument("--gate", default="inferred", choices=["one-one", "inferred", "learnable"])
     ap.add_argument("--frac", default="0.2", help="which data/gating_matrix_<frac>.npy initialises mu")
     ap.add_argument("--unsup-per-sup", type=int, default=1, help="unsupervised train_steps per supervised one")
+    ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
+                    help="gradient exchange of the data-parallel step: fused two-shot all-reduce + Adam over NVLink peer "
+                         "memory (csrc/dp.cu) or NCCL all-reduce")
     ap.add_argument("--e2e-input", default="uint8", choices=["uint8", "fp32"],
                     help="host image dtype of the headline e2e run (the other one is reported as e2e_alt)")
     args = ap.parse_args()
@@ -165,6 +168,40 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------
+# data-parallel self-check (world > 1): sharded step == whole-batch step, with this repo's fp32 engine on both sides
+# ---------------------------------------------------------------------------------------------------
+def dp_equivalence_check(G, cfg, dev, rank, world, exchange, b_local=8, K=10):
+    """One supervised + one unsupervised fp32 train_step with explicit noise: `world` ranks on their shards of a batch of
+    b_local x world images (gradient exchange + Adam through the product's data-parallel path) against ONE device on the
+    whole batch.  Returns the relative loss differences and the fraction of parameters that differ by more than 2e-5
+    after the two updates (lr 1e-3: a wrong exchange moves every parameter by ~1e-3)."""
+    import torch.distributed as dist
+    g = torch.Generator().manual_seed(99)
+    n = b_local * world
+    x = torch.rand(n, 64, 64, 3, generator=g)
+    y = (torch.rand(n, 18, generator=g) < 0.5).to(torch.int64)
+    noise = dict(eps=torch.randn(n, 45, generator=g), eps_k=torch.randn(K, n, 45, generator=g),
+                 U_y=torch.rand(n, 18, generator=g), U1=torch.rand(18, 18, generator=g), U2=torch.rand(18, 18, generator=g))
+    sl = slice(rank * b_local, (rank + 1) * b_local)
+    shard = dict(eps=noise["eps"][sl], eps_k=noise["eps_k"][:, sl], U_y=noise["U_y"][sl], U1=noise["U1"], U2=noise["U2"])
+    c = dict(cfg, lr=1e-3, batch_size=n)
+    mk = lambda ex: G.Learner((64, 64, 3), 45, 18, 18, 1000, 1.0, c, device=dev, precision="fp32", seed=1, dp_exchange=ex)
+    dpl, ref = mk(exchange), mk("nccl")
+    ref._dist, ref.world, ref.rank = None, 1, 0
+    out = {"ranks": world, "exchange": "peer" if dpl._peer is not None else "nccl", "batch_per_rank": b_local}
+    for sup in (True, False):
+        l1, _ = dpl.train_step(x[sl], y[sl] if sup else None, sup, noise=shard, k=K)
+        l0, _ = ref.train_step(x, y if sup else None, sup, noise=noise, k=K)
+        out["loss_rel_diff_sup" if sup else "loss_rel_diff_unsup"] = abs(float(l1) - float(l0)) / abs(float(l0))
+    t = torch.stack([((dpl.store.flat - ref.store.flat).abs() > 2e-5).float().mean(),
+                     (dpl.store.flat - ref.store.flat).abs().max()])
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    out["params_differing_frac"], out["params_max_abs_diff"] = float(t[0]), float(t[1])
+    out["ok"] = bool(out["params_differing_frac"] < 0.01 and max(out["loss_rel_diff_sup"], out["loss_rel_diff_unsup"]) < 1e-5)
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
 # our arm
 # ---------------------------------------------------------------------------------------------------
 def run_ours(args, rank, world, local_rank):
@@ -184,7 +221,8 @@ def run_ours(args, rank, world, local_rank):
     U = max(0, args.unsup_per_sup)
     imgs_per_step = (1 + U) * B
     lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234,
-                    graphs=not args.no_graph)
+                    graphs=not args.no_graph, dp_exchange=args.dp_exchange)
+    dp_check = dp_equivalence_check(G, cfg, dev, rank, world, args.dp_exchange) if world > 1 else None
 
     # synthetic data: a ring of NBUF different batches (> L2 in total) resident in HBM for `value`,
     # and the same ring in pinned host memory for `e2e`
@@ -310,12 +348,17 @@ def run_ours(args, rank, world, local_rank):
                              "reference loader does on the host (utils_data.py:57-59); `e2e_alt`: HOST fp32 batches "
                              "(the reference API's dtype, 4x the PCIe bytes)",
                    "l2": "ring of 4 input batches (201 MB) + ~1 GB of activations per step exceed the 126 MB L2",
-                   "parallelism": "dp{}".format(world)},
+                   "parallelism": "dp{}".format(world),
+                   "dp_exchange": (None if world == 1 else
+                                   ("two-shot all-reduce + Adam in one kernel over NVLink peer memory, inside the step's graph"
+                                    if lrn._peer is not None else "NCCL all-reduce between graph replay and Adam"))},
         "e2e": e2e[head],
         "e2e_alt": e2e[alt[0]] if alt else None,
         "gpu_launches": int(launches),
         "clocks": clocks,
     }
+    if dp_check is not None:
+        line["dp_check"] = dp_check
     if roof is not None:
         pk = peaks.get("hbm_gbs") if roof["bound"] == "hbm" else peaks.get("bf16_tflops_sustained")
         src = "measured"

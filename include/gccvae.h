@@ -385,6 +385,40 @@ int gccvae_adam_fused_f32(float* param, float* grad, float* m, float* v, long lo
                           const float* result_loss, const float* result_c, float* result_ring, int ring_slots,
                           void* stream);
 
+/* Data parallel: two-shot all-reduce (sum over the ranks of one node) of grad[i0..n) over NVLink peer memory, fused with
+ * the same Adam update as gccvae_adam_fused_f32 on the result (csrc/dp.cu).  grad[q] / sync[q] are rank q's gradient
+ * buffer and its block of GCCVAE_DP_SYNC_WORDS zero-initialised 32-bit words, both in memory every rank of the node
+ * can address (torch.distributed._symmetric_memory); every rank must issue the same sequence of calls.  loss_index >= 0:
+ * grad[q][loss_index] is summed over the ranks too (into this rank's slot and, with publish, into the result ring).
+ * The range bounds i0, n, n_zero must be multiples of 4 elements. */
+#define GCCVAE_DP_MAX_RANKS 16
+#define GCCVAE_DP_SYNC_WORDS 32
+typedef struct {
+  int world, rank;
+  float* grad[GCCVAE_DP_MAX_RANKS];
+  void* sync[GCCVAE_DP_MAX_RANKS];
+  float* param;
+  float* m;
+  float* v;
+  long long i0, n, n_zero;
+  long long loss_index;
+  float lr, beta1, beta2, eps;
+  int* step_state;
+  int publish;
+  int ring_slots;
+  const float* result_loss;
+  const float* result_c;
+  float* result_ring;
+  /* push != 0: the one-barrier variant for a short range - every rank pushes grad[i0..n) (+ the loss) into slot `rank`
+   * of every rank's receive buffer recv[q] (world slots of recv_stride >= n - i0 + 4 floats each, peer-addressable like
+   * grad) and sums its own slots after the barrier.  Between two push calls every rank must issue a two-barrier call. */
+  int push;
+  int pad_;
+  long long recv_stride;
+  float* recv[GCCVAE_DP_MAX_RANKS];
+} gccvae_dp_args;
+int gccvae_dp_reduce_adam_f32(const gccvae_dp_args* a, void* stream);
+
 /* loss[0] = sum_b(-elbo_b)/batch_global (+ gating_reg*mean|mu| when mu != NULL): the forward-only
  * value of sup_loss / unsup_loss (gated_ccvae.py:225-230, 291-298). */
 int gccvae_elbo_loss_f32(const float* terms, const float* log_pxz, int batch, int batch_global,

@@ -1,9 +1,14 @@
-"""2-GPU check (run under torchrun, 2 ranks) of the data-parallel train_step on real devices:
+"""Multi-GPU check (run under torchrun, 2 / 4 / 8 ranks) of the data-parallel train_step on real devices (SURVEY.md 8c
+item 9):
  (1) fp32 engine, explicit noise: loss, gate sample and every all-reduced gradient of the sharded step (batch 8 per
-     rank) equal those of ONE device on the whole batch of 16 - relative error <= 1e-4 per tensor (1e-5 on the loss);
- (2) bf16 engine, replayed graphs, Philox noise: after three sup+unsup step pairs both ranks hold bit-identical,
-     finite parameters (the gate sample and the reduced gradients are the same everywhere), and the step counter
-     advanced once per train_step.
+     rank) equal those of ONE device on the whole batch of 8 x world - relative error <= 1e-4 per tensor (1e-5 on the
+     loss);
+ (2) fp32 engine, explicit noise, both exchange paths ("peer": the fused barrier + two-shot all-reduce + Adam kernel over
+     NVLink peer memory, "nccl"): after a supervised and an unsupervised train_step the parameters equal those of ONE
+     device stepping on the whole batch, and the returned losses agree to 1e-5;
+ (3) bf16 engine, replayed graphs, Philox noise, both exchange paths: after three sup+unsup step pairs all ranks hold
+     bit-identical, finite parameters (the gate sample and the reduced gradients are the same everywhere), and the step
+     counter advanced once per train_step.
 Exit code 0 = pass."""
 import os
 import sys
@@ -19,13 +24,13 @@ import gccvae_b200 as G
 import gccvae_oracle as O
 
 rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-assert world == 2, "run with --nproc-per-node 2"
+assert world in (2, 4, 8), "run with --nproc-per-node 2, 4 or 8"
 torch.cuda.set_device(local)
 dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 mu0 = np.load(os.path.join(ROOT, "data", "gating_matrix_0.5.npy"))
 cfg = dict(gate_type="learnable", gate_subtype=None, mu_init=mu0, gating_reg=0.2, lr=1e-3, gating_init_temp=1.0,
-           batch_size=16, init_temp=0.1)
+           batch_size=8 * world, init_temp=0.1)
 BL, K = 8, 10
 p0 = O.init_params(0, trained_like=True)
 x, y, noise = O.make_inputs(world * BL, k=K)
@@ -57,23 +62,56 @@ for supervised in (True, False):
     if rank == 0:
         print("fp32 sharded step == whole-batch step (supervised=%s)" % supervised, flush=True)
 
-lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, device=dev, precision="bf16", graphs=True, seed=7)
-xs = torch.randint(0, 256, (64, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(rank)).pin_memory()
-ys = (torch.rand(64, 18, generator=torch.Generator().manual_seed(10 + rank)) < 0.5).long().pin_memory()
-for i in range(3):
-    lrn.train_step(xs, ys, True)
-    lrn.train_step(xs, None, False)
-torch.cuda.synchronize()
-mine = lrn.store.flat.clone()
-other = mine.clone()
-dist.broadcast(other, src=0)
-same = bool(torch.equal(mine, other)) and bool(torch.isfinite(mine).all())
-its = lrn.optimiser.iterations
-if not same or its != 6:
-    print("rank %d: graphed DP steps: identical=%s iterations=%d" % (rank, same, its), flush=True)
-    ok = False
-elif rank == 0:
-    print("bf16 graphed DP steps: parameters bit-identical on both ranks, iterations = 6", flush=True)
+for mode in ("peer", "nccl"):
+    # ---- (2) train_step: exchange + Adam against one device on the whole batch --------------------------------------------
+    dp_l = G.Learner((64, 64, 3), 45, 18, 18, 1000, 1.0, cfg, device=dev, precision="fp32", dp_exchange=mode)
+    dp_l.store.load_dict(p0)
+    ref = G.Learner((64, 64, 3), 45, 18, 18, 1000, 1.0, cfg, device=dev, precision="fp32", dp_exchange="nccl")
+    ref._dist, ref.world, ref.rank = None, 1, 0
+    ref.store.load_dict(p0)
+    active = "peer" if dp_l._peer is not None else "nccl"
+    for supervised in (True, False):
+        l_dp, c_dp = dp_l.train_step(x[sl], y[sl] if supervised else None, supervised, noise=shard_noise, k=K)
+        l_ref, c_ref = ref.train_step(x, y if supervised else None, supervised, noise=noise, k=K)
+        torch.cuda.synchronize()
+        # (mu is learnable: after the first update the two runs' mu - and so their c - agree to rounding, not bit for bit)
+        if abs(float(l_dp) - float(l_ref)) > 1e-5 * abs(float(l_ref)) or float((c_dp - c_ref).abs().max()) > 1e-6:
+            print("rank %d [%s] train_step sup=%s: loss %.6f vs %.6f" % (rank, active, supervised, float(l_dp), float(l_ref)), flush=True)
+            ok = False
+    d = (dp_l.store.flat - ref.store.flat).abs()
+    # Adam's first steps move every parameter by ~lr = 1e-3 whatever the gradient's size: entries whose gradient is at the
+    # level of the fp32 summation noise may differ by O(lr), all others agree to ~1e-8
+    frac = float((d > 2e-5).float().mean())
+    if frac > 0.01 or dp_l.optimiser.iterations != 2 or float(dp_l.store.grad.abs().max()) != 0.0:
+        print("rank %d [%s] train_step: %.4f of the parameters differ, iterations %d, grad max %g" % (
+            rank, active, frac, dp_l.optimiser.iterations, float(dp_l.store.grad.abs().max())), flush=True)
+        ok = False
+    elif rank == 0:
+        print("fp32 DP train_step == whole-batch train_step (exchange requested %s, active %s; %.5f of the parameters differ by > 2e-5)" % (
+            mode, active, frac), flush=True)
+    # ---- (3) replayed bf16 graphs ----------------------------------------------------------------------------------------
+    lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, device=dev, precision="bf16", graphs=True, seed=7, dp_exchange=mode)
+    xs = torch.randint(0, 256, (64, 64, 64, 3), dtype=torch.uint8, generator=torch.Generator().manual_seed(rank)).pin_memory()
+    ys = (torch.rand(64, 18, generator=torch.Generator().manual_seed(10 + rank)) < 0.5).long().pin_memory()
+    losses = []
+    for i in range(3):
+        losses.append(lrn.train_step(xs, ys, True)[0])
+        losses.append(lrn.train_step(xs, None, False)[0])
+    torch.cuda.synchronize()
+    mine = lrn.store.flat.clone()
+    other = mine.clone()
+    dist.broadcast(other, src=0)
+    lv = torch.stack([v.clone() for v in losses])
+    lv0 = lv.clone()
+    dist.broadcast(lv0, src=0)
+    same = bool(torch.equal(mine, other)) and bool(torch.isfinite(mine).all()) and bool(torch.equal(lv, lv0))
+    its = lrn.optimiser.iterations
+    if not same or its != 6:
+        print("rank %d [%s]: graphed DP steps: identical=%s iterations=%d" % (rank, mode, same, its), flush=True)
+        ok = False
+    elif rank == 0:
+        print("bf16 graphed DP steps (exchange %s): parameters and losses bit-identical on all %d ranks, iterations = 6, losses %s" % (
+            "peer" if lrn._peer is not None else "nccl", world, [round(float(v), 3) for v in lv]), flush=True)
 flag = torch.tensor([0 if ok else 1], device=dev)
 dist.all_reduce(flag)
 dist.destroy_process_group()

@@ -76,6 +76,21 @@ class ChainBwdArgs(C.Structure):
     ]
 
 
+DP_MAX_RANKS, DP_SYNC_WORDS = 16, 32
+
+
+class DpArgs(C.Structure):
+    """gccvae_dp_args (include/gccvae.h)."""
+    _fields_ = [
+        ("world", C.c_int), ("rank", C.c_int), ("grad", C.c_void_p * DP_MAX_RANKS), ("sync", C.c_void_p * DP_MAX_RANKS),
+        ("param", C.c_void_p), ("m", C.c_void_p), ("v", C.c_void_p), ("i0", C.c_longlong), ("n", C.c_longlong),
+        ("n_zero", C.c_longlong), ("loss_index", C.c_longlong), ("lr", C.c_float), ("beta1", C.c_float),
+        ("beta2", C.c_float), ("eps", C.c_float), ("step_state", C.c_void_p), ("publish", C.c_int),
+        ("ring_slots", C.c_int), ("result_loss", C.c_void_p), ("result_c", C.c_void_p), ("result_ring", C.c_void_p),
+        ("push", C.c_int), ("pad_", C.c_int), ("recv_stride", C.c_longlong), ("recv", C.c_void_p * DP_MAX_RANKS),
+    ]
+
+
 class PackJob(C.Structure):
     _fields_ = [("kind", C.c_int), ("taps", C.c_int), ("CL", C.c_int), ("CS", C.c_int), ("W", C.c_void_p),
                 ("out", C.c_void_p), ("sr", C.c_int), ("sk", C.c_int), ("ld_out", C.c_int), ("row_off", C.c_int),
@@ -147,6 +162,7 @@ SIGNATURES = {
     "gccvae_recon_f32": (_I, [_P, _P, _I, _I, _P, _P, _P, _P]),
     "gccvae_adam_f32": (_I, [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _I, _P, _P]),
     "gccvae_adam_fused_f32": (_I, [_P, _P, _P, _P, _LL, _LL, _LL, _F, _F, _F, _F, _P, _I, _P, _P, _P, _I, _P]),
+    "gccvae_dp_reduce_adam_f32": (_I, [C.POINTER(DpArgs), _P]),
     "gccvae_elbo_loss_f32": (_I, [_P, _P, _I, _I, _I, _P, _F, _P, _P]),
     "gccvae_draw_noise_f32": (_I, [_I, _U64, _U64, _I, _I, _P, _P]),
     "gccvae_head_act_f32": (_I, [_P, _P, _LL, _P, _P, _P]),

@@ -114,6 +114,7 @@ class EngineTC(Engine):
         # called once per backward pass when every gradient except the first layer's is complete or queued: the
         # Learner hangs the bulk of the Adam update here, so that only the first layer's update follows the last dgrad
         self.tail_hook = None
+        self.tail_hook_layer = TC_ENC[0]   # ... called when THIS layer's weight gradient has been issued (its dgrad follows)
         self.side3 = None          # its own stream: the first layer's weight / bias gradients must not queue behind it
         self._side3_used = False
         # debug timeline (GCCVAE_MARKERS=1: a globaltimer marker kernel after every op, 2: only at segment ends)
@@ -235,7 +236,8 @@ class EngineTC(Engine):
         if self.mark_buf is None or (self.mark_level == 2 and not coarse) or len(self.marks) >= 1024:
             return
         st = torch.cuda.current_stream()
-        lane = "main" if (st != self.side and st != self.side2) else ("side" if st == self.side else "side2")
+        lane = ("side" if st == self.side else "side2" if st == self.side2 else
+                "side3" if (self.side3 is not None and st == self.side3) else "main")
         _lib.check(self.lib.gccvae_debug_mark(ptr(self.mark_buf), len(self.marks), _stream()), "mark")
         self.marks.append((what, lane))
 
@@ -569,7 +571,7 @@ class EngineTC(Engine):
                     self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
                         C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
             self._side(wg)
-            hook = self.tail_hook if name == TC_ENC[0] else None
+            hook = self.tail_hook if name == self.tail_hook_layer else None
             ev = None
             if hook is not None and self.side is not None and self.side2 is not None:
                 ev = torch.cuda.Event()

@@ -28,8 +28,8 @@ import numpy as np
 import torch
 
 from . import _lib, dp
-from ._lib import (GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, RESULT_SLOT_FLOATS, ChainBwdArgs, ChainFwdArgs, LatentBwdArgs,
-                   LatentFwdArgs, ptr)
+from ._lib import (GATE_WS_FLOATS, LATENT_PARTIAL_FLOATS, RESULT_SLOT_FLOATS, ChainBwdArgs, ChainFwdArgs, DpArgs,
+                   LatentBwdArgs, LatentFwdArgs, ptr)
 from .engine import Engine, _stream
 from .networks import Classifier, Conditional_Prior, Decoder, Encoder, _default_device, as_device_f32
 from .params import ParamStore, keras_default_init
@@ -160,7 +160,8 @@ class Learner:
     """gated_ccvae.py:114-311, 421-455."""
 
     def __init__(self, ip_shape, z_dim, z_classify, y_dim, num_samples, supervision, train_config, device=None,
-                 precision="fp32", seed=1234, init_seed=0, graphs=False, adam_tail=True, engine_options=None):
+                 precision="fp32", seed=1234, init_seed=0, graphs=False, adam_tail=True, engine_options=None,
+                 dp_exchange="peer"):
         if tuple(ip_shape) != (64, 64, 3):
             raise ValueError("the kernels are specialised for 64x64x3 inputs (gated_ccvae.py:481)")
         self.train_config = train_config
@@ -186,7 +187,8 @@ class Learner:
         self._grads_clean = False        # True right after apply_gradients (it clears the gradient buffer)
         # single GPU, tensor-core engine: Adam runs in two parts - everything but the first layer's parameters as soon
         # as their gradients are complete (on a side stream, under the last dgrad), the first layer at the very end
-        self._adam_cut = self.store.offsets["enc.conv2.w"][0]
+        self._tail_layer = "enc.conv2"       # the head part starts when this layer's weight gradient has been issued
+        self._adam_cut = self.store.offsets[self._tail_layer + ".w"][0]
         self._adam_head_done = False
         self.adam_tail = bool(adam_tail)
         # what train_step returns: the publishing Adam launch copies (loss, c) into slot (t - 1) % RING of this ring, so
@@ -204,6 +206,50 @@ class Learner:
         # data parallel
         self._dist = dp.dist_or_none()
         self.world, self.rank = dp.world_and_rank(self._dist)
+        # gradient exchange: "peer" = two-shot all-reduce over NVLink peer memory fused with Adam (one kernel, inside
+        # the step's graph); "nccl" = NCCL all-reduce between the replayed graph and the optimiser.  "peer" falls back
+        # to "nccl" where symmetric memory cannot be set up (collectively: every rank takes the same path).
+        if dp_exchange not in ("peer", "nccl"):
+            raise ValueError("dp_exchange must be 'peer' or 'nccl', got {!r}".format(dp_exchange))
+        self._peer = None
+        if self.world > 1 and dp_exchange == "peer" and self.device.type == "cuda":
+            # the bulk of the exchange (barrier, 4 MB over NVLink, barrier, Adam: ~45 us) needs more room than the last
+            # dgrad gives it: it starts one layer earlier and leaves the first TWO layers' gradients to the closing call
+            self._tail_layer = "enc.conv3"
+            self._adam_cut = self.store.offsets[self._tail_layer + ".w"][0]
+            self._peer = self._setup_peer_exchange()
+            if self._peer is None:
+                self._tail_layer = "enc.conv2"
+                self._adam_cut = self.store.offsets[self._tail_layer + ".w"][0]
+
+    def _setup_peer_exchange(self):
+        peer, err = None, None
+        try:
+            peer = dp.PeerExchange(self._dist, self.store.total + 4, self.device, push_floats=self._adam_cut)
+        except Exception as e:      # noqa: BLE001 - whatever goes wrong, the NCCL path still works
+            err = e
+        flag = torch.tensor([0 if peer is not None else 1], device=self.device)
+        self._dist.all_reduce(flag)
+        if int(flag.item()) != 0:
+            if self.rank == 0:
+                logger.warning("peer-memory gradient exchange unavailable (%s): using the NCCL all-reduce", err)
+            return None
+        self.store.adopt_grad_buffer(peer.grad)
+        return peer
+
+    def _peer_adam(self, lo, hi, zero_hi, publish, push=False):
+        """rank barrier + two-shot all-reduce of grad[lo:hi) + Adam on it, one launch (csrc/dp.cu); `push`: the
+        one-barrier variant for the short range that closes the step."""
+        a, opt = self._peer.fill_args(DpArgs()), self.optimiser
+        a.push = int(bool(push))
+        a.param, a.m, a.v = ptr(self.store.flat), ptr(opt.m), ptr(opt.v)
+        a.i0, a.n, a.n_zero = int(lo), int(hi), int(zero_hi)
+        a.loss_index = self.store.total if publish else -1
+        a.lr, a.beta1, a.beta2, a.eps = opt.lr, opt.beta_1, opt.beta_2, opt.epsilon
+        a.step_state, a.publish = ptr(opt.step_dev), int(bool(publish))
+        a.ring_slots, a.result_loss, a.result_c = self.RING, None, ptr(self._c)
+        a.result_ring = ptr(self._ring) if publish else None
+        _lib.check(self.lib.gccvae_dp_reduce_adam_f32(C.byref(a), _stream()), "dp_reduce_adam")
 
     # ---- buffers of the latent stage -------------------------------------------------------------------
     def _latent_bufs(self, B):
@@ -456,7 +502,11 @@ class Learner:
         return slot[0], slot[1:1 + 324].view(18, 18)
 
     def _adam_head(self):
-        self.optimiser.apply_gradients(lo=self._adam_cut, hi=None, publish=False)
+        if self._peer is not None:
+            self._peer_adam(self._adam_cut, self.n_trainable, self.store.total, publish=False)
+        else:
+            self.optimiser.apply_gradients(lo=self._adam_cut, hi=None, publish=False)
+        getattr(self.engine, "mark", lambda *a, **k: None)("adam head", coarse=True)
         self._adam_head_done = True
 
     def _result(self):
@@ -464,14 +514,20 @@ class Learner:
 
     def _step_body(self, x, y, supervised, noise, k):
         """forward + backward + (all-reduce) + Adam, as issued eagerly or captured into the step's graph."""
-        split = self.world == 1 and hasattr(self.engine, "tail_hook") and self.adam_tail
+        split = (self.world == 1 or self._peer is not None) and hasattr(self.engine, "tail_hook") and self.adam_tail
         self._adam_head_done = False
         if split:
-            self.engine.tail_hook = self._adam_head
+            self.engine.tail_hook, self.engine.tail_hook_layer = self._adam_head, self._tail_layer
         loss, c = self._elbo(x, y, supervised, noise, backward=True, k=k)
         if split:
             self.engine.tail_hook = None
-        if self._adam_head_done:
+        if self._peer is not None:
+            if self._adam_head_done:
+                self._peer_adam(0, self._adam_cut, self._adam_cut, publish=True, push=True)
+            else:
+                self._peer_adam(0, self.n_trainable, self.store.total, publish=True)
+            self._grads_clean = True
+        elif self._adam_head_done:
             self._grads_clean = self.optimiser.apply_gradients(lo=0, hi=self._adam_cut, publish=True,
                                                                result=self._result())
         else:
@@ -519,7 +575,7 @@ class Learner:
             self.engine.zero_grads()   # the graph was captured without a memset: it relies on the previous Adam launch
         g["graph"].replay()
         self.lib.gccvae_add_launch_count(g["launches"])
-        if self.world > 1:     # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
+        if self.world > 1 and self._peer is None:   # NCCL stays outside the graph: replay(fwd+bwd) -> all-reduce -> Adam
             self._allreduce_grads()
             self._grads_clean = self.optimiser.apply_gradients(result=self._result())
         else:
@@ -540,7 +596,7 @@ class Learner:
         def body():
             if getattr(self.engine, "marks", None) is not None:
                 self.engine.marks = []
-            if self.world == 1:
+            if self.world == 1 or self._peer is not None:   # the whole step, exchange + optimiser included, is one graph
                 loss, _ = self._step_body(xs, ys, supervised, None, k)
                 getattr(self.engine, "mark", lambda *a, **k: None)("adam", coarse=True)
             else:       # NCCL stays outside the graph: the all-reduce and Adam follow the replay

@@ -58,6 +58,16 @@ class ParamStore:
         # mu sits last so that "all but mu" is one contiguous prefix (frozen-mu modes)
         self.n_without_mu = self.offsets["mu"][0]
 
+    def adopt_grad_buffer(self, buf):
+        """use `buf` (>= total + 4 floats, e.g. a symmetric-memory allocation the other ranks of the node can address)
+        as the gradient buffer.  Must happen before any kernel pointer into the old buffer is captured."""
+        if buf.numel() < self.total + 4 or buf.dtype != torch.float32 or buf.device != self.device:
+            raise ValueError("gradient buffer must be {} fp32 elements on {}".format(self.total + 4, self.device))
+        buf.zero_()
+        self.grad_full = buf
+        self.grad = self.grad_full[: self.total]
+        self.loss_slot = self.grad_full[self.total: self.total + 1]
+
     def view(self, name, buf=None):
         off, n, shape = self.offsets[name]
         return (self.flat if buf is None else buf)[off:off + n].view(shape)

@@ -1,4 +1,5 @@
-"""Data-parallel train_step on two real GPUs (skipped on a one-GPU box): scripts/dp_equivalence_gpu.py under torchrun."""
+"""Data-parallel train_step on real GPUs (skipped where the box has fewer): scripts/dp_equivalence_gpu.py under torchrun
+with 2, 4 and 8 ranks."""
 import os
 import subprocess
 import sys
@@ -10,9 +11,11 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_gpu_step_equals_whole_batch_step():
-    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr",
-           "127.0.0.1", "--master-port", "29541", os.path.join(ROOT, "scripts", "dp_equivalence_gpu.py")]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_sharded_step_equals_whole_batch_step(world):
+    if torch.cuda.device_count() < world:
+        pytest.skip("needs {} GPUs".format(world))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+           "127.0.0.1", "--master-port", str(29541 + world), os.path.join(ROOT, "scripts", "dp_equivalence_gpu.py")]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
