@@ -57,6 +57,8 @@ def parse():
     ap.add_argument("--dp-exchange", default="peer", choices=["peer", "nccl"],
                     help="gradient exchange of the data-parallel step: fused two-shot all-reduce + Adam over NVLink peer "
                          "memory (csrc/dp.cu) or NCCL all-reduce")
+    ap.add_argument("--engine-options", default="", help="A/B runs: comma-separated key=value options of the bf16 engine "
+                                                          "(fused_chain, wgrad_streams, post_chain_stream)")
     ap.add_argument("--e2e-input", default="uint8", choices=["uint8", "fp32"],
                     help="host image dtype of the headline e2e run (the other one is reported as e2e_alt)")
     args = ap.parse_args()
@@ -220,8 +222,12 @@ def run_ours(args, rank, world, local_rank):
     cfg = train_cfg(args.gate, args.frac)
     U = max(0, args.unsup_per_sup)
     imgs_per_step = (1 + U) * B
+    eopts = {}
+    for kv in filter(None, (args.engine_options or os.environ.get("GCCVAE_BENCH_ENGINE_OPTIONS", "")).replace(":", ",").split(",")):
+        k_, v_ = kv.split("=")
+        eopts[k_] = int(v_) if v_.lstrip("-").isdigit() else v_
     lrn = G.Learner((64, 64, 3), 45, 18, 18, 162770, 0.2, cfg, device=dev, precision=precision, seed=1234,
-                    graphs=not args.no_graph, dp_exchange=args.dp_exchange)
+                    graphs=not args.no_graph, dp_exchange=args.dp_exchange, engine_options=eopts or None)
     dp_check = dp_equivalence_check(G, cfg, dev, rank, world, args.dp_exchange) if world > 1 else None
 
     # synthetic data: a ring of NBUF different batches (> L2 in total) resident in HBM for `value`,

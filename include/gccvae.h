@@ -114,13 +114,6 @@ int gccvae_ls_bf16(const gccvae_geom* g, const void* L, const void* Wp_ls, const
                    const void* mask, void* S, int out_f32, void* stream);
 int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl, const float* bias, int act,
                    const void* mask, void* L, int out_f32, void* stream);
-/* Arms the NEXT gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_gemm_bf16 call of this thread: it additionally does
- * colsum[c % mod] += sum over rows of the values it stores, for channels c < n (mod <= 0: no wrap).  This is the
- * bias gradient of the layer whose pre-activation gradient the dgrad produces, fused into its epilogue.
- * With mod = -1 / -2 it arms the next gccvae_wg_bf16 / gccvae_wg_c4_bf16 / gccvae_gemm_tn_bf16 instead: the
- * column sums of its S operand (-1: Conv2D / Dense, dout = S) or of the own-pixel taps of its L operand
- * (-2: Conv2DTranspose, dout = L) are accumulated by the otherwise idle epilogue warps during the main loop. */
-void gccvae_next_launch_colsum(float* colsum, int n, int mod);
 /* dW (fp32, Keras [kh,kw,cl,cs]) += gather(L)^T S; out[c] += column sums.  Accumulating: zero first. */
 int gccvae_wg_bf16(const gccvae_geom* g, const void* L, const void* S, float* dW, void* stream);
 /* out[c] += column sums of a bf16 [rows, cols] tensor for c < n_valid (0 = all) */
@@ -137,13 +130,6 @@ int gccvae_gemm_bf16(long long rows, int K, int N, const void* A, const void* Wp
                      int bias_mod, int act, const void* mask, void* out, int out_f32, void* stream);
 int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, const void* B, const gccvae_wg_out* out,
                         void* stream);
-/* 3-channel end layers (conv1 input, conv5t output) go through a K=64 im2col matrix
- * M64[(n,oh,ow),(kh,kw,c4)] (bf16, 128-byte rows) so that they are dense tcgen05 GEMMs too. */
-int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* stream);
-int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, const float* coef, float* log_pxz,
-                             void* G64, float* db, void* stream);
-int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream);
-int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream);
 /* s2d storage of the stride-2 layers' L tensors (an H x W x C plane as (H/2+1) x (W/2+1) blocks of 2x2 pixels, block
  * (i,j) = pixels (2i-1+dy, 2j-1+dx) in slot dy*2+dx, zero outside): Conv2D(k4,s2,p1) forward, Conv2DTranspose dgrad and
  * their weight gradients gather 2x2 blocks of 4C channels (gccvae_tap4_ls_bf16 / gccvae_wg_s2d_bf16, weights packed
@@ -181,16 +167,6 @@ int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const void* Wp_sl9,
                         const void* mask, void* L, int out_f32, void* stream);
 int gccvae_cast_f32_to_bf16(const float* in, long long n, void* out, void* stream);
 int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* stream);
-/* debug aid: while set (device buffer of 32*8 int64), block 0 of every tap-GEMM launch records clock64()
- * at its pipeline events: [item][0 slot free,1 TMA issued,2 TMEM free,3 operands landed,4 accum ready,
- * 5 accum read,6 stored]. */
-void gccvae_debug_set_timeline(long long* dev_buf);
-/* debug: a 1-thread kernel that stores %globaltimer (ns) into buf[idx] when the stream reaches it */
-int gccvae_debug_mark(long long* buf, int idx, void* stream);
-
-/* debug aid: one 4-D TMA box load of a bf16 NHWC tensor, raw shared-memory image copied to `out`. */
-int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
-                       int c0, int c1, int c2, int c3, void* out, int out_bytes, void* stream);
 
 /* ---- gate (gated_ccvae.py:62-64,102-111; networks.py:72-74,83-86,104-106,118-127) ------------
  * One relaxed-Bernoulli sample c[18,18] per step from mu, shared by the batch and by all K

@@ -1,9 +1,8 @@
-"""In-graph timeline of one supervised train_step: GCCVAE_MARKERS=1 (marker after every op) or 2 (segments).
+"""In-graph timeline of one supervised train_step: TIMELINE_MARKERS=1 (marker after every op, default) or 2 (segments).
 Marker kernels carry no PDL attribute, so they serialise the stream: compare segment sums, not absolute totals."""
 import os
 import sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-os.environ.setdefault("GCCVAE_MARKERS", "1")
 import numpy as np
 import torch
 import gccvae_b200 as G
@@ -20,7 +19,8 @@ mu = np.load(os.path.join(ROOT, "data", "gating_matrix_0.2.npy"))
 cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=0.3,
            batch_size=B, init_temp=0.1)
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True,
-                dp_exchange=os.environ.get("TIMELINE_DP_EXCHANGE", "peer"))
+                dp_exchange=os.environ.get("TIMELINE_DP_EXCHANGE", "peer"),
+                engine_options=dict(markers=int(os.environ.get("TIMELINE_MARKERS", "1"))))
 x = torch.rand(B, 64, 64, 3, device="cuda")
 y = (torch.rand(B, 18, device="cuda") < 0.5).long()
 for sup in (True, False):

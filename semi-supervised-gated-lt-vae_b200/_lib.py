@@ -131,15 +131,10 @@ SIGNATURES = {
     "gccvae_colsum_bf16": (_I, [_P, _LL, _I, _I, _P, _P]),
     "gccvae_gemm_bf16": (_I, [_LL, _I, _I, _P, _P, _P, _I, _I, _I, _P, _P, _I, _P]),
     "gccvae_gemm_tn_bf16": (_I, [_LL, _I, _I, _P, _P, C.POINTER(WgOut), _P]),
-    "gccvae_im2col_x_bf16": (_I, [_P, _I, _P, _P]),
-    "gccvae_recon_im2col_bf16": (_I, [_P, _P, _I, _P, _P, _P, _P, _P]),
-    "gccvae_pack_c4_bf16": (_I, [_P, _I, _P, _P]),
-    "gccvae_wg_c4_bf16": (_I, [_LL, _P, _P, _I, _P, _P]),
     "gccvae_sl_halo_supported": (_I, [_G]),
     "gccvae_sl_halo_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
     "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
-    "gccvae_next_launch_colsum": (None, [_P, _I, _I]),
     "gccvae_prep_x2_bf16": (_I, [_P, _I, _I, _P, _P]),
     "gccvae_tap4_ls_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_c3conv_bf16": (_I, [_I, _P, _P, _I, _P, _I, _P, _P, _P]),
@@ -147,9 +142,6 @@ SIGNATURES = {
     "gccvae_tap4_wg_bf16": (_I, [_I, _P, _P, _I, _P, _P]),
     "gccvae_convt_recon_bf16": (_I, [_I, _P, _P, _P, _P, _I, _P, _P, _P, _P, _P, _I, _P]),
     "gccvae_fill_f32": (_I, [_P, _LL, _F, _P]),
-    "gccvae_debug_set_timeline": (None, [_P]),
-    "gccvae_debug_mark": (_I, [_P, _I, _P]),
-    "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),
     "gccvae_gate_fwd": (_I, [_P, _P, _P, _P, _U64, _U64, _P, _F, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_latent_fwd": (_I, [C.POINTER(LatentFwdArgs), _P]),
     "gccvae_latent_bwd_partials": (_I, [_I]),
@@ -170,6 +162,14 @@ SIGNATURES = {
     "gccvae_classifier_tiled_f32": (_I, [_P, _LL, _LL, _LL, _I, _P, _P, _P, _P, _P]),
     "gccvae_cond_prior_tiled_f32": (_I, [_P, _LL, _LL, _LL, _I, _P, _P, _P, _P, _P, _P, _P, _P]),
     "gccvae_gaussian_kl_f32": (_I, [_P, _P, _P, _P, _I, _I, _P, _P]),
+}
+
+
+# development aids (include/gccvae_debug.h): not part of the drop-in boundary
+DEBUG_SIGNATURES = {
+    "gccvae_debug_set_timeline": (None, [_P]),
+    "gccvae_debug_mark": (_I, [_P, _I, _P]),
+    "gccvae_debug_tma4d": (_I, [_P] + [_I] * 13 + [_P, _I, _P]),
 }
 
 
@@ -195,7 +195,7 @@ def load():
         # binds it to the runtime torch has already mapped instead of bringing a second one into the process
         import torch  # noqa: F401
         lib = C.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
+        for name, (res, args) in list(SIGNATURES.items()) + list(DEBUG_SIGNATURES.items()):
             try:
                 fn = getattr(lib, name)
             except AttributeError as e:

@@ -5,6 +5,7 @@
 #include <stdio.h>
 
 #include "gccvae.h"
+#include "gccvae_debug.h"
 
 namespace gccvae {
 

@@ -1040,104 +1040,61 @@ __global__ void __launch_bounds__(256) colsum_bf16_kernel(const __nv_bfloat16* _
   }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// The two 3-channel end layers (conv1 input x, conv5t output xhat) cannot feed TMA directly (6-byte
-// pixels).  Both are turned into a K=64 im2col matrix  M64[(n,oh,ow), (kh,kw,c4)]  (c4 = 3 channels +
-// 1 zero; 128-byte rows = exactly one SWIZZLE_128B chunk) so that conv1 forward / wgrad and conv5t
-// dgrad / wgrad are plain dense tcgen05 GEMMs.  Pixel of tap (kh,kw): (2*oh-1+kh, 2*ow-1+kw).
-// One thread per (row, tap): 16 consecutive threads write one 128-byte row.
-// ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256) im2col_x_kernel(const float* __restrict__ x, long long total,
-                                                       uint2* __restrict__ out) {
+// the same with 16-byte loads (8 columns per thread, 4 rows in flight): cols % 8 == 0, 256 % (cols / 8) == 0.  The 4-byte
+// loads of the kernel above reach ~3 TB/s on the two big tensors (75.8 MB: 25 us each); this one is HBM-bound.
+__global__ void __launch_bounds__(256) colsum_bf16_v8_kernel(const __nv_bfloat16* __restrict__ in, long long rows, int cols,
+                                                             int rows_per_cta, int n_valid, float* __restrict__ out) {
   pdl_launch_dependents();
   pdl_wait();
-  for (long long i = blockIdx.x * 256LL + threadIdx.x; i < total; i += (long long)gridDim.x * 256) {
-    const int t = (int)(i & 15);
-    const long long row = i >> 4;
-    const int ow = (int)(row & 31), oh = (int)((row >> 5) & 31);
-    const long long n = row >> 10;
-    const int ih = 2 * oh - 1 + (t >> 2), iw = 2 * ow - 1 + (t & 3);
-    uint2 v = make_uint2(0u, 0u);
-    if ((unsigned)ih < 64u && (unsigned)iw < 64u) {
-      const float* px = x + ((n * 64 + ih) * 64 + iw) * 3;
-      v.x = pack_bf16x2(__ldg(px), __ldg(px + 1));
-      v.y = pack_bf16x2(__ldg(px + 2), 0.0f);
+  const int cp = cols >> 3;
+  const int tc = threadIdx.x % cp, tr = threadIdx.x / cp, nr = 256 / cp;
+  const long long r0 = (long long)blockIdx.x * rows_per_cta;
+  long long r1 = r0 + rows_per_cta;
+  if (r1 > rows) r1 = rows;
+  float acc[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) acc[i] = 0.0f;
+  const uint4* base = reinterpret_cast<const uint4*>(in) + tc;
+  long long r = r0 + tr;
+  for (; r + 3LL * nr < r1; r += 4LL * nr) {
+    uint4 v[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) v[u] = __ldg(base + (r + (long long)u * nr) * cp);
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const uint32_t w[4] = {v[u].x, v[u].y, v[u].z, v[u].w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        acc[2 * i] += __uint_as_float(w[i] << 16);
+        acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+      }
     }
-    out[i] = v;
+  }
+  for (; r < r1; r += nr) {
+    const uint4 v = __ldg(base + r * cp);
+    const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      acc[2 * i] += __uint_as_float(w[i] << 16);
+      acc[2 * i + 1] += __uint_as_float(w[i] & 0xffff0000u);
+    }
+  }
+  __shared__ float red[256][9];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) red[threadIdx.x][i] = acc[i];
+  __syncthreads();
+  // thread t < cols sums column t over the nr row groups
+  if ((int)threadIdx.x < cols && (int)threadIdx.x < n_valid) {
+    const int c8 = threadIdx.x >> 3, ci = threadIdx.x & 7;
+    float tot = 0.0f;
+    for (int q = 0; q < nr; ++q) tot += red[q * cp + c8][ci];
+    atomicAdd(out + threadIdx.x, tot);
   }
 }
 
-// utils.py:101-105 fused with the im2col of its gradient.  One CTA = (image n, 4 output rows):
-//  phase 1: the 10 input rows it touches are read coalesced (x: 768 B/row, xhat4: 1 KB/row),
-//           dlogit = coef[n] * sign(x - xhat) * xhat (1 - xhat) goes to shared memory as bf16x4;
-//           the 8 rows the CTA owns add -|x - xhat| to log_pxz[n] and dlogit to db;
-//  phase 2: the 128 G64 rows (16 taps x 8 bytes each) are written fully coalesced from shared memory.
-__global__ void __launch_bounds__(256) recon_im2col_kernel(const float* __restrict__ x, const float4* __restrict__ xh4,
-                                                           const float* __restrict__ coef,
-                                                           float* __restrict__ log_pxz, uint2* __restrict__ G,
-                                                           float* __restrict__ db) {
-  pdl_launch_dependents();
-  pdl_wait();
-  __shared__ uint2 sD[10][66];   // [input row - (2*oh0-1)][input col + 1], zero border
-  __shared__ float red[8][4];
-  const int n = blockIdx.x >> 3, oh0 = (blockIdx.x & 7) * 4;
-  const int ih0 = 2 * oh0 - 1;
-  const float cb = coef ? __ldg(coef + n) : 0.0f;
-  float l1 = 0.0f, d0 = 0.0f, d1 = 0.0f, d2 = 0.0f;
-  if (threadIdx.x < 20) sD[threadIdx.x >> 1][(threadIdx.x & 1) * 65] = make_uint2(0u, 0u);
-  for (int i = threadIdx.x; i < 640; i += 256) {
-    const int r = i >> 6, col = i & 63;
-    const int ih = ih0 + r;
-    uint2 v = make_uint2(0u, 0u);
-    if ((unsigned)ih < 64u) {
-      const size_t pix = ((size_t)n * 64 + ih) * 64 + col;
-      const float* px = x + pix * 3;
-      const float4 rr = __ldg(xh4 + pix);
-      const float e0 = __ldg(px) - rr.x, e1 = __ldg(px + 1) - rr.y, e2 = __ldg(px + 2) - rr.z;
-      const float g0 = cb * ((e0 > 0.f) - (e0 < 0.f)) * rr.x * (1.0f - rr.x);
-      const float g1 = cb * ((e1 > 0.f) - (e1 < 0.f)) * rr.y * (1.0f - rr.y);
-      const float g2 = cb * ((e2 > 0.f) - (e2 < 0.f)) * rr.z * (1.0f - rr.z);
-      v.x = pack_bf16x2(g0, g1);
-      v.y = pack_bf16x2(g2, 0.0f);
-      if (r >= 1 && r <= 8) {  // rows 2*oh0 .. 2*oh0+7 belong to this CTA
-        l1 += fabsf(e0) + fabsf(e1) + fabsf(e2);
-        d0 += g0; d1 += g1; d2 += g2;
-      }
-    }
-    sD[r][col + 1] = v;
-  }
-  __syncthreads();
-  if (G != nullptr) {
-    uint2* gout = G + ((size_t)n * 1024 + (size_t)oh0 * 32) * 16;
-    for (int i = threadIdx.x; i < 2048; i += 256) {
-      const int t = i & 15, row = i >> 4;
-      const int ow = row & 31, dh = row >> 5;
-      gout[i] = sD[2 * dh + (t >> 2)][2 * ow + (t & 3)];
-    }
-  }
-  l1 = warp_sum(l1); d0 = warp_sum(d0); d1 = warp_sum(d1); d2 = warp_sum(d2);
-  const int w = threadIdx.x >> 5;
-  if ((threadIdx.x & 31) == 0) { red[w][0] = l1; red[w][1] = d0; red[w][2] = d1; red[w][3] = d2; }
-  __syncthreads();
-  if (threadIdx.x < 4) {
-    float tot = 0.0f;
-#pragma unroll
-    for (int q = 0; q < 8; ++q) tot += red[q][threadIdx.x];
-    if (threadIdx.x == 0) atomicAdd(log_pxz + n, -tot);
-    else if (db != nullptr) atomicAdd(db + (threadIdx.x - 1), tot);
-  }
-}
 __global__ void fill_kernel(float* __restrict__ p, int n, float v) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) p[i] = v;
-}
-
-// W[16 taps][3][CS] fp32 -> out[CS][(tap, c4)] bf16 (K = 64, pad channel zero)
-__global__ void pack_c4_kernel(const float* __restrict__ W, int CS, __nv_bfloat16* __restrict__ out) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= CS * 64) return;
-  const int cs = i / 64, k = i % 64, t = k >> 2, c = k & 3;
-  out[i] = __float2bfloat16(c < 3 ? W[(size_t)(t * 3 + c) * CS + cs] : 0.0f);
 }
 
 // all weight repacking of one step in ONE launch: blockIdx.y = job
@@ -1801,8 +1758,10 @@ __global__ void cast_f32_kernel(const __nv_bfloat16* __restrict__ in, long long 
 // ---------------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------------
-static thread_local float* g_colsum = nullptr;
-static thread_local int g_colsum_n = 0, g_colsum_mod = 0;
+// (the column-sum epilogues of the dgrad / wgrad kernels - bias gradients fused into the producing launch - were measured
+// slower than the separate bandwidth-bound pass on B200 and have no entry point any more; the kernels keep the hooks)
+static float* g_colsum = nullptr;
+static int g_colsum_n = 0, g_colsum_mod = 0;
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -2128,12 +2087,6 @@ extern "C" int gccvae_sl_bf16(const gccvae_geom* g, const void* S, const void* W
   return launch_tapgemm(p, groups, phases, (cudaStream_t)stream, "sl_bf16");
 }
 
-// The NEXT gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_gemm_bf16 launch on this thread also accumulates the column
-// sums of what it stores into colsum[(channel % mod)] for channel < n: the bias gradient of the layer whose
-// pre-activation gradient that dgrad produces, fused into the epilogue (no extra pass over the tensor).
-extern "C" void gccvae_next_launch_colsum(float* colsum, int n, int mod) {
-  g_colsum = colsum; g_colsum_n = n; g_colsum_mod = mod;
-}
 extern "C" void gccvae_debug_set_timeline(long long* dev_buf) { g_timeline = dev_buf; }
 
 extern "C" int gccvae_debug_tma4d(const void* src_bf16, int N, int H, int W, int C, int kc, int bw, int bh, int bn, int es,
@@ -2232,18 +2185,6 @@ extern "C" int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, 
   return wg_bf16_impl(&g, A, B, out, 0, stream);
 }
 
-// conv1 / conv5t weight gradient from the K=64 im2col matrix X64[rows, (tap, c4)]:
-// dW[(tap, c<3), cs] += X64^T S   (S = [rows, CS] bf16)
-extern "C" int gccvae_wg_c4_bf16(long long rows, const void* X64, const void* S, int CS, float* dW, void* stream) {
-  GCC_REQUIRE(rows > 0 && rows < (1LL << 31), "wg_c4: bad row count");
-  gccvae_geom g = {(int)rows, 1, 1, 64, 1, 1, CS, 1, 1, 1, 0};
-  gccvae_wg_out o;
-  memset(&o, 0, sizeof(o));
-  o.n_seg = 1; o.m_valid = 64;
-  o.seg[0].col0 = 0; o.seg[0].ncols = CS; o.seg[0].ld = CS; o.seg[0].dst = dW;
-  return wg_bf16_impl(&g, X64, S, &o, 1, stream);
-}
-
 // out[c] += sum_r in[r,c] for a bf16 [rows, cols] tensor (out fp32, pre-zeroed by the caller)
 extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int n_valid, float* out, void* stream) {
   GCC_REQUIRE(in && out && rows > 0 && cols > 0 && cols % 2 == 0 && cols <= 256 && (256 % (cols / 2)) == 0,
@@ -2255,8 +2196,12 @@ extern "C" int gccvae_colsum_bf16(const void* in, long long rows, int cols, int 
   if (ctas > 148 * 4) ctas = 148 * 4;
   const int rpc = (int)((rows + ctas - 1) / ctas);
   ctas = (rows + rpc - 1) / rpc;
-  GCC_CUDA(launch_pdl_k(colsum_bf16_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
-                        (const __nv_bfloat16*)in, rows, cols, rpc, n_valid, out));
+  if (cols % 8 == 0 && 256 % (cols / 8) == 0 && (uintptr_t)in % 16 == 0)
+    GCC_CUDA(launch_pdl_k(colsum_bf16_v8_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
+                          (const __nv_bfloat16*)in, rows, cols, rpc, n_valid, out));
+  else
+    GCC_CUDA(launch_pdl_k(colsum_bf16_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream,
+                          (const __nv_bfloat16*)in, rows, cols, rpc, n_valid, out));
   GCC_CHECK_LAUNCH("colsum_bf16");
   return GCCVAE_OK;
 }
@@ -2687,38 +2632,6 @@ extern "C" int gccvae_pack_weights_bf16(const gccvae_geom* g, const float* W, vo
       GCC_CHECK_LAUNCH("pack_sl2");
     }
   }
-  return GCCVAE_OK;
-}
-
-extern "C" int gccvae_im2col_x_bf16(const float* x, int batch, void* X64, void* stream) {
-  GCC_REQUIRE(x && X64 && batch > 0, "im2col_x: bad args");
-  const long long total = (long long)batch * 1024 * 16;
-  long long ctas = (total + 255) / 256;
-  if (ctas > 148 * 16) ctas = 148 * 16;
-  GCC_CUDA(launch_pdl_k(im2col_x_kernel, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, x, total, (uint2*)X64));
-  GCC_CHECK_LAUNCH("im2col_x");
-  return GCCVAE_OK;
-}
-
-// xhat4: decoder output as [B,64,64,4] fp32 (channel 3 = pad).  log_pxz[b] = -|x-xhat|_1 - 12288 ln2;
-// when coef != NULL also G64 = im2col(dLoss/dlogit) (bf16 [B*1024, 64]) and db[3] += sum dlogit.
-extern "C" int gccvae_recon_im2col_bf16(const float* x, const float* xhat4, int batch, const float* coef,
-                                        float* log_pxz, void* G64, float* db, void* stream) {
-  GCC_REQUIRE(x && xhat4 && log_pxz && batch > 0, "recon_im2col: bad args");
-  GCC_REQUIRE((coef == nullptr) == (G64 == nullptr), "recon_im2col: coef and G64 go together");
-  cudaStream_t st = (cudaStream_t)stream;
-  fill_kernel<<<(batch + 255) / 256, 256, 0, st>>>(log_pxz, batch, (float)(-12288.0 * 0.6931471805599453));
-  GCC_CHECK_LAUNCH("recon_fill");
-  GCC_CUDA(launch_pdl_k(recon_im2col_kernel, dim3(batch * 8), dim3(256), 0, st, x, (const float4*)xhat4, coef, log_pxz,
-                        (uint2*)G64, db));
-  GCC_CHECK_LAUNCH("recon_im2col");
-  return GCCVAE_OK;
-}
-
-extern "C" int gccvae_pack_c4_bf16(const float* W, int CS, void* out, void* stream) {
-  GCC_REQUIRE(W && out && CS > 0, "pack_c4: bad args");
-  pack_c4_kernel<<<(CS * 64 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(W, CS, (__nv_bfloat16*)out);
-  GCC_CHECK_LAUNCH("pack_c4");
   return GCCVAE_OK;
 }
 

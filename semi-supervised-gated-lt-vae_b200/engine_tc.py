@@ -12,9 +12,11 @@ of parameters are fp32.  Layer -> kernel map of the default (x2 + s2d) mode, DES
                    output gradient; wgrad = wg_s2d
   dec.conv5t       forward fused with sigmoid + Laplace log-likelihood + dLoss/dlogit in x2 block form (convt_recon);
                    dgrad = c3conv over those blocks, wgrad = tap4_wg
-Weight gradients run on a side stream, bias gradients (column sums) on a second one, the bulk of Adam on a third; packed
-bf16 weight operands are refreshed from the fp32 master parameters at the start of every step (one launch).
-GCCVAE_X2=0 / GCCVAE_S2D=0 select the older im2col / NHWC formulations (kept for A/B runs and as a cross-check).
+  enc.conv5 out .. dec.conv1t out   fused dense chain (csrc/chain.cu): heads, latent stage, fc1, conv1t and their backward,
+                   one launch each way
+Weight gradients run on two side streams, bias gradients (column sums) on a third, the bulk of Adam (or of the
+data-parallel exchange + Adam) on a fourth; packed bf16 weight operands are refreshed from the fp32 master parameters at
+the start of every step (one launch).  Scheduling choices are constructor options, not environment switches.
 """
 from __future__ import annotations
 
@@ -37,16 +39,20 @@ S2D_LAYERS = ["enc.conv2", "enc.conv3", "enc.conv4", "dec.conv2t", "dec.conv3t",
 S2D_TENSORS = ["enc.conv1.out", "enc.conv2.out", "enc.conv3.out", "dec.conv4t.dout", "dec.conv3t.dout", "dec.conv2t.dout"]
 
 
-def _dense64_geom(rows, cs):
-    """[rows, 64] x [64, cs] as a 1x1 'convolution' (used for the im2col'd end layers)."""
-    return Geom(rows, 1, 1, 64, 1, 1, cs, 1, 1, 1, 0)
-
-
 class EngineTC(Engine):
     precision = "bf16"
 
-    def __init__(self, store, fused_chain=True):
+    def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0):
         super().__init__(store)
+        # scheduling of the weight-gradient kernels (they feed only the optimiser): the encoder's alternate between
+        # `wgrad_streams` side streams so that a layer's weight gradient starts when its operand is ready instead of
+        # queueing behind the previous layer's; the small launches that follow the fused chain kernel (fc1 / heads
+        # weight gradients, gate backward) go to `post_chain_stream` ("side" = the weight-gradient stream, "side2" =
+        # the bias-gradient stream).  Same-box A/B, ms per sup+unsup pair (profiles/r02_ab_log.txt): 1 stream / side
+        # 1.344, 2 streams / side 1.336, 2 streams / side2 1.351, 1 stream / side2 1.375
+        self.wgrad_streams = int(wgrad_streams)
+        self.post_chain_stream = post_chain_stream
+        self.side_b = None
         # conv5 -> heads -> latent -> fc1 -> conv1t (and the reverse) as ONE launch each way (csrc/chain.cu); False keeps
         # the layer-by-layer kernels (A/B runs, cross-check in tests/test_gpu_chain.py)
         self.chain = bool(fused_chain)
@@ -66,19 +72,16 @@ class EngineTC(Engine):
             if lib.gccvae_sl_halo_supported(C.byref(g)):
                 self.halo[name] = True
                 self.wp[name + ".sl9"] = z16(lib.gccvae_packed_weight_elems(C.byref(g), 2))
-        self.wp["enc.conv1.c4"] = z16(32 * 64)
-        self.wp["dec.conv5t.c4"] = z16(32 * 64)
         # x2 (space-to-depth) operands of the 3-channel end layers
         self.wp["enc.conv1.x2"] = z16(32 * 64)       # [cs][(a,b)][(dy,dx,c4)]
         self.wp["dec.conv5t.x2"] = z16(32 * 64)      # same packing: B operand of conv5t's dgrad
         self.wp["dec.conv5t.x2t"] = z16(16 * 128)    # [(dy,dx,c4)][(a,b)][cs]: fused conv5t forward
-        self.x2 = os.environ.get("GCCVAE_X2", "1") != "0"
+        self.x2 = True     # 3-channel tensors in x2 block form
         # s2d storage of the L tensors of the six k4/s2/p1 layers in the middle (include/gccvae.h, GCCVAE_OUT_S2D)
-        self.s2d = self.x2 and os.environ.get("GCCVAE_S2D", "1") != "0"
-        if self.s2d:
-            for name in S2D_LAYERS:
-                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
-                self.wp[name + ".s2d"] = z16(((CS + 15) // 16 * 16) * 16 * CL)
+        self.s2d = True
+        for name in S2D_LAYERS:
+            _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+            self.wp[name + ".s2d"] = z16(((CS + 15) // 16 * 16) * 16 * CL)
         # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
         self.wp["heads.ls"] = z16(96, 256)       # rows 0..44 = W_loc^T, 48..92 = W_std^T
         self.wp["heads.sl"] = z16(256, 96)
@@ -88,27 +91,12 @@ class EngineTC(Engine):
         self.wp["conv1t.sl"] = z16(2048, 64)
         self.wp["conv1t.ls"] = z16(64, 2048)
         self._jobs = None
-        # bias gradients: a separate column-sum pass per layer by default.  Both fused variants were measured slower
-        # on B200: in the dgrad epilogue (registers -> occupancy: 2.57 vs 2.37 ms per step) and in the wgrad main loop
-        # (GCCVAE_BIAS_IN_WGRAD=1: stage release waits for the sums: 2.11 vs 2.09 ms).
-        # weight gradients are off the critical path (only Adam needs them): they run on a side stream, concurrently
-        # with the dgrad chain; under CUDA-graph capture this becomes a parallel branch of the graph
-        self.side = torch.cuda.Stream(device=dev) if os.environ.get("GCCVAE_SIDE_STREAM", "1") != "0" else None
-        # bias gradients (column sums) are needed by Adam only, like the weight gradients: a second side stream keeps
-        # them off the dgrad chain (GCCVAE_BGRAD_STREAM=main puts them back on the main stream)
-        self.side2 = (torch.cuda.Stream(device=dev)
-                      if self.side is not None and os.environ.get("GCCVAE_BGRAD_STREAM", "side") != "main" else None)
-        self.bias_in_wgrad = os.environ.get("GCCVAE_BIAS_IN_WGRAD", "0") != "0"
-        # ... or for selected layers only (comma-separated names)
-        self.bias_in_wgrad_layers = set(filter(None, os.environ.get("GCCVAE_BIAS_IN_WGRAD_LAYERS", "").split(",")))
-        self.wg_rr = os.environ.get("GCCVAE_WG_RR", "0") != "0"   # weight gradients alternate between both side streams
-        # bias gradients fused into the epilogue of the dgrad that produces the layer's pre-activation gradient
-        # (column sums of what it stores): no separate pass over the tensor.  Off: column-sum kernels on side2.
-        # Measured on B200 (batch 1024): 1.507 ms fused vs 1.504 ms un-fused per sup+unsup pair - the column-sum kernels
-        # hide on the second side stream, the fused epilogues lengthen the dgrad chain - so it is off by default.
-        self.fused_bias = os.environ.get("GCCVAE_FUSED_BIAS", "0") != "0"
-        self._bias_fused = set()
-        self._rr = 0
+        # bias gradients: a separate bandwidth-bound column-sum pass per layer on its own stream.  Fusing them into the
+        # dgrad epilogue (registers -> occupancy) or into the wgrad main loop (the stage release waits for the sums) was
+        # measured slower on B200 in both rounds (profiles/r01d_ab_log.txt, r02_ab_log.txt); those options are gone.
+        # Weight gradients are off the critical path (only Adam needs them): side streams, parallel graph branches.
+        self.side = torch.cuda.Stream(device=dev)
+        self.side2 = torch.cuda.Stream(device=dev)
         self._deferred_bias = []
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
         # called once per backward pass when every gradient except the first layer's is complete or queued: the
@@ -117,8 +105,8 @@ class EngineTC(Engine):
         self.tail_hook_layer = TC_ENC[0]   # ... called when THIS layer's weight gradient has been issued (its dgrad follows)
         self.side3 = None          # its own stream: the first layer's weight / bias gradients must not queue behind it
         self._side3_used = False
-        # debug timeline (GCCVAE_MARKERS=1: a globaltimer marker kernel after every op, 2: only at segment ends)
-        self.mark_level = int(os.environ.get("GCCVAE_MARKERS", "0"))
+        # debug timeline (markers=1: a globaltimer marker kernel after every op, 2: only at segment ends)
+        self.mark_level = int(markers)
         self.mark_buf = torch.zeros(1024, dtype=torch.int64, device=dev) if self.mark_level else None
         self.marks = []
 
@@ -133,19 +121,16 @@ class EngineTC(Engine):
             for name in TC_ENC + TC_DEC:
                 lay = _ENC.get(name) or _DEC[name]
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
-                if not (self.s2d and name in S2D_LAYERS):     # the s2d layers use the kind-9 operand instead
+                if name not in S2D_LAYERS:     # the s2d layers use the kind-9 operand instead
                     J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
                 J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
             J(1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"])
             for name in self.halo:
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
                 J(6, 16, CL, CS, v(name + ".w"), self.wp[name + ".sl9"])
-            J(3, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.c4"])
-            J(3, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.c4"])
-            if self.s2d:
-                for name in S2D_LAYERS:
-                    _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
-                    J(9, 16, CL, CS, v(name + ".w"), self.wp[name + ".s2d"])
+            for name in S2D_LAYERS:
+                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+                J(9, 16, CL, CS, v(name + ".w"), self.wp[name + ".s2d"])
             J(7, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.x2"])
             J(7, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2"])
             J(8, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2t"])
@@ -167,13 +152,9 @@ class EngineTC(Engine):
         dev = self.device
         e = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         b = {}
-        if self.x2:
-            b["X2"] = e(B, 33, 33, 16, dt=BF16)      # input image in x2 block form
-            b["D2"] = e(B, 33, 33, 16, dt=BF16)      # dLoss/dlogit of the reconstruction in x2 block form
-            b["xhat3"] = None                        # fp32 reconstruction, allocated on demand (tests / API)
-        else:
-            b["X64"] = e(B * 1024, 64, dt=BF16)
-            b["G64"] = e(B * 1024, 64, dt=BF16)
+        b["X2"] = e(B, 33, 33, 16, dt=BF16)      # input image in x2 block form
+        b["D2"] = e(B, 33, 33, 16, dt=BF16)      # dLoss/dlogit of the reconstruction in x2 block form
+        b["xhat3"] = None                        # fp32 reconstruction, allocated on demand (tests / API)
         for name in ["enc.conv1", "enc.conv2", "enc.conv3", "enc.conv4", "enc.conv5"]:
             oh, ow, oc = out_shape(_ENC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
@@ -188,11 +169,10 @@ class EngineTC(Engine):
             oh, ow, oc = out_shape(_DEC[name])
             b[name + ".out"] = e(B, oh, ow, oc, dt=BF16)
             b[name + ".dout"] = e(B, oh, ow, oc, dt=BF16)
-        b["xhat4"] = None if self.x2 else e(B, 64, 64, 4)
-        if self.s2d:
-            for tname in S2D_TENSORS:
-                Bq, H, W, Cc = b[tname].shape
-                b[tname] = e(B, H // 2 + 1, W // 2 + 1, 4 * Cc, dt=BF16)   # zero borders are never written
+        b["xhat4"] = None
+        for tname in S2D_TENSORS:
+            Bq, H, W, Cc = b[tname].shape
+            b[tname] = e(B, H // 2 + 1, W // 2 + 1, 4 * Cc, dt=BF16)   # zero borders are never written
         return b
 
     def _xhat4(self, b, B):
@@ -293,21 +273,24 @@ class EngineTC(Engine):
         with torch.cuda.stream(self.side2):
             fn()
 
-    def _side(self, fn, small=False):
+    def _side(self, fn, small=False, alt=False):
         """run fn (weight-gradient launches) on the side stream, after everything issued so far on the main one.
-        (`small=True` keeps a launch on the main stream; measured slower for every candidate, so it is unused.)"""
+        (`small=True` keeps a launch on the main stream; measured slower for every candidate, so it is unused.)
+        `alt`: use the second weight-gradient stream (wgrad_streams == 2)."""
         if self.side is None or small:
             fn()
             self._flush_deferred_bias()
             return
         side = self.side
-        if self.wg_rr and self.side2 is not None:
-            side = (self.side, self.side2)[self._rr & 1]
-            self._rr += 1
+        if alt and self.wgrad_streams > 1:
+            if self.side_b is None:
+                self.side_b = torch.cuda.Stream(device=self.device)
+            side = self.side_b
+            self._side_b_used = True
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             fn()
-        self._flush_deferred_bias()      # column-sum passes requested by fn's _arm_wgrad_bias
+        self._flush_deferred_bias()      # column-sum passes requested by fn's _bias
 
     def join_side(self):
         if self.side is not None:
@@ -317,32 +300,16 @@ class EngineTC(Engine):
             if self._side3_used:
                 torch.cuda.current_stream().wait_stream(self.side3)
                 self._side3_used = False
+            if getattr(self, "_side_b_used", False):
+                torch.cuda.current_stream().wait_stream(self.side_b)
+                self._side_b_used = False
 
-    def _fuse_bias(self, name, n, mod=0):
-        """the NEXT dgrad launch (main stream) also accumulates the bias gradient of layer `name` in its epilogue."""
-        if self.fused_bias and self.prof is None:
-            self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, mod)
-            self._bias_fused.add(name)
-
-    def _arm_wgrad_bias(self, name, n, side, dout=None):
-        if name in getattr(self, "_chain_bias", ()):      # produced by the fused chain kernel
+    def _bias(self, name, n, dout):
+        """bias gradient of `name` = column sums of its pre-activation gradient `dout`: queued for the bias-gradient
+        stream (flushed by _side) unless the fused chain kernel produces it."""
+        if name in getattr(self, "_chain_bias", ()):
             return
-        if name in self._bias_fused:      # already produced by the dgrad epilogue
-            self._bias_fused.discard(name)
-            return
-        self._arm_wgrad_bias_unfused(name, n, side, dout)
-
-    def _arm_wgrad_bias_unfused(self, name, n, side, dout=None):
-        """bias gradient of `name`.  Default: a separate bandwidth-bound column-sum pass over dout on the main
-        stream.  GCCVAE_BIAS_IN_WGRAD=1: the next wgrad launch produces it from its staged operand tiles (side 1:
-        S operand, 2: L operand) with its idle epilogue warps - one pass less over dout, but measured 1 % slower
-        end to end on B200 (the stage release waits for the column sums), so it is off by default."""
-        x2_layer = self.x2 and name in ("enc.conv1", "dec.conv5t")    # their wgrad's epilogue warps build the A tile
-        if ((self.bias_in_wgrad or name in self.bias_in_wgrad_layers) and not x2_layer
-                and not (self.s2d and side == 2)):   # (the s2d wgrad sums the S operand only)
-            self.lib.gccvae_next_launch_colsum(ptr(self.store.g(name + ".b")), n, -side)
-        elif dout is not None:
-            self._deferred_bias.append((dout, name, n))
+        self._deferred_bias.append((dout, name, n))
 
     def zero_grads(self):
         self.store.grad.zero_()   # the tensor-core wgrad / bias-grad kernels accumulate (split-K red.global)
@@ -353,7 +320,7 @@ class EngineTC(Engine):
         transform of the image, pre-setting log_pxz - forked onto the two side streams, so that it overlaps the
         gradient memset and the gate kernel on the main stream (parallel branches of the captured graph)."""
         self._begun = False
-        if self.side is None or self.side2 is None or not self.x2:
+        if self.side is None:       # (profile_step issues everything serially)
             return
         B = x.shape[0]
         main = torch.cuda.current_stream()
@@ -378,24 +345,14 @@ class EngineTC(Engine):
         else:
             self._log_pxz_ready = False
             self.pack_weights()
-        if self.x2:
             u8 = int(x.dtype == torch.uint8)
-            if not begun:
-                self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
-            self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
-                B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")),
-                ACT_RELU | (OUT_S2D if self.s2d else 0), None, ptr(b["enc.conv1.out"]), st))
-        else:
-            self._run("im2col_x", (x, b["X64"]), lambda: lib.gccvae_im2col_x_bf16(ptr(x), B, ptr(b["X64"]), st))
-            g = _dense64_geom(B * 1024, 32)
-            g1 = g
-            self._run("enc.conv1 fwd", (b["X64"], b["enc.conv1.out"]), lambda: lib.gccvae_ls_bf16(
-                C.byref(g1), ptr(b["X64"]), ptr(self.wp["enc.conv1.c4"]), ptr(v("enc.conv1.b")), ACT_RELU, None,
-                ptr(b["enc.conv1.out"]), 0, st))
+            self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
+        self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
+            B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU | OUT_S2D, None,
+            ptr(b["enc.conv1.out"]), st))
         h = b["enc.conv1.out"]
         for name in TC_ENC:
-            g = make_geom(_ENC[name], B)
-            if self.s2d and name in S2D_LAYERS:
+            if name in S2D_LAYERS:
                 # L operand in s2d block form: 2x2 taps of 4 C_L channels; the output is stored in s2d form when the
                 # next layer is a stride-2 layer too
                 _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _ENC[name]
@@ -404,12 +361,12 @@ class EngineTC(Engine):
                           lambda h=h, name=name, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag: lib.gccvae_tap4_ls_bf16(
                               B, HS + 1, WS + 1, 4 * CL, ptr(h), ptr(self.wp[name + ".s2d"]), CS, ptr(v(name + ".b")),
                               ACT_RELU | flag, None, ptr(b[name + ".out"]), st))
-                h = b[name + ".out"]
-                continue
-            self._run(name + " fwd", (h, self.wp[name + ".ls"], b[name + ".out"]),
-                      lambda g=g, h=h, name=name: lib.gccvae_ls_bf16(
-                          C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU, None,
-                          ptr(b[name + ".out"]), 0, st))
+            else:
+                g = make_geom(_ENC[name], B)
+                self._run(name + " fwd", (h, self.wp[name + ".ls"], b[name + ".out"]),
+                          lambda g=g, h=h, name=name: lib.gccvae_ls_bf16(
+                              C.byref(g), ptr(h), ptr(self.wp[name + ".ls"]), ptr(v(name + ".b")), ACT_RELU, None,
+                              ptr(b[name + ".out"]), 0, st))
             h = b[name + ".out"]
         if heads:      # (inside the ELBO step the fused chain kernel computes them)
             self._gemm(B, 256, 96, h, self.wp["heads.ls"], self.wp["heads.bias"], 96, 0, ACT_NONE, None, b["pre96"], 1,
@@ -419,7 +376,7 @@ class EngineTC(Engine):
     def decoder_fwd(self, z, b, z16_ready=False, fused_recon=False, batch=None, head=True):
         B = z.shape[0] if batch is None else batch
         lib, st, v = self.lib, _stream(), self.store.view
-        if not z16_ready:          # standalone Decoder(z) call; inside the step the latent kernel writes z16
+        if not z16_ready:          # standalone Decoder(z) call; inside the step the latent stage writes z16
             b["z16"][:, :45].copy_(z)
         if head:                   # (inside the ELBO step the fused chain kernel has produced dec.conv1t.out)
             self._gemm(B, 64, 64, b["z16"], self.wp["fc1.ls"], v("dec.fc1.b"), 45, 0, ACT_RELU, None, b["dec.fc1.out"], 0,
@@ -458,78 +415,45 @@ class EngineTC(Engine):
         self._log_pxz_ready = False
         return xhat
 
-    def recon(self, x, b, coef, log_pxz, backward):
-        B = x.shape[0]
-        self._xhat4(b, B)
-        self._run("recon_im2col", (x, b["xhat4"], b["G64"] if backward else None),
-                  lambda: self.lib.gccvae_recon_im2col_bf16(
-                      ptr(x), ptr(b["xhat4"]), B, ptr(coef) if backward else None, ptr(log_pxz),
-                      ptr(b["G64"]) if backward else None, ptr(self.store.g("dec.conv5t.b")) if backward else None,
-                      _stream()))
-        return b["xhat4"][..., :3]
-
     # ---- backward -----------------------------------------------------------------------------------------------
     def decoder_bwd(self, z, b, want_dz=True, tail=True):
         """`tail=False`: stop after conv2t's dgrad (the fused chain kernel continues from dec.conv1t.dout)."""
         B = z.shape[0]
         lib, st, g_ = self.lib, _stream(), self.store.g
+        self._chain_bias = set() if tail else {"dec.conv1t", "dec.fc1", "enc.conv5"}
         g4 = b["dec.conv4t.out"]
-        if self.x2:
-            # conv5t from the logit gradient in x2 block form (written by the fused forward)
-            self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
-                B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
-            self._fuse_bias("dec.conv4t", 32)
-            self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
-                B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE | (OUT_S2D if self.s2d else 0), ptr(g4),
-                ptr(b["dec.conv4t.dout"]), st))
-        else:
-            # conv5t from the im2col'd logit gradient
-            self._side(lambda: self._run("dec.conv5t wgrad", (b["G64"], g4), lambda: lib.gccvae_wg_c4_bf16(
-                B * 1024, ptr(b["G64"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
-            g = _dense64_geom(B * 1024, 32)
-            self._run("dec.conv5t dgrad", (b["G64"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_ls_bf16(
-                C.byref(g), ptr(b["G64"]), ptr(self.wp["dec.conv5t.c4"]), None, ACT_NONE, ptr(g4),
-                ptr(b["dec.conv4t.dout"]), 0, st))
+        # conv5t from the logit gradient in x2 block form (written by the fused forward)
+        self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
+            B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
+        self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
+            B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE | OUT_S2D, ptr(g4),
+            ptr(b["dec.conv4t.dout"]), st))
         prev_of = {"dec.conv4t": "dec.conv3t", "dec.conv3t": "dec.conv2t", "dec.conv2t": "dec.conv1t"}
         for name in reversed(TC_DEC):
-            geom = make_geom(_DEC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
             _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _DEC[name]
-            def wg(name=name, geom=geom, dout=dout, xin=xin, HS=HS, WS=WS, CL=CL, CS=CS):
-                self._arm_wgrad_bias(name, CL, 2, dout)   # dout is the L operand of a transposed conv
-                if self.s2d:
-                    self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_s2d_bf16(
-                        B, HS, WS, CL, ptr(dout), ptr(xin), CS, ptr(g_(name + ".w")), _stream()))
-                else:
-                    self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_bf16(
-                        C.byref(geom), ptr(dout), ptr(xin), ptr(g_(name + ".w")), _stream()))
+            def wg(name=name, dout=dout, xin=xin, HS=HS, WS=WS, CL=CL, CS=CS):
+                self._bias(name, CL, dout)
+                self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_s2d_bf16(
+                    B, HS, WS, CL, ptr(dout), ptr(xin), CS, ptr(g_(name + ".w")), _stream()))
             self._side(wg)
-            self._fuse_bias(pn, _DEC[pn][2][2])          # this dgrad's output is pn's pre-activation gradient
-            if self.s2d:
-                flag = OUT_S2D if (pn + ".dout") in S2D_TENSORS else 0
-                self._run(name + " dgrad", (dout, self.wp[name + ".s2d"], xin, dxin),
-                          lambda name=name, dout=dout, xin=xin, dxin=dxin, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag:
-                          lib.gccvae_tap4_ls_bf16(B, HS + 1, WS + 1, 4 * CL, ptr(dout), ptr(self.wp[name + ".s2d"]), CS, None,
-                                                  ACT_NONE | flag, ptr(xin), ptr(dxin), st))
-            else:
-                self._run(name + " dgrad", (dout, self.wp[name + ".ls"], xin, dxin), lambda: lib.gccvae_ls_bf16(
-                    C.byref(geom), ptr(dout), ptr(self.wp[name + ".ls"]), None, ACT_NONE, ptr(xin), ptr(dxin), 0, st))
+            flag = OUT_S2D if (pn + ".dout") in S2D_TENSORS else 0
+            self._run(name + " dgrad", (dout, self.wp[name + ".s2d"], xin, dxin),
+                      lambda name=name, dout=dout, xin=xin, dxin=dxin, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag:
+                      lib.gccvae_tap4_ls_bf16(B, HS + 1, WS + 1, 4 * CL, ptr(dout), ptr(self.wp[name + ".s2d"]), CS, None,
+                                              ACT_NONE | flag, ptr(xin), ptr(dxin), st))
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
                                          "dec.conv1t wgrad"))
         if not tail:
             return None
-        if "dec.conv1t" in self._bias_fused:
-            self._bias_fused.discard("dec.conv1t")
-        else:
-            self._on_side2(lambda: self._bias_grad16(dg1, "dec.conv1t", cols=128))
-        self._fuse_bias("dec.fc1", 45)
+        self._on_side2(lambda: self._bias_grad16(dg1, "dec.conv1t", cols=128))
         self._gemm(B, 2048, 64, dg1, self.wp["conv1t.ls"], None, 0, 0, ACT_NONE, g0, dg0, 0, "dec.conv1t dgrad")
         def wg_fc1():
-            self._arm_wgrad_bias("dec.fc1", 45, 1, dg0)
-            self._gemm_tn(B, 64, 64, b["z16"], dg0, [(0, 45, 45, g_("dec.fc1.w"))], 45, "dec.fc1 wgrad")
+            self._bias("dec.fc1", 45, dg0)
+            self.fc1_wgrad(b, B)
         self._side(wg_fc1)
         if want_dz:
             self._gemm(B, 64, 64, dg0, self.wp["fc1.sl"], None, 0, 0, ACT_NONE, None, b["dz64"], 1, "dec.fc1 dgrad")
@@ -551,42 +475,40 @@ class EngineTC(Engine):
         h5, dh5, dpre = b["enc.conv5.out"], b["enc.conv5.dout"], b["dpre16"]
         if heads:
             self._side(lambda: self.heads_wgrad(b, B))
-            self._fuse_bias("enc.conv5", 256)
             self._gemm(B, 96, 256, dpre, self.wp["heads.sl"], None, 0, 0, ACT_NONE, h5, dh5, 0, "enc.heads dgrad")
-        self._chain_bias = {"enc.conv5"} if not heads else set()
         prev_of = {"enc.conv5": "enc.conv4", "enc.conv4": "enc.conv3", "enc.conv3": "enc.conv2",
                    "enc.conv2": "enc.conv1"}
         for name in reversed(TC_ENC):
             geom = make_geom(_ENC[name], B)
             dout, pn = b[name + ".dout"], prev_of[name]
             xin, dxin = b[pn + ".out"], b[pn + ".dout"]
-            s2d_l = self.s2d and name in S2D_LAYERS        # xin (L operand, and the ReLU mask of the dgrad) is s2d
+            s2d_l = name in S2D_LAYERS        # xin (L operand, and the ReLU mask of the dgrad) is s2d
             _, _, (HL, WL, CL), (HS, WS, CS), k_, s_, p_, _ = _ENC[name]
             def wg(name=name, geom=geom, dout=dout, xin=xin, s2d_l=s2d_l, HS=HS, WS=WS, CL=CL, CS=CS):
-                self._arm_wgrad_bias(name, dout.shape[-1], 1, dout)   # dout is the S operand of a conv
+                self._bias(name, dout.shape[-1], dout)
                 if s2d_l:
                     self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_s2d_bf16(
                         B, HS, WS, CL, ptr(xin), ptr(dout), CS, ptr(g_(name + ".w")), _stream()))
                 else:
                     self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
                         C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
-            self._side(wg)
+            self._side(wg, alt=(name in ("enc.conv4", "enc.conv2")))
             hook = self.tail_hook if name == self.tail_hook_layer else None
             ev = None
-            if hook is not None and self.side is not None and self.side2 is not None:
+            if hook is not None and self.side is not None:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())     # everything the main stream has produced so far
-            # this dgrad's output is pn's pre-activation gradient; the dense conv5 dgrad emits (kh,kw,cl) columns
-            self._fuse_bias(pn, _ENC[pn][3][2], mod=(_ENC[pn][3][2] if name == "enc.conv5" else 0))
             self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad", mask_s2d=s2d_l)
             if hook is not None:
                 self.tail_hook = None
-                if ev is not None:     # under the last dgrad: after all earlier weight / bias gradients, not after it
+                if ev is not None:     # under this dgrad: after all earlier weight / bias gradients, not after it
                     if self.side3 is None:
                         self.side3 = torch.cuda.Stream(device=self.device)
                     self.side3.wait_event(ev)
                     self.side3.wait_stream(self.side)
                     self.side3.wait_stream(self.side2)
+                    if getattr(self, "_side_b_used", False):
+                        self.side3.wait_stream(self.side_b)
                     with torch.cuda.stream(self.side3):
                         hook()
                     self._side3_used = True
@@ -594,13 +516,9 @@ class EngineTC(Engine):
                     hook()
         dh1 = b["enc.conv1.dout"]
         def wg1():
-            self._arm_wgrad_bias("enc.conv1", 32, 1, dh1)
-            if self.x2:
-                self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(
-                    B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
-            else:
-                self._run("enc.conv1 wgrad", (b["X64"], dh1), lambda: lib.gccvae_wg_c4_bf16(
-                    B * 1024, ptr(b["X64"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
+            self._bias("enc.conv1", 32, dh1)
+            self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(
+                B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
         self._side(wg1)
         self.join_side()
 

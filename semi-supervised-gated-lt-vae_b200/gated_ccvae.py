@@ -442,7 +442,10 @@ class Learner:
                     self.engine.fc1_wgrad(b, B)
                     self.engine.heads_wgrad(b, B)
                     gate_bwd()
-                self.engine._side(after_chain)
+                if self.engine.post_chain_stream == "side2":
+                    self.engine._on_side2(after_chain)
+                else:
+                    self.engine._side(after_chain)
                 self.engine.encoder_bwd(x, b, heads=False)
             else:
                 gate_bwd()

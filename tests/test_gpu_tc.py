@@ -190,90 +190,3 @@ def test_tc_wgrad(name, batch):
     assert err < 1e-4, err      # fp32 accumulation of exact bf16 products
     errb = float((db.cpu().double() - bf(St).double().sum((0, 1, 2))).abs().max() / bf(St).double().sum((0, 1, 2)).abs().max())
     assert errb < 1e-4, errb
-
-
-def test_tc_end_layers_conv1_and_conv5t():
-    """conv1 forward/wgrad and conv5t forward/dgrad/wgrad through the K=64 im2col matrices."""
-    L, lib = _lib()
-    from gccvae_b200._lib import Geom
-    d = torch.device("cuda", 0)
-    B = 5
-    g = torch.Generator().manual_seed(11)
-    bf = lambda t: t.to(torch.bfloat16)
-    st = _stream()
-    # ---- conv1: x fp32 [B,64,64,3] -> h1 [B,32,32,32]
-    x = torch.rand(B, 64, 64, 3, generator=g)
-    W1 = torch.randn(4, 4, 3, 32, generator=g) * 0.2
-    b1 = torch.randn(32, generator=g) * 0.1
-    xd, W1d, b1d = x.to(d), W1.to(d), b1.to(d)
-    X64 = torch.empty(B * 1024, 64, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_im2col_x_bf16(L.ptr(xd), B, L.ptr(X64), st))
-    wp = torch.empty(32 * 64, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_pack_c4_bf16(L.ptr(W1d), 32, L.ptr(wp), st))
-    gd = Geom(B * 1024, 1, 1, 64, 1, 1, 32, 1, 1, 1, 0)
-    h1 = torch.empty(B, 32, 32, 32, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_ls_bf16(C.byref(gd), L.ptr(X64), L.ptr(wp), L.ptr(b1d), L.ACT_RELU, None, L.ptr(h1), 0, st))
-    want = torch.relu(O._conv(bf(x).double(), bf(W1).double(), b1.double(), 2, 1))
-    torch.cuda.synchronize()
-    err = float((h1.float().cpu().double() - want).abs().max() / want.abs().max())
-    assert err < TOL, ("conv1 fwd", err)
-    dh1 = torch.randn(B, 32, 32, 32, generator=g)
-    dh1d = bf(dh1).to(d).contiguous()
-    dW1 = torch.zeros(4, 4, 3, 32, device=d)
-    L.check(lib.gccvae_wg_c4_bf16(B * 1024, L.ptr(X64), L.ptr(dh1d), 32, L.ptr(dW1), st))
-    Wg = torch.zeros(4, 4, 3, 32, dtype=torch.float64, requires_grad=True)
-    (O._conv(bf(x).double(), Wg, None, 2, 1) * bf(dh1).double()).sum().backward()
-    torch.cuda.synchronize()
-    err = float((dW1.cpu().double() - Wg.grad).abs().max() / Wg.grad.abs().max())
-    assert err < 1e-4, ("conv1 wgrad", err)
-    # ---- conv5t: g4 [B,32,32,32] -> xhat [B,64,64,3] (sigmoid), recon LL, dlogit im2col, dgrad, wgrad
-    g4 = torch.relu(torch.randn(B, 32, 32, 32, generator=g))
-    W5 = torch.randn(4, 4, 3, 32, generator=g) * 0.1
-    b5 = torch.randn(3, generator=g) * 0.1
-    coef = -(torch.rand(B, generator=g) + 0.5) / B
-    g4d, W5d, b5d, coefd = bf(g4).to(d).contiguous(), W5.to(d), b5.to(d), coef.to(d)
-    geom = Geom(B, 64, 64, 3, 32, 32, 32, 4, 4, 2, 1)
-    wsl = torch.empty(lib.gccvae_packed_weight_elems(C.byref(geom), 1), dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_pack_weights_bf16(C.byref(geom), L.ptr(W5d), None, L.ptr(wsl), st))
-    xh4 = torch.full((B, 64, 64, 4), float("nan"), device=d)
-    L.check(lib.gccvae_sl_bf16(C.byref(geom), L.ptr(g4d), L.ptr(wsl), L.ptr(b5d), L.ACT_SIGMOID, None, L.ptr(xh4), 2, st))
-    torch.cuda.synchronize()
-    generic = xh4.clone()
-    assert lib.gccvae_sl_halo_supported(C.byref(geom))
-    w9 = torch.zeros(lib.gccvae_packed_weight_elems(C.byref(geom), 2), dtype=torch.bfloat16, device=d)
-    job = (L.PackJob * 1)(L.PackJob(6, 16, 3, 32, L.ptr(W5d), L.ptr(w9), 0, 0, 0, 0, 0, 0))
-    L.check(lib.gccvae_pack_jobs_bf16(job, 1, st))
-    xh4.fill_(float("nan"))
-    L.check(lib.gccvae_sl_halo_bf16(C.byref(geom), L.ptr(g4d), L.ptr(w9), L.ptr(b5d), L.ACT_SIGMOID, None, L.ptr(xh4), 2, st))
-    torch.cuda.synchronize()
-    assert float((xh4 - generic).abs().max()) < 1e-5, "halo kernel and generic tap-GEMM disagree on conv5t"
-    want_logit = O._convT(bf(g4).double(), bf(W5).double(), b5.double(), 2, 1)
-    want_xh = torch.sigmoid(want_logit)
-    got_xh = xh4.cpu()[..., :3].double()
-    assert torch.isfinite(xh4).all() and float(xh4[..., 3].abs().max()) == 0.0
-    assert float((got_xh - want_xh).abs().max()) < 1e-4, "conv5t fwd (fp32 output)"
-    lpx = torch.empty(B, device=d)
-    G64 = torch.empty(B * 1024, 64, dtype=torch.bfloat16, device=d)
-    db = torch.zeros(3, device=d)
-    L.check(lib.gccvae_recon_im2col_bf16(L.ptr(xd), L.ptr(xh4), B, L.ptr(coefd), L.ptr(lpx), L.ptr(G64), L.ptr(db), st))
-    torch.cuda.synchronize()
-    want_ll = O.img_log_likelihood(got_xh, x.double())
-    assert float(((lpx.cpu().double() - want_ll) / want_ll).abs().max()) < 1e-5, "log_pxz"
-    dlogit = coef.double().view(B, 1, 1, 1) * torch.sign(x.double() - got_xh) * got_xh * (1 - got_xh)
-    assert float((db.cpu().double() - dlogit.sum((0, 1, 2))).abs().max() / dlogit.sum((0, 1, 2)).abs().max()) < 1e-3
-    # dgrad through the im2col matrix: dg4 = conv(dlogit, W5) masked by g4 > 0
-    wls = torch.empty(32 * 64, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_pack_c4_bf16(L.ptr(W5d), 32, L.ptr(wls), st))
-    dg4 = torch.empty(B, 32, 32, 32, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_ls_bf16(C.byref(gd), L.ptr(G64), L.ptr(wls), None, L.ACT_NONE, L.ptr(g4d), L.ptr(dg4), 0, st))
-    want = O._conv(bf(dlogit.float()).double(), bf(W5).double(), None, 2, 1) * (bf(g4).double() > 0)
-    torch.cuda.synchronize()
-    err = float((dg4.float().cpu().double() - want).abs().max() / want.abs().max())
-    assert err < 1e-2, ("conv5t dgrad", err)
-    dW5 = torch.zeros(4, 4, 3, 32, device=d)
-    L.check(lib.gccvae_wg_c4_bf16(B * 1024, L.ptr(G64), L.ptr(g4d), 32, L.ptr(dW5), st))
-    Wg = torch.zeros(4, 4, 3, 32, dtype=torch.float64, requires_grad=True)
-    (O._conv(bf(dlogit.float()).double(), Wg, None, 2, 1) * bf(g4).double()).sum().backward()
-    torch.cuda.synchronize()
-    err = float((dW5.cpu().double() - Wg.grad).abs().max() / Wg.grad.abs().max())
-    assert err < 1e-3, ("conv5t wgrad", err)

@@ -10,8 +10,8 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def _declared_symbols():
-    text = open(os.path.join(ROOT, "include", "gccvae.h")).read()
+def _declared_symbols(header="gccvae.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(gccvae_[a-z0-9_]+)\s*\(", text)))
 
@@ -26,6 +26,12 @@ def test_library_is_built_and_exports_header():
         assert hasattr(lib, name), "libgccvae.so does not export " + name
     assert set(declared) == set(L.SIGNATURES), (set(declared) ^ set(L.SIGNATURES))
     assert lib.gccvae_abi_version() == 1
+    # the development aids live in their own header, outside the boundary
+    debug = _declared_symbols("gccvae_debug.h")
+    assert set(debug) == set(L.DEBUG_SIGNATURES) and all(n.startswith("gccvae_debug_") for n in debug)
+    assert not any(n.startswith("gccvae_debug_") for n in declared)
+    for name in debug:
+        assert hasattr(lib, name)
 
 
 def test_param_store_layout_matches_reference_counts():
