@@ -174,11 +174,13 @@ int gccvae_cast_bf16_to_f32(const void* in, long long n, float* out, void* strea
  * U1,U2: explicit uniforms [18,18], or NULL to draw them from Philox4x32-10(seed, offset [+ *step_dev]).
  * c_in (optional): use this c instead of sampling (classifier_loss(x,y,c), gated_ccvae.py:167); then
  * mu/U1/U2 are ignored and dc/dmu is zero.
+ * temperature_dev (optional): device float that overrides `temperature` - the value is then read when the kernel runs,
+ * so a captured CUDA graph of the step follows the per-epoch decay of gated_ccvae.py:404-406 without re-capture.
  * gate_ws: >= GCCVAE_GATE_WS_FLOATS floats: c | M=c*Wcls | bcls | P_lt | P_lf | P_st | P_sf | dc/dmu
  * (P_x[j,i] = c[i,j]*W_x[j,i]; dc/dmu is kept for gccvae_gate_bwd).  `c_out` (may be NULL) receives a copy of c. */
 #define GCCVAE_GATE_WS_FLOATS (7 * 324 + 32)
 int gccvae_gate_fwd(const float* mu, const float* c_in, const float* U1, const float* U2, uint64_t seed,
-                    uint64_t offset, const int* step_dev, float temperature, const float* Wcls, const float* bcls, const float* Wlt,
+                    uint64_t offset, const int* step_dev, float temperature, const float* temperature_dev, const float* Wcls, const float* bcls, const float* Wlt,
                     const float* Wlf, const float* Wst, const float* Wsf, float* gate_ws, float* c_out,
                     void* stream);
 

@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(352) gate_fwd_kernel(const float* __restrict__
                                                        const float* __restrict__ U1,
                                                        const float* __restrict__ U2, uint64_t seed, uint64_t offset,
                                                        const int* __restrict__ step_dev, float T,
+                                                       const float* __restrict__ T_dev,
                                                        const float* __restrict__ Wcls,
                                                        const float* __restrict__ bcls, const float* __restrict__ Wlt,
                                                        const float* __restrict__ Wlf, const float* __restrict__ Wst,
@@ -33,6 +34,7 @@ __global__ void __launch_bounds__(352) gate_fwd_kernel(const float* __restrict__
                                                        float* __restrict__ c_out) {
   pdl_prologue();
   const int p = threadIdx.x;
+  if (T_dev != nullptr) T = *T_dev;   // a captured step follows the host's per-epoch decay (gated_ccvae.py:404-406)
   if (p < 32) ws[GW_B + p] = (p < Y) ? bcls[p] : 0.0f;
   if (p >= NP) return;
   const int i = p / Y, j = p % Y;
@@ -719,14 +721,14 @@ extern "C" int gccvae_accuracy_f32(const float* logits, const long long* y, int 
 }
 
 extern "C" int gccvae_gate_fwd(const float* mu, const float* c_in, const float* U1, const float* U2, uint64_t seed,
-                               uint64_t offset, const int* step_dev, float temperature, const float* Wcls, const float* bcls, const float* Wlt,
+                               uint64_t offset, const int* step_dev, float temperature, const float* temperature_dev, const float* Wcls, const float* bcls, const float* Wlt,
                                const float* Wlf, const float* Wst, const float* Wsf, float* gate_ws, float* c_out,
                                void* stream) {
   GCC_REQUIRE((mu || c_in) && Wcls && bcls && Wlt && Wlf && Wst && Wsf && gate_ws, "gate_fwd: null pointer");
   GCC_REQUIRE((U1 == nullptr) == (U2 == nullptr), "gate_fwd: U1 and U2 must both be given or both be NULL");
-  GCC_REQUIRE(temperature > 0.0f, "gate_fwd: temperature must be > 0");
+  GCC_REQUIRE(temperature > 0.0f || temperature_dev, "gate_fwd: temperature must be > 0");
   GCC_CUDA(launch_pdl_k(gate_fwd_kernel, dim3(1), dim3(352), 0, (cudaStream_t)stream, mu, c_in, U1, U2, seed, offset,
-                        step_dev, temperature, Wcls, bcls, Wlt, Wlf, Wst, Wsf, gate_ws, c_out));
+                        step_dev, temperature, temperature_dev, Wcls, bcls, Wlt, Wlf, Wst, Wsf, gate_ws, c_out));
   GCC_CHECK_LAUNCH("gate_fwd");
   return GCCVAE_OK;
 }

@@ -19,6 +19,7 @@ Extensions the reference lacks (needed for parity testing and for data paralleli
 """
 from __future__ import annotations
 
+import contextlib
 import ctypes as C
 import logging
 import math
@@ -105,7 +106,7 @@ class CCVAE:
         U1 = None if U1 is None else as_device_f32(U1, self.device)
         U2 = None if U2 is None else as_device_f32(U2, self.device)
         v = self.store.view
-        _lib.check(self.lib.gccvae_gate_fwd(ptr(mu), None, ptr(U1), ptr(U2), seed, offset, None, float(temperature),
+        _lib.check(self.lib.gccvae_gate_fwd(ptr(mu), None, ptr(U1), ptr(U2), seed, offset, None, float(temperature), None,
                                             ptr(v("cls.w")), ptr(v("cls.b")), ptr(v("prior.loc_true")),
                                             ptr(v("prior.loc_false")), ptr(v("prior.scale_true")),
                                             ptr(v("prior.scale_false")), ptr(ws), ptr(c), _stream()), "gate_fwd")
@@ -172,6 +173,7 @@ class Learner:
         self.lr = train_config["lr"]
         self.alpha = 0.1 * num_samples
         self.latent_sampler_temp = train_config.get("init_temp", 0.1)
+        self._temp_dev = None
         self.gating_sampler_temp = train_config["gating_init_temp"]
         self.model = CCVAE(z_dim, z_classify, y_dim, train_config, device=device, precision=precision,
                            init_seed=init_seed, engine_options=engine_options)
@@ -199,6 +201,13 @@ class Learner:
         self._copy_stream = None
         self.last = {}
         self._lat = {}
+        self._temp_dev = torch.full((1,), self._gating_sampler_temp, dtype=torch.float32, device=self.device)
+        # Philox counter offset of the current call: 0 inside train_step (forward and backward regenerate the same noise
+        # from the step counter); every forward-only call (sup_loss / unsup_loss / classifier_loss / classifier_accuracy)
+        # takes a fresh one, so that e.g. the validation batches of accuracy() see different gate samples and noise,
+        # as the reference's tf.random draws do
+        self._noise_offset = 0
+        self._eval_calls = 0
         self._gate_ws = torch.zeros(GATE_WS_FLOATS, dtype=torch.float32, device=self.device)
         self._c = torch.zeros(18, 18, dtype=torch.float32, device=self.device)
         self._loss = torch.zeros(1, dtype=torch.float32, device=self.device)
@@ -303,11 +312,27 @@ class Learner:
         return n
 
     # ---- the ELBO step ----------------------------------------------------------------------------------------
-    def _gate(self, n, c_in=None, temperature=None):
+    @property
+    def gating_sampler_temp(self):
+        """gated_ccvae.py:136: the gate sampler's temperature.  The kernels read it from a device scalar, so assigning it
+        (the per-epoch decay, :404-406) reaches captured graphs too - no re-capture, unlike the reference's traced
+        graph, which keeps the value it was traced with."""
+        return self._gating_sampler_temp
+
+    @gating_sampler_temp.setter
+    def gating_sampler_temp(self, t):
+        t = float(t)
+        if not t > 0.0:
+            raise ValueError("gating_sampler_temp must be > 0")
+        self._gating_sampler_temp = t
+        if getattr(self, "_temp_dev", None) is not None:
+            self._temp_dev.fill_(t)
+
+    def _gate(self, n, c_in=None):
         v = self.store.view
-        T = float(self.gating_sampler_temp if temperature is None else temperature)
         _lib.check(self.lib.gccvae_gate_fwd(ptr(self.store.view("mu")), ptr(c_in), ptr(n["U1"]), ptr(n["U2"]),
-                                            dp.gate_seed(self.seed), 0, ptr(self.optimiser.step_dev), T, ptr(v("cls.w")),
+                                            dp.gate_seed(self.seed), self._noise_offset, ptr(self.optimiser.step_dev),
+                                            self._gating_sampler_temp, ptr(self._temp_dev), ptr(v("cls.w")),
                                             ptr(v("cls.b")), ptr(v("prior.loc_true")), ptr(v("prior.loc_false")),
                                             ptr(v("prior.scale_true")), ptr(v("prior.scale_false")),
                                             ptr(self._gate_ws), ptr(self._c), _stream()), "gate_fwd")
@@ -319,7 +344,7 @@ class Learner:
         a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
         a.z16 = io["z16"]
         a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
-        a.seed, a.offset = dp.data_seed(self.seed, self.rank), 0
+        a.seed, a.offset = dp.data_seed(self.seed, self.rank), self._noise_offset
         a.step_dev = ptr(self.optimiser.step_dev)
         a.gate_ws = ptr(self._gate_ws)
         a.loc, a.scale, a.z, a.terms, a.logits, a.y_out = (ptr(lb["loc"]), ptr(lb["scale"]), ptr(lb["z"]),
@@ -332,7 +357,7 @@ class Learner:
         io = self.engine.latent_io(b)
         a.loc_pre, a.scale_pre, a.ld_pre = io["loc_pre"], io["scale_pre"], io["ld_pre"]
         a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
-        a.seed, a.offset = dp.data_seed(self.seed, self.rank), 0
+        a.seed, a.offset = dp.data_seed(self.seed, self.rank), self._noise_offset
         a.step_dev = ptr(self.optimiser.step_dev)
         a.gate_ws, a.terms, a.log_pxz = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"])
         a.dz, a.ld_dz = io["dz"], io["ld_dz"]
@@ -348,7 +373,7 @@ class Learner:
         for k_ in ("h5", "w_heads", "b_heads", "w_fc1", "b_fc1", "w_conv1t", "b_conv1t", "pre", "z16", "g0", "g1"):
             setattr(a, k_, ptr(io[k_]))
         a.y, a.eps, a.eps_k, a.U_y = ptr(y), ptr(n["eps"]), ptr(n["eps_k"]), ptr(n["U_y"])
-        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), 0, ptr(self.optimiser.step_dev)
+        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), self._noise_offset, ptr(self.optimiser.step_dev)
         a.gate_ws = ptr(self._gate_ws)
         a.loc, a.scale, a.z, a.terms, a.logits, a.y_out = (ptr(lb["loc"]), ptr(lb["scale"]), ptr(lb["z"]),
                                                            ptr(lb["terms"]), ptr(lb["logits"]), ptr(lb["y_i32"]))
@@ -364,7 +389,7 @@ class Learner:
                    "db_scale", "db_fc1", "db_conv1t", "db_conv5"):
             setattr(a, k_, ptr(io[k_]))
         a.y, a.eps, a.eps_k = ptr(lb["y_i32"]), ptr(n["eps"]), ptr(n["eps_k"])
-        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), 0, ptr(self.optimiser.step_dev)
+        a.seed, a.offset, a.step_dev = dp.data_seed(self.seed, self.rank), self._noise_offset, ptr(self.optimiser.step_dev)
         a.gate_ws, a.terms, a.log_pxz, a.partials = ptr(self._gate_ws), ptr(lb["terms"]), ptr(lb["log_pxz"]), ptr(lb["partials"])
         self.engine._run("chain bwd", (io["dg1"], io["w_conv1t_t"], io["w_heads_t"], io["dh5"]),
                          lambda: self.lib.gccvae_chain_bwd(C.byref(a), _stream()))
@@ -463,16 +488,49 @@ class Learner:
                          y=lb["y_i32"], c=self._c, supervised=supervised)
         return (self.store.loss_slot[0] if backward else self._loss[0]), self._c
 
+    @contextlib.contextmanager
+    def _fresh_noise(self):
+        """Philox counter offset of a forward-only call: different for every call (see _noise_offset)."""
+        self._eval_calls += 1
+        self._noise_offset = self._eval_calls << 32
+        try:
+            yield
+        finally:
+            self._noise_offset = 0
+
     # ---- reference API ---------------------------------------------------------------------------------------------
     def sup_loss(self, x, y, noise=None, k=100):
-        """gated_ccvae.py:234-300 -> (loss, c).  Forward only; train_step also runs the backward."""
-        loss, c = self._elbo(x, y, True, noise, backward=False, k=k)
+        """gated_ccvae.py:234-300 -> (loss, c).  With autograd enabled on the parameters (`requires_grad_()`), the
+        returned loss carries the graph edge the reference's GradientTape records (:302-309): `loss.backward()` leaves
+        d loss / d parameters in `self.store.flat.grad` (`gradients()` views it per tensor).  Otherwise forward only."""
+        if self._wants_grad():
+            return _ElboFunction.apply(self.store.flat, self, x, y, True, noise, k)
+        with self._fresh_noise():
+            loss, c = self._elbo(x, y, True, noise, backward=False, k=k)
         return self._global_loss(loss).clone(), c.clone()
 
     def unsup_loss(self, x, noise=None):
-        """gated_ccvae.py:184-232 -> (loss, c)."""
-        loss, c = self._elbo(x, None, False, noise, backward=False)
+        """gated_ccvae.py:184-232 -> (loss, c); differentiable like sup_loss."""
+        if self._wants_grad():
+            return _ElboFunction.apply(self.store.flat, self, x, None, False, noise, 100)
+        with self._fresh_noise():
+            loss, c = self._elbo(x, None, False, noise, backward=False)
         return self._global_loss(loss).clone(), c.clone()
+
+    def requires_grad_(self, flag=True):
+        """make sup_loss / unsup_loss differentiable w.r.t. the (flat) parameter buffer, torch style."""
+        self.store.flat.requires_grad_(bool(flag))
+        if not flag:
+            self.store.flat.grad = None
+        return self
+
+    def _wants_grad(self):
+        return torch.is_grad_enabled() and self.store.flat.requires_grad
+
+    def gradients(self):
+        """{name: view of d loss / d tensor} after `loss.backward()` (None before)."""
+        g = self.store.flat.grad
+        return None if g is None else {k: self.store.view(k, g) for k in self.store.names()}
 
     def classifier_loss(self, x, y, c, k=100, noise=None):
         """gated_ccvae.py:167-182: log q(y|x) ~ logsumexp_k log q(y|z_c^k, c) - log k  -> [B]."""
@@ -480,9 +538,10 @@ class Learner:
         B = x.shape[0]
         n = self._noise(noise, B, True, k)
         b, lb = self.engine.bufs(B), self._latent_bufs(B)
-        self._gate(n, c_in=as_device_f32(c, self.device))
-        self.engine.encoder_fwd(x, b)
-        self._latent_fwd(B, lb, b, y, n, True, k)
+        with self._fresh_noise():
+            self._gate(n, c_in=as_device_f32(c, self.device))
+            self.engine.encoder_fwd(x, b)
+            self._latent_fwd(B, lb, b, y, n, True, k)
         return lb["terms"][2].clone()
 
     def loss_and_grads(self, x, y, supervised, noise=None, k=100):
@@ -543,8 +602,7 @@ class Learner:
         B = int(x.shape[0])
         x = torch.as_tensor(x)
         u8 = x.dtype == torch.uint8 and getattr(self.engine, "x2", False)
-        # the captured kernels bake the gate temperature in as an argument: it is part of the key
-        key = (B, bool(supervised), int(k), bool(u8), float(self.gating_sampler_temp))
+        key = (B, bool(supervised), int(k), bool(u8))      # (the gate temperature is a device scalar: not part of the key)
         # two captured variants per key with their own static input buffers, used alternately: the host->device copy
         # of a batch goes STRAIGHT into the static input of the variant that is not executing (no staging copy) and
         # overlaps the step in flight
@@ -592,7 +650,7 @@ class Learner:
         return g["loss"], self._c
 
     def _capture(self, key):
-        B, supervised, k, u8, _temperature = key
+        B, supervised, k, u8 = key
         xs = torch.zeros(B, *self.ip_shape, dtype=torch.uint8 if u8 else torch.float32, device=self.device)
         ys = torch.zeros(B, self.y_dim, dtype=torch.int64, device=self.device) if supervised else None
 
@@ -638,9 +696,10 @@ class Learner:
         B = x.shape[0]
         n = self._noise(noise, B, False, 0)
         b, lb = self.engine.bufs(B), self._latent_bufs(B)
-        self._gate(n)
-        self.engine.encoder_fwd(x, b)
-        self._latent_fwd(B, lb, b, None, n, False, 0)
+        with self._fresh_noise():
+            self._gate(n)
+            self.engine.encoder_fwd(x, b)
+            self._latent_fwd(B, lb, b, None, n, False, 0)
         _lib.check(self.lib.gccvae_accuracy_f32(ptr(lb["logits"]), ptr(y), B * self.y_dim, ptr(self._acc),
                                                 _stream()), "accuracy")
         return self._acc[0].clone()
@@ -792,9 +851,7 @@ class Learner:
                 best_val_acc = val_acc
                 self.save_model(param_dir, "best")
             if cfg["gate_type"] == "learnable":
-                self.gating_sampler_temp = self.next_gating_temperature(self.gating_sampler_temp)
-                self._graphs.clear()      # graphs captured with the old temperature are never replayed again
-                self._graph_turn.clear()
+                self.gating_sampler_temp = self.next_gating_temperature(self.gating_sampler_temp)   # (device scalar)
                 logger.info("gating_sampler_temp decayed to: %.4f" % self.gating_sampler_temp)
             history.append(dict(epoch=epoch, sup_loss=None if sup_loss is None else float(sup_loss),
                                 unsup_loss=None if unsup_loss is None else float(unsup_loss), val_acc=float(val_acc),
@@ -814,3 +871,28 @@ class Learner:
 
 def v_mu(learner):
     return learner.store.view("mu")
+
+
+class _ElboFunction(torch.autograd.Function):
+    """sup_loss / unsup_loss as a differentiable function of the flat parameter buffer.  The kernels compute forward and
+    backward in one pass, so `forward` already produces d loss / d parameters (all-reduced in data-parallel runs) and
+    `backward` only scales it by the incoming gradient - what tape.gradient(loss, trainable_variables) returns in
+    gated_ccvae.py:309.  Frozen mu (fixed gate types) gets a zero gradient."""
+
+    @staticmethod
+    def forward(ctx, flat, learner, x, y, supervised, noise, k):
+        with learner._fresh_noise():
+            loss, c = learner._elbo(x, y, supervised, noise, backward=True, k=k)
+            learner._allreduce_grads()
+        grad = learner.store.grad.clone()
+        if not learner.model.mu_trainable:
+            learner.store.view("mu", grad).zero_()
+        ctx.save_for_backward(grad)
+        loss, c = loss.clone(), c.clone()
+        ctx.mark_non_differentiable(c)
+        return loss, c
+
+    @staticmethod
+    def backward(ctx, g_loss, _g_c):
+        (grad,) = ctx.saved_tensors
+        return g_loss * grad, None, None, None, None, None, None
