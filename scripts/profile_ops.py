@@ -11,7 +11,11 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 mu = np.load(os.path.join(ROOT, "data", "gating_matrix_0.2.npy"))
 cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.2, lr=1e-4, gating_init_temp=0.3,
            batch_size=B, init_temp=0.1)
-lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16")
+eopts = {}
+for kv in filter(None, os.environ.get("PROFILE_ENGINE_OPTIONS", "").replace(":", ",").split(",")):
+    k_, v_ = kv.split("=")
+    eopts[k_] = int(v_) if v_.lstrip("-").isdigit() else v_
+lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", engine_options=eopts or None)
 x = torch.rand(B, 64, 64, 3, device="cuda")
 if os.environ.get("PROFILE_U8"):
     x = torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, device="cuda")

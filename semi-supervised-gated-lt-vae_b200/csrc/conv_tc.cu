@@ -64,6 +64,11 @@ struct alignas(64) TapGemmParams {
   float* colsum;        // optional: += column sums of the stored tile (bias gradient of the producer layer)
   int colsum_n, colsum_mod;
   int out_s2d, mask_s2d;   // the output / the mask tensor is stored in s2d block form (bf16 only)
+  int rows_valid;          // rows of the 128-row tile that carry work (TMA box rows); the rest is never stored
+  // S -> L in block form (BLK kernels): the tile's rows are output BLOCKS (i, j) of 2x2 pixels, the N = 4 * blk_cl
+  // columns are (dy, dx, channel); the epilogue scatters the four slots to pixels (2i - 1 + dy, 2j - 1 + dx) of the
+  // OH x OW x OC plane (plain NHWC or s2d storage) and skips the slots outside the plane
+  int blk_cl;
 };
 
 // Pipeline timeline (scripts/timeline_probe.py).  Compiled in only with -DGCCVAE_TIMELINE (libgccvae_tl.so): even with
@@ -121,7 +126,7 @@ __device__ __forceinline__ void warp_colsum16(const float (&v)[16], float* s_col
   if ((lane & 1) == 0 && col < n_valid_cols) atomicAdd(s_col + idx_base + col, w1);
 }
 
-template <bool COLSUM>
+template <bool COLSUM, bool BLK = false>
 __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_constant__ TapGemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -186,7 +191,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       uint32_t ph = 0;
       long long prod_wait = 0;
       const long long tp0 = clock64();
-      const uint32_t stage_tx = (uint32_t)(p.tps * (a_bytes + b_bytes));
+      const uint32_t stage_tx = (uint32_t)(p.tps * (p.rows_valid * p.KC * 2 + b_bytes));
       for (int item = item_beg; item < item_end; ++item) {
         const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
         const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
@@ -297,7 +302,92 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
       const int slab0 = slab * p.N;
       const int n = n0 + dn, y = h0 + dy, x = w0 + dx;
-      const bool valid = n < p.batch;
+      const bool valid = n < p.batch && m < p.rows_valid;
+      if constexpr (BLK) {
+        // ---- block-form S -> L epilogue: row = block (y, x) of image n, columns = 4 slots x blk_cl channels ----
+        const int CLb = p.blk_cl;
+        const uint32_t tacc = tmem_base + (uint32_t)as * acc_cols + ((uint32_t)(q * 32) << 16);
+        // pixel index of each slot (in units of OC channels), or -1 outside the plane / for rows without work
+        long long spix[4];
+#pragma unroll
+        for (int sl = 0; sl < 4; ++sl) {
+          const int py = 2 * y - 1 + (sl >> 1), px = 2 * x - 1 + (sl & 1);
+          const bool in = valid && py >= 0 && py < p.OH && px >= 0 && px < p.OW;
+          spix[sl] = in ? (long long)(((size_t)n * p.OH + (size_t)py) * p.OW + px) : -1;
+        }
+        // with s2d storage the four slots of a block are consecutive: block index * 4 + slot
+        const long long blk4 = (long long)((((size_t)n * ((p.OH >> 1) + 1) + (size_t)y) * ((p.OW >> 1) + 1) + x) * 4);
+        // the ReLU mask of the whole row (N / 16 chunks of 32 bytes) is fetched before waiting for the accumulator
+        uint32_t mk[8][8];
+        const bool use_mask = p.mask != nullptr;
+        if (use_mask) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const int c0 = ch * 16;
+            if (c0 >= p.N) break;
+            const int sl = c0 / CLb;
+            if (spix[sl] < 0) continue;
+            const long long mp = p.mask_s2d ? blk4 + sl : spix[sl];
+            ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + mp * p.OC + (c0 - sl * CLb), mk[ch]);
+          }
+        }
+        mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
+        tc_fence_after();
+        const uint32_t s_bias_u32 = smem_u32(s_bias);
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+          if (half * 128 >= p.N) break;
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const int c0 = half * 128 + ch * 16;
+            uint32_t r[16];
+            tmem_ld16(tacc + (uint32_t)c0, r);
+            tmem_ld_wait();
+            if (c0 + 16 >= p.N) {  // accumulator fully read: hand the TMEM stage back to the MMA warp
+              tc_fence_before();
+              if (lane == 0) mbar_arrive(&tempty[as]);
+            }
+            const int sl = c0 / CLb, cc = c0 - sl * CLb;
+            if (spix[sl] < 0) continue;
+            const uint32_t bsrc = s_bias_u32 + (uint32_t)(cc * 4);
+            float v[16];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 t = lds_f4(bsrc + 16u * i);
+              v[4 * i] = __uint_as_float(r[4 * i]) + t.x;
+              v[4 * i + 1] = __uint_as_float(r[4 * i + 1]) + t.y;
+              v[4 * i + 2] = __uint_as_float(r[4 * i + 2]) + t.z;
+              v[4 * i + 3] = __uint_as_float(r[4 * i + 3]) + t.w;
+            }
+            if (p.act == GCCVAE_ACT_RELU) {
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = fmaxf(v[i], 0.0f);
+            }
+            if (use_mask) {
+              uint32_t mw[8];
+              if (half == 0) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) mw[i] = mk[ch][i];
+              } else {   // N = 256: the second half of the row's mask is fetched here
+                const long long mp = p.mask_s2d ? blk4 + sl : spix[sl];
+                ld_global_nc_256(reinterpret_cast<const __nv_bfloat16*>(p.mask) + mp * p.OC + cc, mw);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const uint32_t lo = mw[i] & 0xffffu, hi = mw[i] >> 16;
+                if (!(lo != 0 && lo < 0x8000u)) v[2 * i] = 0.0f;
+                if (!(hi != 0 && hi < 0x8000u)) v[2 * i + 1] = 0.0f;
+              }
+            }
+            const long long op = p.out_s2d ? blk4 + sl : spix[sl];
+            uint32_t w[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) w[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            st_global_256(reinterpret_cast<__nv_bfloat16*>(p.out) + op * p.OC + cc, w);
+          }
+        }
+        continue;
+      }
       const int oyy = y * p.oys + p.oy0[phase_id], oxx = x * p.oxs + p.ox0[phase_id];
       const size_t opix_lin = ((size_t)n * p.OH + (size_t)oyy) * p.OW + oxx;
       const size_t opix_s2d = (p.out_s2d | p.mask_s2d) ? s2d_slot(n, oyy, oxx, p.OH, p.OW) : 0;
@@ -1157,6 +1247,17 @@ __global__ void __launch_bounds__(256) pack_jobs_kernel(const __grid_constant__ 
       const int kh = 2 * (t >> 1) + (sub >> 1), kw = 2 * (t & 1) + (sub & 1);
       out[i] = __float2bfloat16(cs < CS ? W[((size_t)(kh * 4 + kw) * CL + c) * CS + cs] : 0.0f);
     }
+  } else if (jb.kind == 10) {
+    // block-form S -> L packing of a k4/s2/p1 kernel W[kh,kw,CL,CS]: out[(dy,dx,cl)][(a,b,cs)], kh = 2a+dy, kw = 2b+dx
+    // (B operand of the 4-tap S -> L GEMM whose rows are output blocks: gccvae_sl_blk_bf16; N = 4 CL, K = 4 CS)
+    const int K = 4 * CS;
+    const long long n = (long long)4 * CL * K;
+    for (long long i = i0; i < n; i += stride) {
+      const int row = (int)(i / K), k = (int)(i % K);
+      const int sub = row / CL, cl = row % CL, t = k / CS, cs = k % CS;
+      const int kh = 2 * (t >> 1) + (sub >> 1), kw = 2 * (t & 1) + (sub & 1);
+      out[i] = __float2bfloat16(W[((size_t)(kh * 4 + kw) * CL + cl) * CS + cs]);
+    }
   } else if (jb.kind == 7 || jb.kind == 8) {
     // x2 (space-to-depth) packing of a 3-channel k4/s2/p1 kernel W[kh,kw,3,CS]:
     //  kind 7: out[cs][(a,b)][(dy,dx,c4)]   (B operand of the 4-tap L->S GEMM: conv1 forward, conv5t dgrad)
@@ -1908,6 +2009,9 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
                     (p.colsum_mod >= (1 << 29) || p.colsum_mod % 16 == 0),
                 "%s: unsupported column-sum shape (n=%d mod=%d)", name, p.colsum_n, p.colsum_mod);
   }
+  if (p.rows_valid <= 0) p.rows_valid = 128;
+  const bool blk = p.blk_cl > 0;
+  GCC_REQUIRE(!blk || p.colsum == nullptr, "%s: no fused column sums in block form", name);
   const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
   // Persistent CTAs, `per_sm` of them per SM (their epilogues and issue threads overlap).  The single MMA-issuing
   // thread pays ~400 cycles per pipeline stage (barrier wait, fences, commit) and ~50 per MMA, so a stage carries
@@ -1943,24 +2047,26 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(tapgemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
   GCC_REQUIRE(smem <= 200 * 1024, "%s: %zu bytes of shared memory", name, smem);
   if (p.n_slabs < 1) p.n_slabs = 1;
   if (p.bias_mod < 1 || p.bias == nullptr) p.bias_mod = 1 << 30;
   if (p.bias_n < 1) p.bias_n = p.n_store;
-  GCC_REQUIRE(p.bias_mod >= p.n_store || p.bias_mod % p.N == 0, "%s: bias_mod %d incompatible with N slab %d", name,
+  GCC_REQUIRE(blk || p.bias_mod >= p.n_store || p.bias_mod % p.N == 0, "%s: bias_mod %d incompatible with N slab %d", name,
               p.bias_mod, p.N);
   GCC_REQUIRE(p.bias == nullptr || ((uintptr_t)p.bias % 16) == 0, "%s: bias must be 16-byte aligned", name);
   p.phases = phases;
   p.total_items = groups * p.tiles_w * p.tiles_h * p.n_slabs * phases;
   // never launch more persistent CTAs than are resident at once: a second wave would serialise behind the first.
   // Residency limits: registers (64K per SM), shared memory (227 KB per SM, 1 KB reserved per CTA), TMEM (above).
-  static int regs_per_cta[2] = {0, 0};
-  const int ki = p.colsum != nullptr ? 1 : 0;
+  static int regs_per_cta[3] = {0, 0, 0};
+  const int ki = blk ? 2 : (p.colsum != nullptr ? 1 : 0);
   if (regs_per_cta[ki] == 0) {
     cudaFuncAttributes fa;
-    if (ki) GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<true>));
+    if (ki == 2) GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<false, true>));
+    else if (ki) GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<true>));
     else GCC_CUDA(cudaFuncGetAttributes(&fa, tapgemm_kernel<false>));
     const int per_warp = ((fa.numRegs + 7) / 8) * 8 * 32;
     regs_per_cta[ki] = per_warp * (TG_THREADS / 32);
@@ -1980,7 +2086,8 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
     ctas = (p.total_items + per_cta - 1) / per_cta;
   }
   dim3 grid(ctas, 1, 1);
-  if (p.colsum != nullptr) GCC_CUDA(launch_pdl(tapgemm_kernel<true>, grid, TG_THREADS, smem, st, p));
+  if (blk) GCC_CUDA(launch_pdl(tapgemm_kernel<false, true>, grid, TG_THREADS, smem, st, p));
+  else if (p.colsum != nullptr) GCC_CUDA(launch_pdl(tapgemm_kernel<true>, grid, TG_THREADS, smem, st, p));
   else GCC_CUDA(launch_pdl(tapgemm_kernel<false>, grid, TG_THREADS, smem, st, p));
   GCC_CHECK_LAUNCH(name);
   return GCCVAE_OK;
@@ -2353,6 +2460,43 @@ extern "C" int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void
   return launch_tapgemm(p, groups, 1, (cudaStream_t)stream, "tap4_ls");
 }
 
+// S -> L of a k4/s2/p1 layer (Conv2DTranspose forward / Conv2D dgrad) in BLOCK form:
+//   blocks[n, i, j, (dy,dx), cl] = sum_{a,b in {0,1}} sum_cs S[n, i - a, j - b, cs] * W[2a + dy, 2b + dx, cl, cs]
+// (oracle/block_forms.py: convT_k4s2_to_blocks) - a 2x2-tap stride-1 gather over S with N = 4 CL output columns, so one
+// 128-row tile produces 4 x 128 output pixels from 4 x (128 x CS) operand bytes, against 16 (phase, tap) operand tiles
+// per 128 pixels in the phase formulation.  The tile's rows are the (WS + 1) blocks of one block row of `bn` images;
+// the epilogue writes each slot to its pixel of L (NHWC, or s2d storage with GCCVAE_OUT_S2D) and drops the slots that
+// fall outside the plane.  Wp = pack kind 10: [(dy,dx,cl)][(a,b,cs)] bf16.
+extern "C" int gccvae_sl_blk_supported(int HS, int WS, int CS, int CL) {
+  return (WS + 1 <= 128 && (CS == 32 || CS == 64 || CS == 128) && (CL == 32 || CL == 64) && HS >= 1) ? 1 : 0;
+}
+extern "C" int gccvae_sl_blk_bf16(int batch, int HS, int WS, int CS, const void* S, const void* Wp, int CL, const float* bias,
+                                  int act, const void* mask, void* L, void* stream) {
+  GCC_REQUIRE(S && Wp && L && batch > 0, "sl_blk: null pointer");
+  GCC_REQUIRE(gccvae_sl_blk_supported(HS, WS, CS, CL), "sl_blk: unsupported shape %dx%dx%d -> CL %d", HS, WS, CS, CL);
+  const int kc = CS >= 64 ? 64 : CS;
+  const int bw = WS + 1, bn = 128 / bw;
+  TapGemmParams p;
+  memset(&p, 0, sizeof(p));
+  int rc;
+  if ((rc = encode_act_map(&p.tmA, S, batch, HS, WS, CS, kc, bw, 1, bn, 1))) return rc;
+  if ((rc = encode_mat_map(&p.tmB, Wp, 4LL * CL, 4LL * CS, kc, 4 * CL))) return rc;
+  p.num_taps = 4; p.chunks = CS / kc; p.a_scale = 1; p.BW = bw; p.BH = 1; p.BN = bn;
+  p.tiles_w = 1; p.tiles_h = HS + 1;
+  for (int t = 0; t < 4; ++t) { p.a_dh[0][t] = (short)(-(t >> 1)); p.a_dw[0][t] = (short)(-(t & 1)); }
+  p.b_tap_stride = CS;
+  p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
+  p.N = 4 * CL; p.n_store = 4 * CL; p.n_slabs = 1;
+  p.rows_valid = bw * bn; p.blk_cl = CL;
+  p.out = L; p.mask = mask; p.bias = bias; p.bias_mod = CL; p.bias_n = CL;
+  p.act = act & ~GCCVAE_LAYOUT_FLAGS; p.out_f32 = 0;
+  p.out_s2d = (act & GCCVAE_OUT_S2D) ? 1 : 0; p.mask_s2d = (act & GCCVAE_MASK_S2D) ? 1 : 0;
+  p.OH = 2 * HS; p.OW = 2 * WS; p.OC = CL; p.oys = p.oxs = 1;
+  p.batch = batch;
+  const int groups = (batch + bn - 1) / bn;
+  return launch_tapgemm(p, groups, 1, (cudaStream_t)stream, "sl_blk");
+}
+
 // dW[(kh,kw,c<3), cs] (fp32, Keras layout) += sum_pix gather4(in2)[pix, (a,b,dy,dx,c4)] * S[pix, cs]
 // in2 = [B,33,33,16] bf16 x2 blocks of a 3-channel 64x64 tensor, S = [B,32,32,CS] bf16.
 extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream) {
@@ -2640,7 +2784,7 @@ extern "C" int gccvae_pack_jobs_bf16(const gccvae_pack_job* jobs, int n_jobs, vo
   PackJobs pj;
   memset(&pj, 0, sizeof(pj));
   for (int i = 0; i < n_jobs; ++i) {
-    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 9, "pack_jobs: bad job %d", i);
+    GCC_REQUIRE(jobs[i].W && jobs[i].out && jobs[i].kind >= 0 && jobs[i].kind <= 10, "pack_jobs: bad job %d", i);
     pj.j[i] = jobs[i];
   }
   GCC_CUDA(launch_pdl_k(pack_jobs_kernel, dim3(64, n_jobs, 1), dim3(256), 0, (cudaStream_t)stream, pj));

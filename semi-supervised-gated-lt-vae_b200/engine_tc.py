@@ -42,7 +42,8 @@ S2D_TENSORS = ["enc.conv1.out", "enc.conv2.out", "enc.conv3.out", "dec.conv4t.do
 class EngineTC(Engine):
     precision = "bf16"
 
-    def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0):
+    def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0, tail_split=False,
+                 sl_block_form=False):
         super().__init__(store)
         # scheduling of the weight-gradient kernels (they feed only the optimiser): the encoder's alternate between
         # `wgrad_streams` side streams so that a layer's weight gradient starts when its operand is ready instead of
@@ -50,6 +51,11 @@ class EngineTC(Engine):
         # weight gradients, gate backward) go to `post_chain_stream` ("side" = the weight-gradient stream, "side2" =
         # the bias-gradient stream).  Same-box A/B, ms per sup+unsup pair (profiles/r02_ab_log.txt): 1 stream / side
         # 1.344, 2 streams / side 1.336, 2 streams / side2 1.351, 1 stream / side2 1.375
+        # the step ends with conv2's dgrad -> conv1's weight / bias gradient, a strict chain of two HBM-bound kernels.
+        # `tail_split`: both run on the two halves of the batch, so the second half's dgrad overlaps the first half's
+        # weight gradient (tensors are contiguous per image: a half is a pointer offset).  Measured +2 % per step on
+        # B200 (the half-batch launches are less efficient than the overlap gains): off by default.
+        self.tail_split = bool(tail_split)
         self.wgrad_streams = int(wgrad_streams)
         self.post_chain_stream = post_chain_stream
         self.side_b = None
@@ -82,6 +88,17 @@ class EngineTC(Engine):
         for name in S2D_LAYERS:
             _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
             self.wp[name + ".s2d"] = z16(((CS + 15) // 16 * 16) * 16 * CL)
+        # S -> L direction of the six k4/s2/p1 layers (convT forward, conv dgrad) in block form: rows = output blocks of
+        # 2x2 pixels, N = 4 C_L, 4 taps over S (gccvae_sl_blk_bf16).  Parity-tested, but its 128 / 256-column epilogue on 4
+        # warps is slower than the halo kernel's 8 epilogue warps (conv2 dgrad 65 vs 49 us, conv4t forward 43 vs 39 us in
+        # the eager per-op profile; +7 % per step): off by default, the halo / 4-phase kernels stay the product path.
+        self.blk = {}
+        if sl_block_form:
+            for name in S2D_LAYERS:
+                _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
+                if lib.gccvae_sl_blk_supported(HS, WS, CS, CL):
+                    self.blk[name] = (HS, WS, CS, CL)
+                    self.wp[name + ".blk"] = z16(4 * CL * 4 * CS)
         # 45-wide dense layers, zero-padded to tensor-core widths (pad regions stay zero forever)
         self.wp["heads.ls"] = z16(96, 256)       # rows 0..44 = W_loc^T, 48..92 = W_std^T
         self.wp["heads.sl"] = z16(256, 96)
@@ -123,11 +140,16 @@ class EngineTC(Engine):
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
                 if name not in S2D_LAYERS:     # the s2d layers use the kind-9 operand instead
                     J(0, k * k, CL, CS, v(name + ".w"), self.wp[name + ".ls"])
-                J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
+                if name not in self.blk:       # (the block-form layers use the kind-10 operand instead)
+                    J(2 if (HS == 1 and WS == 1) else 1, k * k, CL, CS, v(name + ".w"), self.wp[name + ".sl"])
             J(1, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.sl"])
             for name in self.halo:
+                if name in self.blk:
+                    continue
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
                 J(6, 16, CL, CS, v(name + ".w"), self.wp[name + ".sl9"])
+            for name, (HS, WS, CS, CL) in self.blk.items():
+                J(10, 16, CL, CS, v(name + ".w"), self.wp[name + ".blk"])
             for name in S2D_LAYERS:
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
                 J(9, 16, CL, CS, v(name + ".w"), self.wp[name + ".s2d"])
@@ -226,7 +248,12 @@ class EngineTC(Engine):
         st = _stream()
         if mask_s2d:
             act = act | MASK_S2D
-        if name in self.halo:
+        if name in self.blk and out_f32 == 0:
+            HS, WS, CS, CL = self.blk[name]
+            W = self.wp[name + ".blk"]
+            self._run(what, (S, mask, L), lambda: self.lib.gccvae_sl_blk_bf16(
+                geom.batch, HS, WS, CS, ptr(S), ptr(W), CL, ptr(bias), act, ptr(mask), ptr(L), st))
+        elif name in self.halo:
             W = self.wp[name + ".sl9"]
             self._run(what, (S, mask, L), lambda: self.lib.gccvae_sl_halo_bf16(
                 C.byref(geom), ptr(S), ptr(W), ptr(bias), act, ptr(mask), ptr(L), out_f32, st))
@@ -498,7 +525,9 @@ class EngineTC(Engine):
             if hook is not None and self.side is not None:
                 ev = torch.cuda.Event()
                 ev.record(torch.cuda.current_stream())     # everything the main stream has produced so far
-            self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad", mask_s2d=s2d_l)
+            split = self.tail_split and name == "enc.conv2" and B % 2 == 0 and B >= 128 and self.side is not None
+            if not split:
+                self._sl(name, geom, dout, None, ACT_NONE, xin, dxin, 0, name + " dgrad", mask_s2d=s2d_l)
             if hook is not None:
                 self.tail_hook = None
                 if ev is not None:     # under this dgrad: after all earlier weight / bias gradients, not after it
@@ -515,6 +544,22 @@ class EngineTC(Engine):
                 else:
                     hook()
         dh1 = b["enc.conv1.dout"]
+        if split:
+            # last layer pair in two halves of the batch: dgrad(h0), then dgrad(h1) on the main stream while conv1's
+            # weight / bias gradient of h0 runs on the side streams, then those of h1
+            h = B // 2
+            geom_h = make_geom(_ENC["enc.conv2"], h)
+            dout2, mask2, X2 = b["enc.conv2.dout"], b["enc.conv1.out"], b["X2"]
+            for i in (0, 1):
+                sl = slice(i * h, (i + 1) * h)
+                self._sl("enc.conv2", geom_h, dout2[sl], None, ACT_NONE, mask2[sl], dh1[sl], 0, "enc.conv2 dgrad", mask_s2d=True)
+                def wg1(sl=sl):
+                    self._bias("enc.conv1", 32, dh1[sl])
+                    self._run("enc.conv1 wgrad", (X2[sl], dh1[sl]), lambda: lib.gccvae_tap4_wg_bf16(
+                        h, ptr(X2[sl]), ptr(dh1[sl]), 32, ptr(g_("enc.conv1.w")), _stream()))
+                self._side(wg1)
+            self.join_side()
+            return
         def wg1():
             self._bias("enc.conv1", 32, dh1)
             self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(

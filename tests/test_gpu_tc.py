@@ -121,6 +121,20 @@ def _run_tc(direction, geom_t, batch, act, use_mask, use_bias=True):
         got2 = out2.float().cpu().double()
         assert torch.isfinite(got2).all(), "halo output has NaN/unwritten elements"
         err = max(err, float((got2 - want).abs().max() / want.abs().max()))
+    if direction == "SL" and k == 4 and s == 2 and p == 1 and lib.gccvae_sl_blk_supported(HS, WS, CS, CL):
+        # ... and in block form (4-tap gather over S, rows = output blocks, N = 4 CL; pack kind 10), NHWC output
+        wb = torch.zeros(4 * CL * 4 * CS, dtype=torch.bfloat16, device=d)
+        job = (L.PackJob * 1)(L.PackJob(10, 16, CL, CS, L.ptr(Wd), L.ptr(wb), 0, 0, 0, 0, 0, 0))
+        L.check(lib.gccvae_pack_jobs_bf16(job, 1, _stream()))
+        out3 = torch.full(want.shape, float("nan"), dtype=torch.bfloat16, device=d)
+        L.check(lib.gccvae_sl_blk_bf16(batch, HS, WS, CS, L.ptr(Xd), L.ptr(wb), CL, L.ptr(bd), act, L.ptr(md), L.ptr(out3),
+                                       _stream()))
+        torch.cuda.synchronize()
+        got3 = out3.float().cpu().double()
+        assert torch.isfinite(got3).all(), "block-form output has NaN/unwritten elements"
+        e3 = float((got3 - want).abs().max() / want.abs().max())
+        assert e3 < 2e-2, ("block form", e3)
+        err = max(err, e3)
     return err
 
 
