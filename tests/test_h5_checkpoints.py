@@ -139,6 +139,27 @@ def test_writer_round_trips_the_reference_checkpoint(tmp_path, stem):
     assert fa.visit("/") == fb.visit("/") and fa.keys("/") == fb.keys("/")
 
 
+@pytest.mark.parametrize("stem", ["encoder_model_best", "classifier_best"])
+def test_written_file_opens_with_libhdf5_when_h5py_is_available(tmp_path, stem):
+    """interoperability of `write_keras_weights` with the real HDF5 library (what Keras' load_weights uses).  h5py is
+    not installed in the build image, so this is skipped there: until it has run somewhere, written checkpoints are
+    known to be readable by this repo's reader only (README)."""
+    h5py = pytest.importorskip("h5py")
+    from gccvae_b200.h5lite import write_keras_weights
+    src = os.path.join(CKPT, stem + ".h5")
+    out = str(tmp_path / (stem + ".h5"))
+    write_keras_weights(out, _layers_of(src))
+    with h5py.File(src, "r") as fa, h5py.File(out, "r") as fb:
+        assert list(fa.attrs["layer_names"]) == list(fb.attrs["layer_names"])
+        for ln in fa.attrs["layer_names"]:
+            ln = ln.decode() if isinstance(ln, bytes) else ln
+            wa, wb = list(fa[ln].attrs["weight_names"]), list(fb[ln].attrs["weight_names"])
+            assert wa == wb
+            for wn in wa:
+                wn = wn.decode() if isinstance(wn, bytes) else wn
+                assert np.array_equal(fa[ln][wn][()], fb[ln][wn][()])
+
+
 def test_written_file_has_the_reference_files_on_disk_structure(tmp_path):
     """superblock fields, node sizes and signatures equal those of the reference's files (what libhdf5 wrote)."""
     import struct
