@@ -326,7 +326,7 @@ def run_ours(args, rank, world, local_rank):
                 "bytes_per_launch": nbytes, "ms_per_launch": ms, "launches_per_step": n,
                 "share_of_profiled_step": ms * n / tot, "traffic": None}
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01d_traffic.json")))
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r02_traffic.json")))
             roof["traffic"] = traffic.get(name)
         except Exception:
             pass

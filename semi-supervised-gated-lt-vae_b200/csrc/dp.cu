@@ -20,7 +20,7 @@
 //   word q (< 16)  arrival flag written by rank q,   word 16 local block-arrival counter (reset by the last block),
 //   word 17 local gate,   word 18 number of completed calls,   word 19 exit ticket,   word 20 error flag.
 // Block 0 of every rank signals all peers (st.release.sys) and waits for all of them (ld.acquire.sys); the other
-// blocks wait at the local gate.  All waits are bounded (~4 s): a lost peer traps instead of hanging the GPU.
+// blocks wait at the local gate.  All waits are bounded (~20 s): a lost peer traps instead of hanging the GPU.
 #include <string.h>
 
 #include "common.cuh"
@@ -69,7 +69,7 @@ __device__ __forceinline__ void wait_ge(const uint32_t* p, uint32_t want, uint32
   for (uint32_t spin = 0;; ++spin) {
     const uint32_t v = SYS ? ld_acquire_sys(p) : ld_acquire_gpu(p);
     if ((int32_t)(v - want) >= 0) return;
-    if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 4000000000ull) {
+    if ((spin & 1023u) == 1023u && globaltimer_ns() - t0 > 20000000000ull) {
       *err = 1u;
       printf("gccvae: data-parallel barrier timed out (block %d thread %d: have %u want %u)\n", blockIdx.x, threadIdx.x, v,
              want);

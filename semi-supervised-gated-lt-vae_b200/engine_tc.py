@@ -128,13 +128,15 @@ class EngineTC(Engine):
         self.marks = []
 
     # ---- packed weights ---------------------------------------------------------------------------------
-    def pack_weights(self):
-        """refresh every packed bf16 operand from the fp32 master weights: one kernel launch."""
+    def pack_weights(self, part=None):
+        """refresh every packed bf16 operand from the fp32 master weights: one kernel launch - or two (`part` 0: the
+        first layer's operand, which is all conv1's forward waits for; `part` 1: the rest, under conv1's forward)."""
         if self._jobs is None:
             v = self.store.view
             jobs = []
             J = lambda kind, taps, CL, CS, W, out, sr=0, sk=0, ld=0, ro=0, co=0: jobs.append(
                 _lib.PackJob(kind, taps, CL, CS, ptr(W), ptr(out), sr, sk, ld, ro, co, 0))
+            J(7, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.x2"])       # job 0: see `part`
             for name in TC_ENC + TC_DEC:
                 lay = _ENC.get(name) or _DEC[name]
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = lay
@@ -153,7 +155,6 @@ class EngineTC(Engine):
             for name in S2D_LAYERS:
                 _, _, (HL, WL, CL), (HS, WS, CS), k, s_, p_, _ = (_ENC.get(name) or _DEC[name])
                 J(9, 16, CL, CS, v(name + ".w"), self.wp[name + ".s2d"])
-            J(7, 16, 3, 32, v("enc.conv1.w"), self.wp["enc.conv1.x2"])
             J(7, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2"])
             J(8, 16, 3, 32, v("dec.conv5t.w"), self.wp["dec.conv5t.x2t"])
             # kind 4/5: out[(ro + r) * ld + co + k] = W[r * sr + k * sk],  r < taps(R), k < CL(K)
@@ -165,9 +166,14 @@ class EngineTC(Engine):
             J(4, 45, 45, 0, v("dec.fc1.w"), self.wp["fc1.sl"], 45, 1, 64)
             J(4, 2048, 45, 0, v("dec.conv1t.w"), self.wp["conv1t.sl"], 45, 1, 64)
             J(4, 45, 2048, 0, v("dec.conv1t.w"), self.wp["conv1t.ls"], 1, 45, 2048)
-            arr = (_lib.PackJob * len(jobs))(*jobs)
-            self._jobs = arr
-        self._run("pack_weights", (), lambda: self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()))
+            self._jobs = (_lib.PackJob * len(jobs))(*jobs)
+            self._jobs_rest = (_lib.PackJob * (len(jobs) - 1))(*jobs[1:])
+        if part is None:
+            self._run("pack_weights", (), lambda: self.lib.gccvae_pack_jobs_bf16(self._jobs, len(self._jobs), _stream()))
+        elif part == 0:
+            self._run("pack_weights", (), lambda: self.lib.gccvae_pack_jobs_bf16(self._jobs, 1, _stream()))
+        else:
+            self._run("pack_weights", (), lambda: self.lib.gccvae_pack_jobs_bf16(self._jobs_rest, len(self._jobs_rest), _stream()))
 
     # ---- buffers -----------------------------------------------------------------------------------------
     def _alloc(self, B):
@@ -353,7 +359,10 @@ class EngineTC(Engine):
         main = torch.cuda.current_stream()
         self.side.wait_stream(main)
         with torch.cuda.stream(self.side):
-            self.pack_weights()
+            self.pack_weights(part=0)
+            self._ev_pack0 = torch.cuda.Event()
+            self._ev_pack0.record(self.side)
+            self.pack_weights(part=1)
         self.side2.wait_stream(main)
         with torch.cuda.stream(self.side2):
             u8 = int(x.dtype == torch.uint8)
@@ -367,8 +376,10 @@ class EngineTC(Engine):
         B = x.shape[0]
         lib, st, v = self.lib, _stream(), self.store.view
         begun, self._begun = getattr(self, "_begun", False), False
-        if begun:
-            self.join_side()
+        if begun:      # conv1 needs the image blocks and its own operand; the other operands land under its forward
+            main = torch.cuda.current_stream()
+            main.wait_event(self._ev_pack0)
+            main.wait_stream(self.side2)
         else:
             self._log_pxz_ready = False
             self.pack_weights()
@@ -377,6 +388,8 @@ class EngineTC(Engine):
         self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU | OUT_S2D, None,
             ptr(b["enc.conv1.out"]), st))
+        if begun:
+            self.join_side()
         h = b["enc.conv1.out"]
         for name in TC_ENC:
             if name in S2D_LAYERS:
