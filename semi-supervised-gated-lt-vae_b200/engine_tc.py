@@ -118,6 +118,9 @@ class EngineTC(Engine):
         self.prof = None   # list of (op, start event, end event, algorithmic bytes) while profiling
         # called once per backward pass when every gradient except the first layer's is complete or queued: the
         # Learner hangs the bulk of the Adam update here, so that only the first layer's update follows the last dgrad
+        # True while a step is issued whose image blocks b["X2"] were produced by the caller (Learner's graph replay does
+        # the x2 transform on the copy stream, one step ahead)
+        self.x2_ready = False
         self.tail_hook = None
         self.tail_hook_layer = TC_ENC[0]   # ... called when THIS layer's weight gradient has been issued (its dgrad follows)
         self.side3 = None          # its own stream: the first layer's weight / bias gradients must not queue behind it
@@ -366,7 +369,8 @@ class EngineTC(Engine):
         self.side2.wait_stream(main)
         with torch.cuda.stream(self.side2):
             u8 = int(x.dtype == torch.uint8)
-            self._run("prep_x2", (x, b["X2"]), lambda: self.lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), _stream()))
+            if not self.x2_ready:     # (a replayed step gets its image blocks from the copy stream, ahead of the replay)
+                self._run("prep_x2", (x, b["X2"]), lambda: self.lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), _stream()))
             if log_pxz is not None:
                 _lib.check(self.lib.gccvae_fill_f32(ptr(log_pxz), B, -12288.0 * 0.6931471805599453, _stream()), "fill")
         self._begun = True
@@ -384,7 +388,8 @@ class EngineTC(Engine):
             self._log_pxz_ready = False
             self.pack_weights()
             u8 = int(x.dtype == torch.uint8)
-            self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
+            if not self.x2_ready:
+                self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
         self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU | OUT_S2D, None,
             ptr(b["enc.conv1.out"]), st))

@@ -550,14 +550,17 @@ class Learner:
         self._allreduce_grads()      # the loss rides in the tail slot of the gradient buffer
         return loss.clone(), c.clone()
 
-    def train_step(self, x, y, supervised, noise=None, k=100):
+    def train_step(self, x, y, supervised, noise=None, k=100, inputs_ready=False):
         """gated_ccvae.py:302-311: loss, gradients of all trainable variables, Adam update -> (loss, c), both fresh
-        for the next RING steps (rows of the result ring the publishing Adam launch fills)."""
+        for the next RING steps (rows of the result ring the publishing Adam launch fills).
+        `inputs_ready` (graph replay only): the caller promises that DEVICE tensors x / y are complete - nothing that
+        writes them is pending on any stream - so their staging (copy into the graph's input buffers, x2 transform) may
+        run under the step in flight instead of behind it.  Host tensors are always staged that way."""
         if self._t_host is None:
             self._t_host = self.optimiser.iterations
         slot = self._ring[self._t_host % self.RING]
         if self.use_graphs and noise is None:
-            self._train_step_graphed(x, y, supervised, k)
+            self._train_step_graphed(x, y, supervised, k, inputs_ready)
         else:
             self._step_body(x, y, supervised, noise, k)
         self._t_host += 1
@@ -598,7 +601,7 @@ class Learner:
         return loss, c
 
     # ---- CUDA-graph replay of the step (the reference's @tf.function, gated_ccvae.py:302) -------------------------
-    def _train_step_graphed(self, x, y, supervised, k):
+    def _train_step_graphed(self, x, y, supervised, k, inputs_ready=False):
         B = int(x.shape[0])
         x = torch.as_tensor(x)
         u8 = x.dtype == torch.uint8 and getattr(self.engine, "x2", False)
@@ -615,16 +618,24 @@ class Learner:
         if x.dtype == torch.uint8 and not u8:
             x = x.to(self.device, non_blocking=True).to(torch.float32) / 255.0
         main = torch.cuda.current_stream()
-        if x.device.type == "cpu":
+        if x.device.type == "cpu" or g["x2"] is not None:
+            # inputs travel on the copy stream: the copy of a host batch - or of a resident one - into this variant's static
+            # buffers and (bf16 engine) the x2 block transform of the image run AHEAD of the replay, under the step in flight
             if self._copy_stream is None:
                 self._copy_stream = torch.cuda.Stream(device=self.device)
             cs = self._copy_stream
             if g.get("done") is not None:
                 cs.wait_event(g["done"])          # the previous replay of this variant no longer reads its inputs
+            else:
+                cs.wait_stream(main)
+            if x.device.type != "cpu" and not inputs_ready:
+                cs.wait_stream(main)              # a resident batch may still be in production on the caller's stream
             with torch.cuda.stream(cs):
                 g["x"].copy_(x, non_blocking=True)
                 if supervised:
                     g["y"].copy_(torch.as_tensor(y), non_blocking=True)
+                if g["x2"] is not None:
+                    _lib.check(self.lib.gccvae_prep_x2_bf16(ptr(g["x"]), int(u8), B, ptr(g["x2"]), cs.cuda_stream), "prep_x2")
                 ready = torch.cuda.Event()
                 ready.record(cs)
             main.wait_event(ready)
@@ -653,6 +664,11 @@ class Learner:
         B, supervised, k, u8 = key
         xs = torch.zeros(B, *self.ip_shape, dtype=torch.uint8 if u8 else torch.float32, device=self.device)
         ys = torch.zeros(B, self.y_dim, dtype=torch.int64, device=self.device) if supervised else None
+        # bf16 engine: this variant's own image blocks, filled ahead of each replay on the copy stream (_train_step_graphed)
+        x2 = bufs = None
+        if getattr(self.engine, "x2", False):
+            bufs = self.engine.bufs(B)
+            x2 = torch.zeros_like(bufs["X2"])
 
         def body():
             if getattr(self.engine, "marks", None) is not None:
@@ -667,6 +683,8 @@ class Learner:
         # warm-up on a side stream (first-use attribute calls, buffer allocation), state restored afterwards
         saved = (self.store.flat.clone(), self.optimiser.m.clone(), self.optimiser.v.clone(),
                  self.optimiser.step_dev.clone())
+        if x2 is not None:
+            saved_x2, bufs["X2"], self.engine.x2_ready = bufs["X2"], x2, True
         side = torch.cuda.Stream(device=self.device)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
@@ -688,7 +706,9 @@ class Learner:
         for dst, src in zip((self.store.flat, self.optimiser.m, self.optimiser.v, self.optimiser.step_dev), saved):
             dst.copy_(src)
         self._grads_clean = True         # nothing ran during the capture: the buffer is as clean as before it
-        return dict(graph=graph, x=xs, y=ys, loss=loss, launches=launches, done=None, clean=fused)
+        if x2 is not None:
+            bufs["X2"], self.engine.x2_ready = saved_x2, False
+        return dict(graph=graph, x=xs, y=ys, x2=x2, loss=loss, launches=launches, done=None, clean=fused)
 
     def classifier_accuracy(self, x, y, noise=None):
         """gated_ccvae.py:421-446."""
