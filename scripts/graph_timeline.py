@@ -39,7 +39,7 @@ for sup in (True, False):
     marks = lrn.engine.marks
     t = lrn.engine.mark_buf.cpu()[:len(marks)].double() / 1e3
     t0 = t[0]
-    last = {"main": t0, "side": None, "side2": None, "side3": None}
+    last = {"main": t0, "side": None, "side2": None, "side3": None, "wg1": None, "wg2": None}
     for (what, lane), ti in zip(marks, t):
         prev = last[lane]
         d = (ti - prev) if prev is not None else float("nan")

@@ -43,7 +43,7 @@ class EngineTC(Engine):
     precision = "bf16"
 
     def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0, tail_split=False,
-                 sl_block_form=False):
+                 sl_block_form=False, wgrad_plan="201202"):
         super().__init__(store)
         # scheduling of the weight-gradient kernels (they feed only the optimiser): the encoder's alternate between
         # `wgrad_streams` side streams so that a layer's weight gradient starts when its operand is ready instead of
@@ -56,9 +56,16 @@ class EngineTC(Engine):
         # weight gradient (tensors are contiguous per image: a half is a pointer offset).  Measured +2 % per step on
         # B200 (the half-batch launches are less efficient than the overlap gains): off by default.
         self.tail_split = bool(tail_split)
+        # which weight-gradient lane (0, 1, 2 = three side streams) takes: the post-chain launches, conv5, conv4, conv3,
+        # conv2, conv1 of the encoder backward (decoder weight gradients: lane 0).  After the fused chain kernel the encoder's
+        # backward is bound by the weight-gradient streams: with everything on two lanes ("001010") the three small
+        # post-chain launches (fc1 / heads weight gradients, gate backward: ~35 us of latency) sat in front of conv5's weight
+        # gradient and the chain conv5 -> conv3 -> conv1 ended 70 us after the last dgrad; on their own lane the step is
+        # 3 % shorter (profiles/r02_ab_log.txt: 1.304 -> 1.263 ms per pair; "101010" 1.279, "201201" / "201002" 1.264)
+        self.wgrad_plan = [int(c) for c in str(wgrad_plan).zfill(6)]
+        self.wg_lanes = [None, torch.cuda.Stream(device=store.device), torch.cuda.Stream(device=store.device)]
         self.wgrad_streams = int(wgrad_streams)
         self.post_chain_stream = post_chain_stream
-        self.side_b = None
         # conv5 -> heads -> latent -> fc1 -> conv1t (and the reverse) as ONE launch each way (csrc/chain.cu); False keeps
         # the layer-by-layer kernels (A/B runs, cross-check in tests/test_gpu_chain.py)
         self.chain = bool(fused_chain)
@@ -248,7 +255,8 @@ class EngineTC(Engine):
             return
         st = torch.cuda.current_stream()
         lane = ("side" if st == self.side else "side2" if st == self.side2 else
-                "side3" if (self.side3 is not None and st == self.side3) else "main")
+                "side3" if (self.side3 is not None and st == self.side3) else
+                "wg1" if st == self.wg_lanes[1] else "wg2" if st == self.wg_lanes[2] else "main")
         _lib.check(self.lib.gccvae_debug_mark(ptr(self.mark_buf), len(self.marks), _stream()), "mark")
         self.marks.append((what, lane))
 
@@ -309,20 +317,23 @@ class EngineTC(Engine):
         with torch.cuda.stream(self.side2):
             fn()
 
-    def _side(self, fn, small=False, alt=False):
-        """run fn (weight-gradient launches) on the side stream, after everything issued so far on the main one.
-        (`small=True` keeps a launch on the main stream; measured slower for every candidate, so it is unused.)
-        `alt`: use the second weight-gradient stream (wgrad_streams == 2)."""
+    def _lane(self, k):
+        """weight-gradient lane k: 0 = self.side, 1 / 2 = further streams (created on first use, joined by join_side)."""
+        if k == 0 or self.wgrad_streams <= 1:
+            return self.side
+        if self.wg_lanes[k] is None:
+            self.wg_lanes[k] = torch.cuda.Stream(device=self.device)
+        self._lanes_used = True
+        return self.wg_lanes[k]
+
+    def _side(self, fn, small=False, lane=0):
+        """run fn (weight-gradient launches) on a side stream, after everything issued so far on the main one.
+        (`small=True` keeps a launch on the main stream; measured slower for every candidate, so it is unused.)"""
         if self.side is None or small:
             fn()
             self._flush_deferred_bias()
             return
-        side = self.side
-        if alt and self.wgrad_streams > 1:
-            if self.side_b is None:
-                self.side_b = torch.cuda.Stream(device=self.device)
-            side = self.side_b
-            self._side_b_used = True
+        side = self._lane(lane)
         side.wait_stream(torch.cuda.current_stream())
         with torch.cuda.stream(side):
             fn()
@@ -336,9 +347,11 @@ class EngineTC(Engine):
             if self._side3_used:
                 torch.cuda.current_stream().wait_stream(self.side3)
                 self._side3_used = False
-            if getattr(self, "_side_b_used", False):
-                torch.cuda.current_stream().wait_stream(self.side_b)
-                self._side_b_used = False
+            if getattr(self, "_lanes_used", False):
+                for st_ in self.wg_lanes:
+                    if st_ is not None:
+                        torch.cuda.current_stream().wait_stream(st_)
+                self._lanes_used = False
 
     def _bias(self, name, n, dout):
         """bias gradient of `name` = column sums of its pre-activation gradient `dout`: queued for the bias-gradient
@@ -537,7 +550,7 @@ class EngineTC(Engine):
                 else:
                     self._run(name + " wgrad", (xin, dout), lambda: lib.gccvae_wg_bf16(
                         C.byref(geom), ptr(xin), ptr(dout), ptr(g_(name + ".w")), _stream()))
-            self._side(wg, alt=(name in ("enc.conv4", "enc.conv2")))
+            self._side(wg, lane=self.wgrad_plan[{"enc.conv5": 1, "enc.conv4": 2, "enc.conv3": 3, "enc.conv2": 4}[name]])
             hook = self.tail_hook if name == self.tail_hook_layer else None
             ev = None
             if hook is not None and self.side is not None:
@@ -554,8 +567,9 @@ class EngineTC(Engine):
                     self.side3.wait_event(ev)
                     self.side3.wait_stream(self.side)
                     self.side3.wait_stream(self.side2)
-                    if getattr(self, "_side_b_used", False):
-                        self.side3.wait_stream(self.side_b)
+                    for st_ in self.wg_lanes:
+                        if st_ is not None:
+                            self.side3.wait_stream(st_)
                     with torch.cuda.stream(self.side3):
                         hook()
                     self._side3_used = True
@@ -575,14 +589,14 @@ class EngineTC(Engine):
                     self._bias("enc.conv1", 32, dh1[sl])
                     self._run("enc.conv1 wgrad", (X2[sl], dh1[sl]), lambda: lib.gccvae_tap4_wg_bf16(
                         h, ptr(X2[sl]), ptr(dh1[sl]), 32, ptr(g_("enc.conv1.w")), _stream()))
-                self._side(wg1)
+                self._side(wg1, lane=self.wgrad_plan[5])
             self.join_side()
             return
         def wg1():
             self._bias("enc.conv1", 32, dh1)
             self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(
                 B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
-        self._side(wg1)
+        self._side(wg1, lane=self.wgrad_plan[5])
         self.join_side()
 
     # ---- per-op device timing (bench.py roofline) -------------------------------------------------------------

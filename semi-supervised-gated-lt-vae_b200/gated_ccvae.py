@@ -470,7 +470,7 @@ class Learner:
                 if self.engine.post_chain_stream == "side2":
                     self.engine._on_side2(after_chain)
                 else:
-                    self.engine._side(after_chain)
+                    self.engine._side(after_chain, lane=self.engine.wgrad_plan[0])
                 self.engine.encoder_bwd(x, b, heads=False)
             else:
                 gate_bwd()
