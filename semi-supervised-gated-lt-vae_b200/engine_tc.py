@@ -43,7 +43,7 @@ class EngineTC(Engine):
     precision = "bf16"
 
     def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0, tail_split=False,
-                 sl_block_form=False, wgrad_plan="201202"):
+                 sl_block_form=False, wgrad_plan="201202", dec_wgrad_plan="00000"):
         super().__init__(store)
         # scheduling of the weight-gradient kernels (they feed only the optimiser): the encoder's alternate between
         # `wgrad_streams` side streams so that a layer's weight gradient starts when its operand is ready instead of
@@ -63,7 +63,9 @@ class EngineTC(Engine):
         # gradient and the chain conv5 -> conv3 -> conv1 ended 70 us after the last dgrad; on their own lane the step is
         # 3 % shorter (profiles/r02_ab_log.txt: 1.304 -> 1.263 ms per pair; "101010" 1.279, "201201" / "201002" 1.264)
         self.wgrad_plan = [int(c) for c in str(wgrad_plan).zfill(6)]
+        self.dec_wgrad_plan = [int(c) for c in str(dec_wgrad_plan).zfill(5)]     # lanes of conv5t, conv4t, conv3t, conv2t, conv1t
         self.wg_lanes = [None, torch.cuda.Stream(device=store.device), torch.cuda.Stream(device=store.device)]
+        self._lanes_used = set()
         self.wgrad_streams = int(wgrad_streams)
         self.post_chain_stream = post_chain_stream
         # conv5 -> heads -> latent -> fc1 -> conv1t (and the reverse) as ONE launch each way (csrc/chain.cu); False keeps
@@ -323,7 +325,7 @@ class EngineTC(Engine):
             return self.side
         if self.wg_lanes[k] is None:
             self.wg_lanes[k] = torch.cuda.Stream(device=self.device)
-        self._lanes_used = True
+        self._lanes_used.add(k)      # (only lanes that carry work of THIS step may be waited for inside a capture)
         return self.wg_lanes[k]
 
     def _side(self, fn, small=False, lane=0):
@@ -347,11 +349,9 @@ class EngineTC(Engine):
             if self._side3_used:
                 torch.cuda.current_stream().wait_stream(self.side3)
                 self._side3_used = False
-            if getattr(self, "_lanes_used", False):
-                for st_ in self.wg_lanes:
-                    if st_ is not None:
-                        torch.cuda.current_stream().wait_stream(st_)
-                self._lanes_used = False
+            for k in sorted(self._lanes_used):
+                torch.cuda.current_stream().wait_stream(self.wg_lanes[k])
+            self._lanes_used.clear()
 
     def _bias(self, name, n, dout):
         """bias gradient of `name` = column sums of its pre-activation gradient `dout`: queued for the bias-gradient
@@ -482,7 +482,7 @@ class EngineTC(Engine):
         g4 = b["dec.conv4t.out"]
         # conv5t from the logit gradient in x2 block form (written by the fused forward)
         self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
-            B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())))
+            B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())), lane=self.dec_wgrad_plan[0])
         self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE | OUT_S2D, ptr(g4),
             ptr(b["dec.conv4t.dout"]), st))
@@ -495,7 +495,7 @@ class EngineTC(Engine):
                 self._bias(name, CL, dout)
                 self._run(name + " wgrad", (dout, xin), lambda: lib.gccvae_wg_s2d_bf16(
                     B, HS, WS, CL, ptr(dout), ptr(xin), CS, ptr(g_(name + ".w")), _stream()))
-            self._side(wg)
+            self._side(wg, lane=self.dec_wgrad_plan[{"dec.conv4t": 1, "dec.conv3t": 2, "dec.conv2t": 3}[name]])
             flag = OUT_S2D if (pn + ".dout") in S2D_TENSORS else 0
             self._run(name + " dgrad", (dout, self.wp[name + ".s2d"], xin, dxin),
                       lambda name=name, dout=dout, xin=xin, dxin=dxin, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag:
@@ -504,7 +504,7 @@ class EngineTC(Engine):
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,
-                                         "dec.conv1t wgrad"))
+                                         "dec.conv1t wgrad"), lane=self.dec_wgrad_plan[4])
         if not tail:
             return None
         self._on_side2(lambda: self._bias_grad16(dg1, "dec.conv1t", cols=128))
@@ -567,9 +567,8 @@ class EngineTC(Engine):
                     self.side3.wait_event(ev)
                     self.side3.wait_stream(self.side)
                     self.side3.wait_stream(self.side2)
-                    for st_ in self.wg_lanes:
-                        if st_ is not None:
-                            self.side3.wait_stream(st_)
+                    for k in sorted(self._lanes_used):
+                        self.side3.wait_stream(self.wg_lanes[k])
                     with torch.cuda.stream(self.side3):
                         hook()
                     self._side3_used = True

@@ -94,3 +94,32 @@ def test_gate_temperature_reaches_captured_graphs_without_recapture():
     assert float((cg - 0.5).abs().mean()) > float((c_warm - 0.5).abs().mean())
     with pytest.raises(ValueError):
         lrn.gating_sampler_temp = 0.0
+
+
+def test_inputs_staged_ahead_of_the_replay_give_the_same_steps():
+    """graph replay stages a batch (copy into the variant's buffers, x2 transform) on the copy stream; with host batches,
+    and with resident batches flagged `inputs_ready`, that runs under the step in flight.  Same trajectory either way."""
+    import gccvae_b200 as G
+    cfg = dict(cfg_for("learnable", "0.5"), batch_size=32)
+    g = torch.Generator().manual_seed(2)
+    xs = [torch.randint(0, 256, (32, 64, 64, 3), generator=g, dtype=torch.uint8) for _ in range(3)]
+    ys = [(torch.rand(32, 18, generator=g) < 0.5).long() for _ in range(3)]
+    outs = []
+    for mode in ("host", "resident", "resident-ready"):
+        lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True, seed=4)
+        lrn.store.load_dict(O.init_params(0, trained_like=True))
+        losses = []
+        for i in range(6):
+            x, y = xs[i % 3], ys[i % 3]
+            if mode == "host":
+                x, y = x.pin_memory(), y.pin_memory()
+            else:
+                x, y = x.cuda(), y.cuda()
+                torch.cuda.synchronize()
+            sup = i % 2 == 0
+            losses.append(lrn.train_step(x, y if sup else None, sup, inputs_ready=(mode == "resident-ready"))[0])
+        torch.cuda.synchronize()
+        outs.append([float(v) for v in losses])
+    for other in outs[1:]:
+        for a, b in zip(outs[0], other):
+            assert abs(a - b) <= 2e-3 * abs(a), outs      # (weight gradients are accumulated with atomics)
