@@ -137,7 +137,8 @@ int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, const void*
  * gccvae_ls_bf16 / gccvae_sl_bf16 / gccvae_sl_halo_bf16 / gccvae_tap4_ls_bf16 / gccvae_c3conv_bf16:            */
 #define GCCVAE_OUT_S2D 0x10      /* store the (bf16, spatial) output in s2d block form                          */
 #define GCCVAE_MASK_S2D 0x20     /* the mask tensor is stored in s2d block form                                 */
-#define GCCVAE_LAYOUT_FLAGS 0x30
+#define GCCVAE_TAP_HALO 0x40     /* gccvae_tap4_ls_bf16: two column-shifted boxes with a halo row instead of four boxes */
+#define GCCVAE_LAYOUT_FLAGS 0x70
 int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void* in2, const void* S, int CS, float* dW,
                        void* stream);
 /* Space-to-depth ("x2") form of the 3-channel end layers (conv1 = networks.py:11,22; conv5t = :49,58; likelihood =

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", os.environ.get("GCCVAE_LIB", "libgccvae.so"))
 
 ACT_NONE, ACT_RELU, ACT_SIGMOID, ACT_ACCUMULATE = 0, 1, 2, 0x100
-OUT_S2D, MASK_S2D = 0x10, 0x20   # layout flags OR-ed into `act` (include/gccvae.h)
+OUT_S2D, MASK_S2D, TAP_HALO = 0x10, 0x20, 0x40   # layout flags OR-ed into `act` (include/gccvae.h)
 GATE_WS_FLOATS = 7 * 324 + 32
 LATENT_PARTIAL_FLOATS = 5 * 324 + 32
 RESULT_SLOT_FLOATS = 328

@@ -69,6 +69,12 @@ struct alignas(64) TapGemmParams {
   // columns are (dy, dx, channel); the epilogue scatters the four slots to pixels (2i - 1 + dy, 2j - 1 + dx) of the
   // OH x OW x OC plane (plain NHWC or s2d storage) and skips the slots outside the plane
   int blk_cl;
+  // "halo2" (4-tap L -> S over s2d blocks, full-width tiles of one image): instead of four shifted boxes of BH x BW block
+  // rows, TWO column-shifted boxes (b = 0, 1) of (BH + 1) x BW rows are loaded per chunk and the row tap a = 0, 1 is a
+  // start-address offset of BW rows (a multiple of the 1 KB swizzle atom) in the A descriptor: (BH + 1) / (2 BH) of the
+  // L2 -> shared-memory traffic the four-box form needs.  A k-block then carries the B tiles of both row taps.
+  int halo2;
+  int a_box_rows;     // rows of one A box (128, or (BH + 1) * BW in halo2 mode)
 };
 
 // Pipeline timeline (scripts/timeline_probe.py).  Compiled in only with -DGCCVAE_TIMELINE (libgccvae_tl.so): even with
@@ -131,7 +137,7 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  const int a_bytes = 128 * p.KC * 2, b_bytes = p.N * p.KC * 2;
+  const int a_bytes = p.a_box_rows * p.KC * 2, b_tile = p.N * p.KC * 2, b_bytes = (p.halo2 ? 2 : 1) * b_tile;
   const int a_stride = (a_bytes + 1023) & ~1023, b_stride = (b_bytes + 1023) & ~1023;
   const int stage_stride = p.tps * (a_stride + b_stride);   // [tps A blocks][tps B blocks]
   uint8_t* sA = smem;
@@ -191,7 +197,8 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       uint32_t ph = 0;
       long long prod_wait = 0;
       const long long tp0 = clock64();
-      const uint32_t stage_tx = (uint32_t)(p.tps * (p.rows_valid * p.KC * 2 + b_bytes));
+      const uint32_t stage_tx =
+          (uint32_t)(p.tps * ((p.halo2 ? p.a_box_rows : p.rows_valid) * p.KC * 2 + b_bytes));
       for (int item = item_beg; item < item_end; ++item) {
         const int phase_id = item % p.phases, slab = (item / p.phases) % p.n_slabs, tile = item / (p.phases * p.n_slabs);
         const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
@@ -208,7 +215,12 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           uint8_t* b_dst = sB + stage * stage_stride;
           for (int j = 0; j < p.tps; ++j) {
             tma_load_4d(a_dst, &p.tmA, &full[stage], c * p.KC, aw + p.a_dw[phase_id][t], ah + p.a_dh[phase_id][t], n0);
-            tma_load_2d(b_dst, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, brow);
+            if (p.halo2) {   // t = column tap b; the B tiles of row taps a = 0, 1 (tap index a * 2 + b)
+              tma_load_2d(b_dst, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, brow);
+              tma_load_2d(b_dst + b_tile, &p.tmB, &full[stage], (2 + t) * p.b_tap_stride + c * p.KC, brow);
+            } else {
+              tma_load_2d(b_dst, &p.tmB, &full[stage], t * p.b_tap_stride + c * p.KC, brow);
+            }
             a_dst += a_stride;
             b_dst += b_stride;
             if (++c == p.chunks) { c = 0; ++t; }
@@ -253,12 +265,25 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (it + p.tps >= k_iters) TL(li, 3);
           uint64_t ad = adesc0 + (uint64_t)((uint32_t)stage * st_step);
           uint64_t bd = bdesc0 + (uint64_t)((uint32_t)stage * st_step);
+          if (p.halo2) {
+            // per k-block (column tap, chunk): row tap a = 0, 1 -> A shifted by BW rows, B tile a
+            const uint32_t a_shift = (uint32_t)(p.BW * p.KC * 2) >> 4, b_shift = (uint32_t)b_tile >> 4;
+            for (int j = 0; j < p.tps; ++j) {
+              for (int a = 0; a < 2; ++a)
+                for (int kk = 0; kk < kk_n; ++kk)
+                  umma_bf16(tacc, ad + (uint64_t)(a * a_shift + 2u * kk), bd + (uint64_t)(a * b_shift + 2u * kk), idesc,
+                            (it > 0 || j > 0 || a > 0 || kk > 0) ? 1u : 0u);
+              ad += a_step;
+              bd += b_step;
+            }
+          } else {
           umma_bf16(tacc, ad, bd, idesc, it > 0 ? 1u : 0u);
           for (int kk = 1; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
           for (int j = 1; j < p.tps; ++j) {
             ad += a_step;
             bd += b_step;
             for (int kk = 0; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
+          }
           }
           umma_commit(&empty[stage]);
           if (it + p.tps >= k_iters) umma_commit(&tfull[as]);
@@ -2046,9 +2071,11 @@ static int launch_tapgemm(TapGemmParams& p, int groups, int phases, cudaStream_t
                 "%s: unsupported column-sum shape (n=%d mod=%d)", name, p.colsum_n, p.colsum_mod);
   }
   if (p.rows_valid <= 0) p.rows_valid = 128;
+  if (p.a_box_rows <= 0) p.a_box_rows = 128;
   const bool blk = p.blk_cl > 0;
   GCC_REQUIRE(!blk || p.colsum == nullptr, "%s: no fused column sums in block form", name);
-  const int a_stride = (128 * p.KC * 2 + 1023) & ~1023, b_stride = (p.N * p.KC * 2 + 1023) & ~1023;
+  const int a_stride = (p.a_box_rows * p.KC * 2 + 1023) & ~1023,
+            b_stride = ((p.halo2 ? 2 : 1) * p.N * p.KC * 2 + 1023) & ~1023;
   // Persistent CTAs, `per_sm` of them per SM (their epilogues and issue threads overlap).  The single MMA-issuing
   // thread pays ~400 cycles per pipeline stage (barrier wait, fences, commit) and ~50 per MMA, so a stage carries
   // `tps` k-blocks (taps x chunks): few, fat stages.  TMEM: two accumulator stages per CTA, 512 columns per SM.
@@ -2483,11 +2510,21 @@ extern "C" int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void
   GCC_REQUIRE(pick_tile(HS, WS, &bw, &bh, &bn) == 0, "tap4_ls: cannot tile %dx%d", HS, WS);
   TapGemmParams p;
   memset(&p, 0, sizeof(p));
-  if ((rc = encode_act_map(&p.tmA, in2, batch, HB, WB, CB, kc, bw, bh, bn, 1))) return rc;
+  // halo2 form (GCCVAE_TAP_HALO): full-width tiles of one image, 128-byte operand rows, the row shift a multiple of the
+  // 1 KB swizzle atom, the box of (bh + 1) x bw rows within TMA's limits
+  const bool halo2 = (act & GCCVAE_TAP_HALO) && bn == 1 && bw == WS && kc == 64 && (bw * kc * 2) % 1024 == 0 &&
+                     (size_t)(bh + 1) * bw * kc * 2 <= 24 * 1024 && CS * kc * 2 % 1024 == 0;
+  if ((rc = encode_act_map(&p.tmA, in2, batch, HB, WB, CB, kc, bw, halo2 ? bh + 1 : bh, bn, 1))) return rc;
   if ((rc = encode_mat_map(&p.tmB, Wp, CS, 4LL * CB, kc, CS))) return rc;
-  p.num_taps = 4; p.chunks = CB / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
+  p.chunks = CB / kc; p.a_scale = 1; p.BW = bw; p.BH = bh; p.BN = bn;
   p.tiles_w = WS / bw; p.tiles_h = HS / bh;
-  for (int t = 0; t < 4; ++t) { p.a_dh[0][t] = (short)(t >> 1); p.a_dw[0][t] = (short)(t & 1); }
+  if (halo2) {
+    p.halo2 = 1; p.num_taps = 2; p.a_box_rows = (bh + 1) * bw;
+    for (int t = 0; t < 2; ++t) { p.a_dh[0][t] = 0; p.a_dw[0][t] = (short)t; }
+  } else {
+    p.num_taps = 4;
+    for (int t = 0; t < 4; ++t) { p.a_dh[0][t] = (short)(t >> 1); p.a_dw[0][t] = (short)(t & 1); }
+  }
   p.b_tap_stride = CB;
   p.KC = kc; p.swz = umma_swizzle_for(kc * 2);
   p.N = CS; p.n_store = CS; p.n_slabs = 1;

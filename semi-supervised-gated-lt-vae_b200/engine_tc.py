@@ -26,7 +26,7 @@ import os
 import torch
 
 from . import _lib
-from ._lib import ACT_ACCUMULATE, ACT_NONE, ACT_RELU, ACT_SIGMOID, MASK_S2D, OUT_S2D, Geom, ptr
+from ._lib import ACT_ACCUMULATE, ACT_NONE, ACT_RELU, ACT_SIGMOID, MASK_S2D, OUT_S2D, TAP_HALO, Geom, ptr
 from .engine import DEC_LAYERS, ENC_LAYERS, HEAD_LAYERS, Engine, _stream, make_geom, out_shape
 
 BF16 = torch.bfloat16
@@ -43,7 +43,7 @@ class EngineTC(Engine):
     precision = "bf16"
 
     def __init__(self, store, fused_chain=True, wgrad_streams=2, post_chain_stream="side", markers=0, tail_split=False,
-                 sl_block_form=False, wgrad_plan="201202", dec_wgrad_plan="00000"):
+                 sl_block_form=False, wgrad_plan="201202", dec_wgrad_plan="00000", tap_halo=True):
         super().__init__(store)
         # scheduling of the weight-gradient kernels (they feed only the optimiser): the encoder's alternate between
         # `wgrad_streams` side streams so that a layer's weight gradient starts when its operand is ready instead of
@@ -62,6 +62,9 @@ class EngineTC(Engine):
         # post-chain launches (fc1 / heads weight gradients, gate backward: ~35 us of latency) sat in front of conv5's weight
         # gradient and the chain conv5 -> conv3 -> conv1 ended 70 us after the last dgrad; on their own lane the step is
         # 3 % shorter (profiles/r02_ab_log.txt: 1.304 -> 1.263 ms per pair; "101010" 1.279, "201201" / "201002" 1.264)
+        # L -> S layers over s2d blocks (conv2-4 forward, convT dgrads): two column-shifted boxes with one halo row instead
+        # of four shifted boxes where the geometry allows it (16x16 outputs: conv2 forward, conv4t dgrad)
+        self.tap_flag = TAP_HALO if tap_halo else 0
         self.wgrad_plan = [int(c) for c in str(wgrad_plan).zfill(6)]
         self.dec_wgrad_plan = [int(c) for c in str(dec_wgrad_plan).zfill(5)]     # lanes of conv5t, conv4t, conv3t, conv2t, conv1t
         self.wg_lanes = [None, torch.cuda.Stream(device=store.device), torch.cuda.Stream(device=store.device)]
@@ -418,7 +421,7 @@ class EngineTC(Engine):
                 self._run(name + " fwd", (h, self.wp[name + ".s2d"], b[name + ".out"]),
                           lambda h=h, name=name, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag: lib.gccvae_tap4_ls_bf16(
                               B, HS + 1, WS + 1, 4 * CL, ptr(h), ptr(self.wp[name + ".s2d"]), CS, ptr(v(name + ".b")),
-                              ACT_RELU | flag, None, ptr(b[name + ".out"]), st))
+                              ACT_RELU | flag | self.tap_flag, None, ptr(b[name + ".out"]), st))
             else:
                 g = make_geom(_ENC[name], B)
                 self._run(name + " fwd", (h, self.wp[name + ".ls"], b[name + ".out"]),
@@ -500,7 +503,7 @@ class EngineTC(Engine):
             self._run(name + " dgrad", (dout, self.wp[name + ".s2d"], xin, dxin),
                       lambda name=name, dout=dout, xin=xin, dxin=dxin, HS=HS, WS=WS, CL=CL, CS=CS, flag=flag:
                       lib.gccvae_tap4_ls_bf16(B, HS + 1, WS + 1, 4 * CL, ptr(dout), ptr(self.wp[name + ".s2d"]), CS, None,
-                                              ACT_NONE | flag, ptr(xin), ptr(dxin), st))
+                                              ACT_NONE | flag | self.tap_flag, ptr(xin), ptr(dxin), st))
         # conv1t ([B,64(45)] -> [B,2048]) and fc1 as padded dense GEMMs
         dg1, g0, dg0 = b["dec.conv1t.dout"], b["dec.fc1.out"], b["dec.fc1.dout"]
         self._side(lambda: self._gemm_tn(B, 2048, 64, dg1, g0, [(0, 45, 45, g_("dec.conv1t.w"))], 2048,

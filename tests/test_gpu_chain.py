@@ -97,6 +97,8 @@ def test_fused_chain_train_step_graph_replay_matches_eager():
     for a, b in zip(outs[0][0], outs[1][0]):
         assert abs(a - b) <= 1e-3 * abs(a), (outs[0][0], outs[1][0])
     # Adam's first steps move every parameter by ~lr whatever the gradient's size, so entries whose gradient is at the
-    # level of the atomics' summation noise may differ by O(lr); a wrong step would move (almost) all of them
+    # level of the atomics' summation noise may differ by O(lr).  Measured: the two runs are usually bit-identical; when
+    # the order of the bias-gradient atomics of one step differs (one ulp in dec.conv1t.b / dec.fc1.b), 5 % of the
+    # entries differ after that step and 10 % after the next one.  A wrong step moves (almost) all of them.
     differs = ((outs[0][1] - outs[1][1]).abs() > 2e-6).float().mean().item()
-    assert differs < 0.05, differs
+    assert differs < 0.3, differs

@@ -61,6 +61,15 @@ def test_s2d_ls_forward_wgrad_and_mask(HL, CL, CS, B):
     want = torch.relu(O._conv(bf(Lt).double(), bf(W).double(), bias.double(), 2, 1))
     err = float((S.float().cpu().double() - want).abs().max() / want.abs().max())
     assert err < 6e-3, ("s2d ls fwd", err)
+    # ---- the same through the halo form (two column-shifted boxes with a halo row; where the geometry does not allow
+    # it the flag is ignored): same operands, same MMAs in another order -> the same bits up to fp32 summation order
+    Sh = torch.full((B, HS, HS, CS), float("nan"), dtype=torch.bfloat16, device=d)
+    L.check(lib.gccvae_tap4_ls_bf16(B, HS + 1, HS + 1, 4 * CL, L.ptr(L2), L.ptr(wp), CS, L.ptr(bd),
+                                    L.ACT_RELU | L.TAP_HALO, None, L.ptr(Sh), _stream()))
+    torch.cuda.synchronize()
+    errh = float((Sh.float().cpu().double() - want).abs().max() / want.abs().max())
+    assert errh < 6e-3, ("s2d ls fwd, halo form", errh)
+    assert float((Sh.float() - S.float()).abs().max()) <= 2e-2 * float(S.float().abs().max())
     # ---- forward, s2d output (what the next stride-2 layer consumes)
     if HS >= 2:
         S2 = torch.zeros(B, HS // 2 + 1, HS // 2 + 1, 4 * CS, dtype=torch.bfloat16, device=d)
