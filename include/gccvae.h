@@ -146,7 +146,9 @@ int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void* in2, const
  * Conv2D(k4,s2,p1) over the image is a 2x2-tap stride-1 GEMM over the blocks and Conv2DTranspose(k4,s2,same)
  * produces its output directly in block form.  x may be uint8 (0..255): it is divided by 255 on the device
  * exactly as utils_data.py:57-59 does on the host. */
-int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* stream);
+/* XB (optional, uint8 images only): [B,33,33,16] uint8, the RAW bytes of every block (4 pixels x 3 channels + 4 zero
+ * bytes, zero outside the image): the image operand of gccvae_convt_recon_bf16 with x_u8 = 2. */
+int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* XB, void* stream);
 int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, const void* Wp, int CS, const float* bias,
                         int act, const void* mask, void* out, void* stream);
 /* same contraction as gccvae_tap4_ls_bf16 for the 33x33x16 blocks of a 64x64x3 image, with the im2col tile built
@@ -154,7 +156,9 @@ int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, cons
 int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, int CS, const float* bias, int act, const void* mask,
                        void* out, void* stream);
 int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream);
-/* log_pxz_ready != 0: the caller has already set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32), e.g. on a side stream */
+/* x_u8: 0 = x is the fp32 image [B,64,64,3], 1 = the uint8 image, 2 = the raw-byte blocks XB of gccvae_prep_x2_bf16 (one
+ * 16-byte load per block instead of twelve 1-byte loads).
+ * log_pxz_ready != 0: the caller has already set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32), e.g. on a side stream */
 int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp8, const float* bias, const void* x, int x_u8,
                             const float* coef, float* log_pxz, void* D2, float* xhat, float* db, int log_pxz_ready,
                             void* stream);

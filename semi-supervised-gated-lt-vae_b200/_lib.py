@@ -137,7 +137,7 @@ SIGNATURES = {
     "gccvae_sl_halo_bf16": (_I, [_G, _P, _P, _P, _I, _P, _P, _I, _P]),
     "gccvae_cast_f32_to_bf16": (_I, [_P, _LL, _P, _P]),
     "gccvae_cast_bf16_to_f32": (_I, [_P, _LL, _P, _P]),
-    "gccvae_prep_x2_bf16": (_I, [_P, _I, _I, _P, _P]),
+    "gccvae_prep_x2_bf16": (_I, [_P, _I, _I, _P, _P, _P]),
     "gccvae_tap4_ls_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_c3conv_bf16": (_I, [_I, _P, _P, _I, _P, _I, _P, _P, _P]),
     "gccvae_wg_s2d_bf16": (_I, [_I, _I, _I, _I, _P, _P, _I, _P, _P]),

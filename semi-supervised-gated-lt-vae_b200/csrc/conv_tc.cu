@@ -19,6 +19,7 @@
 #include <string.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.cuh"
 #include "tc_common.cuh"
@@ -1363,8 +1364,16 @@ template <>
 __device__ __forceinline__ float px_value<uint8_t>(uint8_t raw, const float* lut) { return lut[raw]; }
 
 // one thread per block (n, i, j): 4 pixels x 3 channels in, 32 bytes out
+// XB (uint8 images only, optional): the RAW bytes of the block, [B,33,33,16] uint8 = 4 pixels x 3 channels + 4 zero bytes
+// (zero outside the image) - what the fused likelihood kernel reads back with one 16-byte load per block.
 template <typename XT>
-__global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, long long total, uint4* __restrict__ X2) {
+__device__ __forceinline__ uint32_t raw_byte(XT) { return 0u; }
+template <>
+__device__ __forceinline__ uint32_t raw_byte<uint8_t>(uint8_t v) { return (uint32_t)v; }
+
+template <typename XT>
+__global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, long long total, uint4* __restrict__ X2,
+                                                      uint4* __restrict__ XB) {
   pdl_launch_dependents();
   __shared__ float s_lut[256];
   s_lut[threadIdx.x] = g_u8lut[threadIdx.x];   // written once at library initialisation, never by a kernel
@@ -1374,6 +1383,7 @@ __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, 
     const int j = (int)(idx % 33), i = (int)((idx / 33) % 33);
     const long long n = idx / (33 * 33);
     uint32_t w[8];
+    uint32_t rb[3] = {0u, 0u, 0u};
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
       const int Y = 2 * i - 1 + (q >> 1), X = 2 * j - 1 + (q & 1);
@@ -1381,19 +1391,23 @@ __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, 
       if ((unsigned)Y < 64u && (unsigned)X < 64u) {
         const XT* px = x + ((n * 64 + Y) * 64 + X) * 3;
         v0 = load_px<XT>(px, s_lut); v1 = load_px<XT>(px + 1, s_lut); v2 = load_px<XT>(px + 2, s_lut);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) rb[(3 * q + c) >> 2] |= raw_byte<XT>(__ldg(px + c)) << (8 * ((3 * q + c) & 3));
       }
       w[2 * q] = pack_bf16x2(v0, v1);
       w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
     }
     X2[2 * idx] = make_uint4(w[0], w[1], w[2], w[3]);
     X2[2 * idx + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+    if (XB != nullptr) XB[idx] = make_uint4(rb[0], rb[1], rb[2], 0u);
   }
 }
 
 // uint8 images: one CTA per image stages the 12 288 bytes in shared memory with coalesced 16-byte loads (the kernel
 // above issues twelve 1-byte loads per block: 16 us for 1024 images against ~8 us of HBM time), then every thread builds
 // blocks from shared memory.  Same table lookup, same output bits.
-__global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* __restrict__ x, int batch, uint4* __restrict__ X2) {
+__global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* __restrict__ x, int batch, uint4* __restrict__ X2,
+                                                                uint4* __restrict__ XB) {
   pdl_launch_dependents();
   __shared__ float s_lut[256];
   __shared__ __align__(16) uint8_t s_img[64 * 64 * 3];
@@ -1408,6 +1422,7 @@ __global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* _
     for (int blk = threadIdx.x; blk < 33 * 33; blk += 256) {
       const int j = blk % 33, i = blk / 33;
       uint32_t w[8];
+      uint32_t rb[3] = {0u, 0u, 0u};
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const int Y = 2 * i - 1 + (q >> 1), X = 2 * j - 1 + (q & 1);
@@ -1415,6 +1430,8 @@ __global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* _
         if ((unsigned)Y < 64u && (unsigned)X < 64u) {
           const uint8_t* px = s_img + (Y * 64 + X) * 3;
           v0 = s_lut[px[0]]; v1 = s_lut[px[1]]; v2 = s_lut[px[2]];
+#pragma unroll
+          for (int c = 0; c < 3; ++c) rb[(3 * q + c) >> 2] |= (uint32_t)px[c] << (8 * ((3 * q + c) & 3));
         }
         w[2 * q] = pack_bf16x2(v0, v1);
         w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
@@ -1422,14 +1439,21 @@ __global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* _
       const size_t o = ((size_t)n * 1089 + blk) * 2;
       X2[o] = make_uint4(w[0], w[1], w[2], w[3]);
       X2[o + 1] = make_uint4(w[4], w[5], w[6], w[7]);
+      if (XB != nullptr) XB[(size_t)n * 1089 + blk] = make_uint4(rb[0], rb[1], rb[2], 0u);
     }
   }
 }
 
 // Fused Conv2DTranspose(32 -> 3, k4, s2, same) + sigmoid + Laplace log-likelihood (utils.py:101-105) + its
 // gradient w.r.t. the logits, written in block form D2 (the operand of conv5t's dgrad and wgrad).
-// Tile = 11 x 11 blocks of one image (9 tiles per image, 121 of the 128 MMA rows used); 4 taps, each a TMA box
-// of the decoder activation g4 [B,32,32,32] shifted by (-a, -b) (zero-filled outside), K = 32 per tap, N = 16.
+// Output block (i, j) of an image = sum over the 2x2 taps (a, b) of g4[i - a, j - b, :] . W_ab  (K = 32 per tap, N = 16).
+// Tile = 128 CONSECUTIVE blocks f = 33 i + j of one image (9 tiles per image, the last one holds 65).  The operand of
+// all four taps is ONE TMA box of the decoder activation g4 [B,32,32,32]: 6 image rows x 33 columns starting at column
+// -1 (TMA zero-fills the column and the rows outside the image), i.e. the rows' pixels with pitch 33 and a zero pixel
+// between consecutive rows.  In that buffer the tap (a, b) of block f0 + m is row  m + d0 + 34 - 33 a - b  (d0 = f0 mod
+// 33): a start-address offset of the A descriptor.  The swizzle XOR is taken from the absolute shared-memory address, so
+// a K-major operand may start at ANY row of a swizzled buffer (scripts/microbench/desc_offset.cu,
+// profiles/r02_microbench_desc_offset.txt) - 198 box rows per tile instead of the 4 x 121 of one box per tap.
 struct alignas(64) CtrParams {
   CUtensorMap tmA, tmB;
   const void* x;
@@ -1444,12 +1468,33 @@ struct alignas(64) CtrParams {
   long long* timeline;
 };
 
-template <typename XT>
-__global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_constant__ CtrParams p) {
+constexpr int CTR_BOX_ROWS = 6 * 33;          // rows of the A box (64 bytes each)
+constexpr int CTR_A_STAGE = 13 * 1024;        // >= CTR_BOX_ROWS * 64, a multiple of the swizzle pattern
+
+__device__ __forceinline__ float ex2_approx(float v) {
+  float r;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+
+// XM = form of the image operand: 0 fp32 NHWC, 1 uint8 NHWC, 2 uint8 raw-byte blocks XB [B,33,33,16] (prep_x2).
+// XM = 2: the 2 KB of raw bytes of a tile's 128 blocks travel with the tile's operand box (one bulk copy into the same
+// pipeline stage, same barrier); the stage is free again when the MMAs have read the box AND the four epilogue warps have
+// taken their bytes.  A register prefetch one tile ahead (XM = 0 / 1) is too short: a tile's epilogue is ~0.3 us of work,
+// an HBM access under load ~1.3 us (scripts/timeline_ctr.py: the epilogue warps sat ~1.1 us per tile on that load).
+constexpr int CTR_X_BYTES = 128 * 16;
+template <int XM>
+__global__ void __launch_bounds__(TG_THREADS, 4) convt_recon_kernel(const __grid_constant__ CtrParams p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* smem = smem_raw + (base - smem_u32(smem_raw));
-  constexpr int A_SLOT = 8192, A_BOX = 121 * 64, B_TAP = 1024, STAGE = 4 * A_SLOT;
+  constexpr int B_TAP = 1024;
+  constexpr int STAGE = CTR_A_STAGE + (XM == 2 ? CTR_X_BYTES : 0);   // [A box][raw bytes of the tile's blocks]
   uint8_t* sB = smem;                 // 4 taps x [16 rows x 64 B]
   uint8_t* sA = smem + 4 * B_TAP;
   uint64_t* full = reinterpret_cast<uint64_t*>(sA + p.stages * STAGE);
@@ -1471,7 +1516,7 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
     tma_prefetch_desc(&p.tmB);
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&empty[s], 1);
+      mbar_init(&empty[s], XM == 2 ? 5 : 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull[s], 1);
@@ -1482,11 +1527,20 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
   }
   if (threadIdx.x < 4) s_db[threadIdx.x] = 0.0f;
   for (int i = threadIdx.x; i < 256; i += TG_THREADS) s_lut[i] = g_u8lut[i];
+  if (XM == 2)   // the last tile of an image brings 65 blocks: the other rows read whatever the stage holds (masked)
+    for (int i = threadIdx.x; i < p.stages * (CTR_X_BYTES / 16); i += TG_THREADS)
+      reinterpret_cast<uint4*>(sA + (i / (CTR_X_BYTES / 16)) * STAGE + CTR_A_STAGE)[i % (CTR_X_BYTES / 16)] = make_uint4(0u, 0u, 0u, 0u);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes above, async-proxy (bulk copy) writes later
   if (warp == 2) tmem_alloc(tmem_slot, 64);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  if (TL_ON(p) && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.timeline[40 * 8 + 2 * blockIdx.x] = (long long)gt;
+  }
   pdl_wait();
 
   if (warp == 0) {
@@ -1495,16 +1549,20 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       for (int t = 0; t < 4; ++t) tma_load_2d(sB + t * B_TAP, &p.tmB, bfull, t * 32, 0);
       int stage = 0;
       uint32_t ph = 0;
+      int n = tile_beg / 9, k = tile_beg - n * 9;
       for (int tile = tile_beg; tile < tile_end; ++tile) {
-        const int n = tile / 9, r = tile - n * 9, i0 = (r / 3) * 11, j0 = (r % 3) * 11;
-        mbar_wait(&empty[stage], ph ^ 1);
+        const int i_first = (k * 128) / 33;
+        const uint32_t xbytes = XM == 2 ? (uint32_t)min(128, 33 * 33 - k * 128) * 16u : 0u;
+        mbar_wait_relaxed(&empty[stage], ph ^ 1);   // runs stages ahead of its consumers: back off instead of spinning
         TL(tile - tile_beg, 0);
-        mbar_expect_tx(&full[stage], 4 * A_BOX);
-#pragma unroll
-        for (int t = 0; t < 4; ++t)
-          tma_load_4d(sA + stage * STAGE + t * A_SLOT, &p.tmA, &full[stage], 0, j0 - (t & 1), i0 - (t >> 1), n);
+        mbar_expect_tx(&full[stage], CTR_BOX_ROWS * 64 + xbytes);
+        tma_load_4d(sA + stage * STAGE, &p.tmA, &full[stage], 0, -1, i_first - 1, n);
+        if (XM == 2)
+          bulk_load_1d(sA + stage * STAGE + CTR_A_STAGE, reinterpret_cast<const uint4*>(p.x) + ((size_t)n * 1089 + (size_t)k * 128),
+                       xbytes, &full[stage]);
         TL(tile - tile_beg, 1);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        if (++k == 9) { k = 0; ++n; }
       }
     }
   } else if (warp == 1) {
@@ -1514,68 +1572,84 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       const uint64_t adesc0 = dproto + (uint64_t)(smem_u32(sA) >> 4), bdesc0 = dproto + (uint64_t)(smem_u32(sB) >> 4);
       int stage = 0;
       uint32_t ph = 0;
+      int k = tile_beg % 9;
       mbar_wait(bfull, 0);
       for (int tile = tile_beg; tile < tile_end; ++tile) {
         const int li = tile - tile_beg, as = li & 1;
+        const int f0 = k * 128, d0 = f0 - (f0 / 33) * 33;
         mbar_wait(&tempty[as], ((uint32_t)(li >> 1) & 1u) ^ 1u);
         TL(li, 2);
         mbar_wait(&full[stage], ph);
         tc_fence_after();
         TL(li, 3);
-        const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * (STAGE >> 4));
+        // descriptor units are 16 bytes: one operand row = 4
+        const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * (STAGE >> 4) + (uint32_t)(d0 + 34) * 4u);
         const uint32_t tacc = tmem_base + (uint32_t)as * 32u;
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
+          const uint32_t row_off = (uint32_t)(33 * (t >> 1) + (t & 1)) * 4u;   // tap (a, b) = (t >> 1, t & 1)
 #pragma unroll
           for (int kk = 0; kk < 2; ++kk)
-            umma_bf16(tacc, a_st + (uint64_t)(t * (A_SLOT >> 4) + 2 * kk), bdesc0 + (uint64_t)(t * (B_TAP >> 4) + 2 * kk),
+            umma_bf16(tacc, a_st - (uint64_t)row_off + (uint64_t)(2 * kk), bdesc0 + (uint64_t)(t * (B_TAP >> 4) + 2 * kk),
                       idesc, (t > 0 || kk > 0) ? 1u : 0u);
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
         TL(li, 7);
         if (++stage == p.stages) { stage = 0; ph ^= 1; }
+        if (++k == 9) k = 0;
       }
     }
   } else {
     const int q = warp & 3;
     const int m = q * 32 + lane;
-    const int li_ = m / 11, lj_ = m - li_ * 11;
-    const bool row_ok = m < 121;
-    const float b0 = __ldg(p.bias), b1 = __ldg(p.bias + 1), b2 = __ldg(p.bias + 2);
-    const XT* xs = reinterpret_cast<const XT*>(p.x);
+    constexpr float LOG2E = 1.4426950408889634f;
+    const float nb0 = -LOG2E * __ldg(p.bias), nb1 = -LOG2E * __ldg(p.bias + 1), nb2 = -LOG2E * __ldg(p.bias + 2);
     float d0 = 0.f, d1 = 0.f, d2 = 0.f;
-    // The image pixels of a block do not depend on the accumulator and come straight from HBM: they are fetched one
-    // tile AHEAD (register double buffer), so their latency hides behind the arithmetic of the current tile.  The
-    // prefetch keeps the RAW values (bytes for uint8 images) and is branch-free - coordinates clamped into the image,
-    // out-of-image pixels are masked by `ok` below - so that all 12 loads are in flight together; the uint8 -> float
-    // table lookup happens when the values are consumed (a lookup right behind its load would stall the warp for
-    // the full memory latency, four times per tile).
-    XT xn[12];
-    auto fetch_x = [&](int tile, XT (&xv)[12]) {
-      const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
+    // XM = 0 / 1: the image pixels of a block are fetched from the NHWC image one tile AHEAD (register double buffer),
+    // branch-free - coordinates clamped into the image, out-of-image pixels masked by `ok` below - and keep their RAW
+    // form; the uint8 -> float table lookup happens when the values are consumed.
+    using XT = typename std::conditional<XM == 0, float, uint8_t>::type;
+    XT xn[XM == 2 ? 1 : 12];
+    auto fetch_x = [&](int n, int k) {
+      if constexpr (XM != 2) {
+        const int f = k * 128 + m;
+        const XT* xs = reinterpret_cast<const XT*>(p.x);
+        const int i = f / 33, j = f - i * 33;
 #pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int Y = min(max(2 * i - 1 + (qq >> 1), 0), 63), X = min(max(2 * j - 1 + (qq & 1), 0), 63);
-        const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
-        xv[3 * qq] = __ldg(px); xv[3 * qq + 1] = __ldg(px + 1); xv[3 * qq + 2] = __ldg(px + 2);
+        for (int qq = 0; qq < 4; ++qq) {
+          const int Y = min(max(2 * i - 1 + (qq >> 1), 0), 63), X = min(max(2 * j - 1 + (qq & 1), 0), 63);
+          const XT* px = xs + (((size_t)n * 64 + Y) * 64 + X) * 3;
+          xn[3 * qq] = __ldg(px); xn[3 * qq + 1] = __ldg(px + 1); xn[3 * qq + 2] = __ldg(px + 2);
+        }
       }
     };
-    if (tile_beg < tile_end) fetch_x(tile_beg, xn);
+    int n = tile_beg / 9, k = tile_beg - n * 9;
+    if (tile_beg < tile_end) fetch_x(n, k);
+    float l1 = 0.0f;   // |x - xhat|_1 of this thread's blocks of the current image
+    int stage = 0;
+    uint32_t ph = 0;
     for (int tile = tile_beg; tile < tile_end; ++tile) {
       const int li = tile - tile_beg, as = li & 1;
-      const int n = tile / 9, r = tile - n * 9, i = (r / 3) * 11 + li_, j = (r % 3) * 11 + lj_;
+      const int f = k * 128 + m, i = f / 33, j = f - i * 33;
+      const bool row_ok = f < 33 * 33;
+      const int n_cur = n;
+      // (consumed at the very end of the tile: an L2 access that needs no prefetch)
+      const float cb = p.coef != nullptr ? __ldg(p.coef + n_cur) : 0.0f;
       float xv[12];
+      uint4 xb = make_uint4(0u, 0u, 0u, 0u);
+      if constexpr (XM == 2) {
+        mbar_wait(&full[stage], ph);     // the MMA thread waits on the same phase; here it makes the bulk copy visible
+        xb = lds_u4(smem_u32(sA + stage * STAGE + CTR_A_STAGE) + (uint32_t)m * 16u);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (++stage == p.stages) { stage = 0; ph ^= 1; }
+      } else {
 #pragma unroll
-      for (int k2 = 0; k2 < 12; ++k2) xv[k2] = px_value<XT>(xn[k2], s_lut);
-      if (tile + 1 < tile_end) fetch_x(tile + 1, xn);
-      bool ok[4];
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) {
-        const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
-        ok[qq] = row_ok && (unsigned)Y < 64u && (unsigned)X < 64u;
+        for (int k2 = 0; k2 < 12; ++k2) xv[k2] = px_value<XT>(xn[k2], s_lut);
       }
-      const float cb = p.coef != nullptr ? __ldg(p.coef + n) : 0.0f;
+      if (++k == 9) { k = 0; ++n; }
+      if (tile + 1 < tile_end) fetch_x(n, k);
       mbar_wait(&tfull[as], (uint32_t)(li >> 1) & 1u);
       tc_fence_after();
       if (threadIdx.x == 64) TL(li, 4);
@@ -1585,30 +1659,47 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       tc_fence_before();
       if (lane == 0) mbar_arrive(&tempty[as]);
       if (threadIdx.x == 64) TL(li, 5);
-      // branch-free arithmetic: 12 independent sigmoid / sign chains the scheduler can interleave
+      if constexpr (XM == 2) {   // table lookups: their shared-memory latency hides behind the sigmoid chains below
+        const uint32_t w[3] = {xb.x, xb.y, xb.z};
+#pragma unroll
+        for (int k2 = 0; k2 < 12; ++k2) xv[k2] = s_lut[(w[k2 >> 2] >> (8 * (k2 & 3))) & 0xffu];
+      }
+      // pixel (dy, dx) of block (i, j) lies in the image unless the block touches that border
+      const bool oky[2] = {row_ok && i > 0, row_ok && i < 32}, okx[2] = {j > 0, j < 32};
+      bool ok[4];
+      float okf[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) {
+        ok[qq] = oky[qq >> 1] && okx[qq & 1];
+        okf[qq] = ok[qq] ? 1.0f : 0.0f;
+      }
+      // branch-free arithmetic, 12 independent chains: xhat = 1 / (1 + 2^(-(a + b) log2 e)); every row of the tile reads
+      // operand rows the box has written (zero-filled outside the image), so rows without work hold finite values
       float xh[12], g[12];
-      float l1 = 0.0f;
 #pragma unroll
       for (int k2 = 0; k2 < 12; ++k2) {
         const int qq = k2 / 3, c = k2 % 3;
-        // rows 121..127 of the MMA tile are never loaded (stale shared memory, possibly NaN patterns): zero them
-        const float a = row_ok ? __uint_as_float(acc[4 * qq + c]) : 0.0f;
-        const float logit = a + (c == 0 ? b0 : (c == 1 ? b1 : b2));
-        xh[k2] = __fdividef(1.0f, 1.0f + __expf(-logit));
+        const float t = fmaf(__uint_as_float(acc[4 * qq + c]), -LOG2E, c == 0 ? nb0 : (c == 1 ? nb1 : nb2));
+        xh[k2] = rcp_approx(1.0f + ex2_approx(t));
       }
+      float cq[4];
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) cq[qq] = okf[qq] * cb;
 #pragma unroll
       for (int k2 = 0; k2 < 12; ++k2) {
-        const float okf = ok[k2 / 3] ? 1.0f : 0.0f;
+        const int qq = k2 / 3;
         const float e = xv[k2] - xh[k2];
-        const float sgn = (e > 0.0f ? 1.0f : 0.0f) - (e < 0.0f ? 1.0f : 0.0f);
-        l1 = fmaf(okf, fabsf(e), l1);
-        g[k2] = okf * cb * sgn * xh[k2] * (1.0f - xh[k2]);
+        l1 = fmaf(okf[qq], fabsf(e), l1);
+        // dLoss/dlogit = coef * sign(x - xhat) * xhat (1 - xhat):  the sign bit of e flips s, e == 0 gives 0
+        const float s = fmaf(-xh[k2], xh[k2], xh[k2]) * cq[qq];
+        const float sg = __uint_as_float(__float_as_uint(s) ^ (__float_as_uint(e) & 0x80000000u));
+        g[k2] = e != 0.0f ? sg : 0.0f;
       }
       d0 += g[0] + g[3] + g[6] + g[9];
       d1 += g[1] + g[4] + g[7] + g[10];
       d2 += g[2] + g[5] + g[8] + g[11];
       if (p.D2 != nullptr && row_ok) {
-        uint4* dst = p.D2 + (((size_t)n * 33 + i) * 33 + j) * 2;
+        uint4* dst = p.D2 + ((size_t)n_cur * 1089 + f) * 2;
         dst[0] = make_uint4(pack_bf16x2(g[0], g[1]), pack_bf16x2(g[2], 0.0f), pack_bf16x2(g[3], g[4]), pack_bf16x2(g[5], 0.0f));
         dst[1] = make_uint4(pack_bf16x2(g[6], g[7]), pack_bf16x2(g[8], 0.0f), pack_bf16x2(g[9], g[10]), pack_bf16x2(g[11], 0.0f));
       }
@@ -1617,12 +1708,17 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
         for (int qq = 0; qq < 4; ++qq)
           if (ok[qq]) {
             const int Y = 2 * i - 1 + (qq >> 1), X = 2 * j - 1 + (qq & 1);
-            float* dstx = p.xhat + (((size_t)n * 64 + Y) * 64 + X) * 3;
+            float* dstx = p.xhat + (((size_t)n_cur * 64 + Y) * 64 + X) * 3;
             dstx[0] = xh[3 * qq]; dstx[1] = xh[3 * qq + 1]; dstx[2] = xh[3 * qq + 2];
           }
       }
-      l1 = warp_sum(l1);
-      if (lane == 0 && l1 != 0.0f) atomicAdd(p.log_pxz + n, -l1);
+      // the likelihood sum leaves the registers once per image (and at the end of the CTA's range), not once per tile:
+      // five dependent shuffles per tile were 10 % of the kernel's stall samples
+      if (k == 0 || tile + 1 == tile_end) {
+        l1 = warp_sum(l1);
+        if (lane == 0 && l1 != 0.0f) atomicAdd(p.log_pxz + n_cur, -l1);
+        l1 = 0.0f;
+      }
       if (threadIdx.x == 64) TL(li, 6);
     }
     if (p.db != nullptr) {
@@ -1630,6 +1726,11 @@ __global__ void __launch_bounds__(TG_THREADS) convt_recon_kernel(const __grid_co
       if (lane == 0) { atomicAdd(&s_db[0], d0); atomicAdd(&s_db[1], d1); atomicAdd(&s_db[2], d2); }
     }
     tc_fence_before();
+  }
+  if (TL_ON(p) && threadIdx.x == 0 && blockIdx.x < 1024) {
+    unsigned long long gt;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(gt));
+    p.timeline[40 * 8 + 2 * blockIdx.x + 1] = (long long)gt;
   }
   __syncthreads();
   if (p.db != nullptr && threadIdx.x < 3 && s_db[threadIdx.x] != 0.0f) atomicAdd(p.db + threadIdx.x, s_db[threadIdx.x]);
@@ -2477,22 +2578,25 @@ extern "C" int gccvae_sl_halo_bf16(const gccvae_geom* g, const void* S, const vo
 
 
 // ---- x2 (space-to-depth) end layers ----------------------------------------------------------------------
-// x [B,64,64,3] (fp32 in [0,1], or uint8 0..255 which is divided by 255 on the fly) -> X2 [B,33,33,16] bf16
-extern "C" int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* stream) {
+// x [B,64,64,3] (fp32 in [0,1], or uint8 0..255 which is divided by 255 on the fly) -> X2 [B,33,33,16] bf16 and, for
+// uint8 images, optionally XB [B,33,33,16] uint8: the raw bytes of every block (gccvae_convt_recon_bf16 with x_u8 = 2)
+extern "C" int gccvae_prep_x2_bf16(const void* x, int x_u8, int batch, void* X2, void* XB, void* stream) {
   GCC_REQUIRE(x && X2 && batch > 0, "prep_x2: bad args");
+  GCC_REQUIRE(XB == nullptr || x_u8, "prep_x2: the raw-byte blocks exist for uint8 images only");
+  GCC_REQUIRE(((uintptr_t)X2 % 16) == 0 && ((uintptr_t)XB % 16) == 0, "prep_x2: outputs must be 16-byte aligned");
   const long long total = (long long)batch * 33 * 33;
   long long ctas = (total + 255) / 256;
   if (ctas > 148 * 16) ctas = 148 * 16;
   if (int rc2 = ensure_u8lut()) return rc2;
   if (x_u8 && (uintptr_t)x % 16 == 0)
     GCC_CUDA(launch_pdl_k(prep_x2_u8_staged_kernel, dim3(batch < 148 * 8 ? batch : 148 * 8), dim3(256), 0, (cudaStream_t)stream,
-                          (const uint8_t*)x, batch, (uint4*)X2));
+                          (const uint8_t*)x, batch, (uint4*)X2, (uint4*)XB));
   else if (x_u8)
     GCC_CUDA(launch_pdl_k(prep_x2_kernel<uint8_t>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, (const uint8_t*)x,
-                          total, (uint4*)X2));
+                          total, (uint4*)X2, (uint4*)XB));
   else
     GCC_CUDA(launch_pdl_k(prep_x2_kernel<float>, dim3((int)ctas), dim3(256), 0, (cudaStream_t)stream, (const float*)x, total,
-                          (uint4*)X2));
+                          (uint4*)X2, (uint4*)nullptr));
   GCC_CHECK_LAUNCH("prep_x2");
   return GCCVAE_OK;
 }
@@ -2538,7 +2642,7 @@ extern "C" int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void
 
 // S -> L of a k4/s2/p1 layer (Conv2DTranspose forward / Conv2D dgrad) in BLOCK form:
 //   blocks[n, i, j, (dy,dx), cl] = sum_{a,b in {0,1}} sum_cs S[n, i - a, j - b, cs] * W[2a + dy, 2b + dx, cl, cs]
-// (oracle/block_forms.py: convT_k4s2_to_blocks) - a 2x2-tap stride-1 gather over S with N = 4 CL output columns, so one
+// (restated in the test tree, block_forms.py: convT_k4s2_to_blocks) - a 2x2-tap stride-1 gather over S with N = 4 CL output columns, so one
 // 128-row tile produces 4 x 128 output pixels from 4 x (128 x CS) operand bytes, against 16 (phase, tap) operand tiles
 // per 128 pixels in the phase formulation.  The tile's rows are the (WS + 1) blocks of one block row of `bn` images;
 // the epilogue writes each slot to its pixel of L (NHWC, or s2d storage with GCCVAE_OUT_S2D) and drops the slots that
@@ -2649,6 +2753,7 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
                                        int log_pxz_ready, void* stream) {
   GCC_REQUIRE(g4 && Wp8 && bias && x && log_pxz && batch > 0, "convt_recon: null pointer");
   GCC_REQUIRE((coef == nullptr) == (D2 == nullptr), "convt_recon: coef and D2 go together");
+  GCC_REQUIRE(x_u8 >= 0 && x_u8 <= 2 && (x_u8 != 2 || (uintptr_t)x % 16 == 0), "convt_recon: x_u8 = %d (0 fp32 image, 1 uint8 image, 2 raw-byte blocks, 16-byte aligned)", x_u8);
   cudaStream_t st = (cudaStream_t)stream;
   CtrParams p;
   memset(&p, 0, sizeof(p));
@@ -2657,7 +2762,7 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   {
     cuuint64_t dims[4] = {32, 32, 32, (cuuint64_t)batch};
     cuuint64_t strides[3] = {64, 32 * 64, 32 * 32 * 64};
-    cuuint32_t box[4] = {32, 11, 11, 1};
+    cuuint32_t box[4] = {32, 33, 6, 1};   // 6 image rows x (zero column + 32 pixels): CTR_BOX_ROWS rows of 64 bytes
     cuuint32_t estr[4] = {1, 1, 1, 1};
     CUresult r = enc(&p.tmA, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(g4), dims, strides, box, estr,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
@@ -2669,28 +2774,30 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
   p.x = x; p.x_u8 = x_u8; p.bias = bias; p.coef = coef; p.log_pxz = log_pxz; p.D2 = (uint4*)D2; p.xhat = xhat; p.db = db;
   p.batch = batch; p.total_tiles = batch * 9;
   p.timeline = g_timeline;
-  // CTAs per SM: the kernel is bound by the latency of its per-tile chain (TMA -> MMA -> epilogue), not by a
-  // throughput: more resident CTAs = more tiles in flight.  Limits: 4 x 77 registers x 192 threads, 4 x 39 KB of shared
-  // memory (one A stage each), 4 x 64 TMEM columns.  GCCVAE_CTR_PER_SM overrides (A/B runs).
-  static int env_per_sm = -1;
+  // CTAs per SM and A stages per CTA: more resident CTAs = more tiles in flight (the per-tile chain TMA -> MMA ->
+  // epilogue is latency-bound).  Limits: registers x 192 threads, 64 TMEM columns and 4 KB + stages x 13 KB of shared
+  // memory per CTA.  GCCVAE_CTR_PER_SM / GCCVAE_CTR_STAGES override (A/B runs).
+  static int env_per_sm = -1, env_stages = -1;
   if (env_per_sm < 0) {
     const char* e = getenv("GCCVAE_CTR_PER_SM");
     env_per_sm = e ? atoi(e) : 0;
+    e = getenv("GCCVAE_CTR_STAGES");
+    env_stages = e ? atoi(e) : 0;
   }
-  int per_sm = env_per_sm > 0 ? env_per_sm : 4;   // measured on B200 (batch 1024): 2 -> 1.469, 3 -> 1.444, 4 -> 1.430 ms per step pair
-  if (per_sm > 4) per_sm = 4;
-  // (3 CTAs x 2 stages fit as well - 224 KB / 3 - but measured slower than 4 x 1: the kernel is bound by the TMA
-  // row rate, profiles/r01c_timeline_probe.txt)
-  int stages = (200 * 1024 / per_sm - 4096 - 4096) / (4 * 8192);
+  int per_sm = env_per_sm > 0 ? env_per_sm : 4;
+  if (per_sm > 6) per_sm = 6;
+  int stages = env_stages > 0 ? env_stages : 3;
   if (stages > 4) stages = 4;
-  GCC_REQUIRE(stages >= 1, "convt_recon: shared memory");
+  const int stage_bytes = CTR_A_STAGE + (x_u8 == 2 ? CTR_X_BYTES : 0);
+  while (stages > 1 && per_sm * (4096 + stages * stage_bytes + 1024 + 2048 + 1024) > 227 * 1024) --stages;
   p.stages = stages;
-  const size_t smem = 4096 + (size_t)stages * 4 * 8192 + 1024 + 2048;
+  const size_t smem = 4096 + (size_t)stages * stage_bytes + 1024 + 2048;
   if (int rc2 = ensure_u8lut()) return rc2;
   static bool attr_set = false;
   if (!attr_set) {
-    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
-    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<uint8_t>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
+    GCC_CUDA(cudaFuncSetAttribute(convt_recon_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
   if (!log_pxz_ready) {   // otherwise the caller pre-set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32) off the critical path
@@ -2702,8 +2809,9 @@ extern "C" int gccvae_convt_recon_bf16(int batch, const void* g4, const void* Wp
     const int per_cta = (p.total_tiles + ctas - 1) / ctas;
     ctas = (p.total_tiles + per_cta - 1) / per_cta;
   }
-  if (x_u8) GCC_CUDA(launch_pdl(convt_recon_kernel<uint8_t>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
-  else GCC_CUDA(launch_pdl(convt_recon_kernel<float>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
+  if (x_u8 == 2) GCC_CUDA(launch_pdl(convt_recon_kernel<2>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
+  else if (x_u8) GCC_CUDA(launch_pdl(convt_recon_kernel<1>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
+  else GCC_CUDA(launch_pdl(convt_recon_kernel<0>, dim3(ctas, 1, 1), TG_THREADS, smem, st, p));
   GCC_CHECK_LAUNCH("convt_recon");
   return GCCVAE_OK;
 }

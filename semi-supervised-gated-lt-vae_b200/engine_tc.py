@@ -195,7 +195,9 @@ class EngineTC(Engine):
         dev = self.device
         e = lambda *s, dt=torch.float32: torch.zeros(*s, dtype=dt, device=dev)
         b = {}
-        b["X2"] = e(B, 33, 33, 16, dt=BF16)      # input image in x2 block form
+        # input image in x2 block form [B,33,33,16] bf16, followed (same allocation, so that the graph variants' private
+        # copies carry both) by the raw bytes of the blocks [B,33,33,16] uint8 that prep_x2 writes for uint8 images
+        b["X2"] = e(B * 33 * 33 * 24, dt=BF16)
         b["D2"] = e(B, 33, 33, 16, dt=BF16)      # dLoss/dlogit of the reconstruction in x2 block form
         b["xhat3"] = None                        # fp32 reconstruction, allocated on demand (tests / API)
         for name in ["enc.conv1", "enc.conv2", "enc.conv3", "enc.conv4", "enc.conv5"]:
@@ -386,11 +388,21 @@ class EngineTC(Engine):
         with torch.cuda.stream(self.side2):
             u8 = int(x.dtype == torch.uint8)
             if not self.x2_ready:     # (a replayed step gets its image blocks from the copy stream, ahead of the replay)
-                self._run("prep_x2", (x, b["X2"]), lambda: self.lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), _stream()))
+                self._run("prep_x2", (x, b["X2"]), lambda: self.prep_x2(x, b["X2"], _stream()))
             if log_pxz is not None:
                 _lib.check(self.lib.gccvae_fill_f32(ptr(log_pxz), B, -12288.0 * 0.6931471805599453, _stream()), "fill")
         self._begun = True
         self._log_pxz_ready = log_pxz is not None
+
+    @staticmethod
+    def xb_ptr(x2, B):
+        """address of the raw-byte blocks behind the B x 1089 bf16 blocks of an X2 buffer"""
+        return ptr(x2) + B * 1089 * 32
+
+    def prep_x2(self, x, x2, stream):
+        """image [B,64,64,3] (fp32 or uint8) -> x2 blocks (+ raw-byte blocks for uint8 images) in the buffer `x2`"""
+        B, u8 = x.shape[0], int(x.dtype == torch.uint8)
+        return self.lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(x2), self.xb_ptr(x2, B) if u8 else None, stream)
 
     def encoder_fwd(self, x, b, heads=True):
         B = x.shape[0]
@@ -405,7 +417,7 @@ class EngineTC(Engine):
             self.pack_weights()
             u8 = int(x.dtype == torch.uint8)
             if not self.x2_ready:
-                self._run("prep_x2", (x, b["X2"]), lambda: lib.gccvae_prep_x2_bf16(ptr(x), u8, B, ptr(b["X2"]), st))
+                self._run("prep_x2", (x, b["X2"]), lambda: self.prep_x2(x, b["X2"], st))
         self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU | OUT_S2D, None,
             ptr(b["enc.conv1.out"]), st))
@@ -469,7 +481,8 @@ class EngineTC(Engine):
         v = self.store.view
         self._run("dec.conv5t fwd+recon", (b["dec.conv4t.out"], x, b["D2"] if backward else None),
                   lambda: self.lib.gccvae_convt_recon_bf16(
-                      B, ptr(b["dec.conv4t.out"]), ptr(self.wp["dec.conv5t.x2t"]), ptr(v("dec.conv5t.b")), ptr(x), u8,
+                      B, ptr(b["dec.conv4t.out"]), ptr(self.wp["dec.conv5t.x2t"]), ptr(v("dec.conv5t.b")),
+                      self.xb_ptr(b["X2"], B) if u8 else ptr(x), 2 * u8,    # uint8 images: the raw-byte blocks prep_x2 wrote
                       ptr(coef) if backward else None, ptr(log_pxz), ptr(b["D2"]) if backward else None, ptr(xhat),
                       ptr(self.store.g("dec.conv5t.b")) if backward else None, int(getattr(self, "_log_pxz_ready", False)),
                       _stream()))

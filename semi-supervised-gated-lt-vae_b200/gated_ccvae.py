@@ -635,7 +635,7 @@ class Learner:
                 if supervised:
                     g["y"].copy_(torch.as_tensor(y), non_blocking=True)
                 if g["x2"] is not None:
-                    _lib.check(self.lib.gccvae_prep_x2_bf16(ptr(g["x"]), int(u8), B, ptr(g["x2"]), cs.cuda_stream), "prep_x2")
+                    _lib.check(self.engine.prep_x2(g["x"], g["x2"], cs.cuda_stream), "prep_x2")
                 ready = torch.cuda.Event()
                 ready.record(cs)
             main.wait_event(ready)

@@ -119,7 +119,7 @@ def test_c3conv_s2d_output():
     W = (torch.randn(4, 4, 3, 32, generator=g) * 0.2).to(d)
     bias = (torch.randn(32, generator=g) * 0.1).to(d)
     X2 = torch.empty(B, 33, 33, 16, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_prep_x2_bf16(L.ptr(x), 0, B, L.ptr(X2), _stream()))
+    L.check(lib.gccvae_prep_x2_bf16(L.ptr(x), 0, B, L.ptr(X2), None, _stream()))
     wp = torch.zeros(32 * 64, dtype=torch.bfloat16, device=d)
     job = (L.PackJob * 1)(L.PackJob(7, 16, 3, 32, L.ptr(W), L.ptr(wp), 0, 0, 0, 0, 0, 0))
     L.check(lib.gccvae_pack_jobs_bf16(job, 1, _stream()))

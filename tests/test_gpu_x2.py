@@ -57,10 +57,38 @@ def test_prep_x2(u8):
         x = torch.rand(B, 64, 64, 3, generator=g)
         xin = x.to(d)
     X2 = torch.full((B, 33, 33, 16), float("nan"), dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_prep_x2_bf16(L.ptr(xin), int(u8), B, L.ptr(X2), _stream()))
+    L.check(lib.gccvae_prep_x2_bf16(L.ptr(xin), int(u8), B, L.ptr(X2), None, _stream()))
     torch.cuda.synchronize()
     want = x2_blocks(x).to(torch.bfloat16)
     assert torch.equal(X2.cpu().view(torch.int16), want.view(torch.int16)), "x2 block transform must be bit-exact"
+    if u8:
+        # the raw-byte blocks (image operand of the fused likelihood kernel): staged kernel (16-byte aligned image) and
+        # the per-block kernel (unaligned image) must both give the block's 12 bytes + 4 zero bytes, zero outside the image
+        want_b = _raw_byte_blocks(xi)
+        for shift in (0, 1):
+            buf = torch.zeros(xi.numel() + 16, dtype=torch.uint8, device=d)
+            buf[shift:shift + xi.numel()] = xi.reshape(-1).to(d)
+            XB = torch.full((B, 33, 33, 16), 0xAB, dtype=torch.uint8, device=d)
+            X2.fill_(float("nan"))
+            L.check(lib.gccvae_prep_x2_bf16(L.ptr(buf) + shift, 1, B, L.ptr(X2), L.ptr(XB), _stream()))
+            torch.cuda.synchronize()
+            assert torch.equal(XB.cpu(), want_b), ("raw-byte blocks", shift)
+            assert torch.equal(X2.cpu().view(torch.int16), want.view(torch.int16))
+    else:
+        assert lib.gccvae_prep_x2_bf16(L.ptr(xin), 0, B, L.ptr(X2), L.ptr(X2), _stream()) != 0   # fp32 images have no raw bytes
+
+
+def _raw_byte_blocks(xi):
+    """[B,64,64,3] uint8 -> [B,33,33,16] uint8: block (i, j) = pixels (2i-1+dy, 2j-1+dx) x 3 channels, 4 zero bytes."""
+    B = xi.shape[0]
+    pad = torch.zeros(B, 66, 66, 3, dtype=torch.uint8)
+    pad[:, 1:65, 1:65] = xi
+    out = torch.zeros(B, 33, 33, 16, dtype=torch.uint8)
+    for dy in range(2):
+        for dx in range(2):
+            q = dy * 2 + dx
+            out[..., 3 * q:3 * q + 3] = pad[:, dy:dy + 65:2, dx:dx + 65:2][:, :33, :33]
+    return out
 
 
 def test_u8_normalisation_is_bit_exact_for_all_256_values():
@@ -103,7 +131,7 @@ def test_conv1_x2_forward_and_wgrad(impl):
     bias = torch.randn(32, generator=g) * 0.1
     xd, Wd, bd = x.to(d), W.to(d), bias.to(d)
     X2 = torch.empty(B, 33, 33, 16, dtype=torch.bfloat16, device=d)
-    L.check(lib.gccvae_prep_x2_bf16(L.ptr(xd), 0, B, L.ptr(X2), _stream()))
+    L.check(lib.gccvae_prep_x2_bf16(L.ptr(xd), 0, B, L.ptr(X2), None, _stream()))
     wp = pack(lib, L, 7, Wd, 32 * 64)
     h1 = torch.full((B, 32, 32, 32), float("nan"), dtype=torch.bfloat16, device=d)
     L.check(ls(X2, wp, bd, L.ACT_RELU, None, h1))
@@ -131,16 +159,20 @@ def test_conv1_x2_forward_and_wgrad(impl):
     assert err < 1e-4, ("conv1 x2 wgrad", err)
 
 
-@pytest.mark.parametrize("u8", [False, True])
-def test_fused_conv5t_recon(u8):
+@pytest.mark.parametrize("B", [5, 1, 70])
+@pytest.mark.parametrize("u8", [0, 1, 2])
+def test_fused_conv5t_recon(u8, B):
+    """u8 = form of the image operand: 0 fp32 image, 1 uint8 image, 2 the raw-byte blocks of prep_x2.  Batch 70 (630 tiles,
+    more than the 592 resident CTAs) gives every CTA a range of two tiles, some of which cross an image boundary."""
     L, lib = _lib()
     d = torch.device("cuda", 0)
     g = torch.Generator().manual_seed(7)
-    B = 5
     if u8:
         xi = torch.randint(0, 256, (B, 64, 64, 3), generator=g, dtype=torch.uint8)
         x = torch.from_numpy(xi.numpy().astype(np.float32) / 255.0)
         xin = xi.to(d)
+        if u8 == 2:
+            xin = _raw_byte_blocks(xi).to(d)
     else:
         x = torch.rand(B, 64, 64, 3, generator=g)
         xin = x.to(d)
@@ -154,7 +186,7 @@ def test_fused_conv5t_recon(u8):
     D2 = torch.full((B, 33, 33, 16), float("nan"), dtype=torch.bfloat16, device=d)
     xhat = torch.full((B, 64, 64, 3), float("nan"), device=d)
     db = torch.zeros(3, device=d)
-    L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), int(u8), L.ptr(coefd), L.ptr(lpx),
+    L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), u8, L.ptr(coefd), L.ptr(lpx),
                                         L.ptr(D2), L.ptr(xhat), L.ptr(db), 0, _stream()))
     torch.cuda.synchronize()
     want_xh = torch.sigmoid(O._convT(bf(g4).double(), bf(W5).double(), b5.double(), 2, 1))
@@ -170,7 +202,7 @@ def test_fused_conv5t_recon(u8):
     assert float((db.cpu().double() - dlogit.sum((0, 1, 2))).abs().max() / dlogit.sum((0, 1, 2)).abs().max()) < 1e-3
     # forward-only form: no gradient outputs
     lp2 = torch.empty(B, device=d)
-    L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), int(u8), None, L.ptr(lp2), None,
+    L.check(lib.gccvae_convt_recon_bf16(B, L.ptr(g4d), L.ptr(w8), L.ptr(b5d), L.ptr(xin), u8, None, L.ptr(lp2), None,
                                         None, None, 0, _stream()))
     torch.cuda.synchronize()
     assert float((lp2 - lpx).abs().max() / lpx.abs().max()) < 1e-6
