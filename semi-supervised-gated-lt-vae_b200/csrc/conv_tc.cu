@@ -250,6 +250,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
       uint32_t ph = 0;
       long long mma_wait = 0, acc_wait = 0;
       const long long tm0 = clock64();
+      // the whole issue loop is instantiated per KC / 16 (1, 2 or 4 MMAs per k-block): with a run-time trip count every
+      // UTCHMMA drags ~100 cycles of uniform-register moves and convergence code along (scripts/microbench/mma_rate.cu)
+      auto run = [&](auto kk_c) {
+      constexpr int KK = decltype(kk_c)::value;
       for (int item = item_beg; item < item_end; ++item) {
         const int li = item - item_beg, as = li & 1;
         const long long ta0 = TL_ON(p) ? clock64() : 0;
@@ -271,7 +275,8 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
             const uint32_t a_shift = (uint32_t)(p.BW * p.KC * 2) >> 4, b_shift = (uint32_t)b_tile >> 4;
             for (int j = 0; j < p.tps; ++j) {
               for (int a = 0; a < 2; ++a)
-                for (int kk = 0; kk < kk_n; ++kk)
+#pragma unroll
+                for (int kk = 0; kk < KK; ++kk)
                   umma_bf16(tacc, ad + (uint64_t)(a * a_shift + 2u * kk), bd + (uint64_t)(a * b_shift + 2u * kk), idesc,
                             (it > 0 || j > 0 || a > 0 || kk > 0) ? 1u : 0u);
               ad += a_step;
@@ -279,11 +284,13 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
             }
           } else {
           umma_bf16(tacc, ad, bd, idesc, it > 0 ? 1u : 0u);
-          for (int kk = 1; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
+#pragma unroll
+          for (int kk = 1; kk < KK; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
           for (int j = 1; j < p.tps; ++j) {
             ad += a_step;
             bd += b_step;
-            for (int kk = 0; kk < kk_n; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
+#pragma unroll
+            for (int kk = 0; kk < KK; ++kk) umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, 1u);
           }
           }
           umma_commit(&empty[stage]);
@@ -291,6 +298,10 @@ __global__ void __launch_bounds__(TG_THREADS) tapgemm_kernel(const __grid_consta
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
+      };
+      if (kk_n == 4) run(std::integral_constant<int, 4>{});
+      else if (kk_n == 2) run(std::integral_constant<int, 2>{});
+      else run(std::integral_constant<int, 1>{});
       if (TL_ON(p) && blockIdx.x == 0) {
         p.timeline[32 * 8 + 2] = mma_wait;
         p.timeline[32 * 8 + 3] = acc_wait;
@@ -707,12 +718,26 @@ __global__ void __launch_bounds__(HALO_THREADS) sl_halo_kernel(const __grid_cons
         TL(li, 3);
         const uint64_t a_st = adesc0 + (uint64_t)((uint32_t)stage * a_stage16);
         const uint32_t tacc = tmem_base + (uint32_t)as * 4u * (uint32_t)p.N;
+        // fully unrolled for both channel counts: from a loop with a run-time trip count every UTCHMMA drags ~100 cycles of
+        // uniform-register moves and convergence code along (scripts/microbench/mma_rate.cu)
+        if (kk_n == 2) {
 #pragma unroll
-        for (int view = 0; view < 9; ++view) {
-          const uint64_t ad = a_st + (uint64_t)((uint32_t)(view % 3) * avb16 + (uint32_t)(view / 3) * row16);
-          const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)view * bblk16);
-          for (int kk = 0; kk < kk_n; ++kk)
-            umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, (view > 0 || kk > 0) ? 1u : 0u);
+          for (int view = 0; view < 9; ++view) {
+            const uint64_t ad = a_st + (uint64_t)((uint32_t)(view % 3) * avb16 + (uint32_t)(view / 3) * row16);
+            const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)view * bblk16);
+#pragma unroll
+            for (int kk = 0; kk < 2; ++kk)
+              umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, (view > 0 || kk > 0) ? 1u : 0u);
+          }
+        } else {
+#pragma unroll
+          for (int view = 0; view < 9; ++view) {
+            const uint64_t ad = a_st + (uint64_t)((uint32_t)(view % 3) * avb16 + (uint32_t)(view / 3) * row16);
+            const uint64_t bd = bdesc0 + (uint64_t)((uint32_t)view * bblk16);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk)
+              umma_bf16(tacc, ad + 2u * kk, bd + 2u * kk, idesc, (view > 0 || kk > 0) ? 1u : 0u);
+          }
         }
         umma_commit(&empty[stage]);
         umma_commit(&tfull[as]);
