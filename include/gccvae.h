@@ -142,7 +142,8 @@ int gccvae_gemm_tn_bf16(long long rows, int M, int N, const void* A, const void*
 int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void* in2, const void* S, int CS, float* dW,
                        void* stream);
 /* Space-to-depth ("x2") form of the 3-channel end layers (conv1 = networks.py:11,22; conv5t = :49,58; likelihood =
- * utils.py:101-105).  X2[n,i,j,(dy,dx,c4)] = x[n,2i-1+dy,2j-1+dx,c] (bf16 [B,33,33,16], zero outside the image):
+ * utils.py:101-105).  X2[n,i,j,(dy,dx,c4)] = x[n,2i-1+dy,2j-1+dx,c] (bf16 [B,33,33,16], zero outside the image
+ * and in the pad channels - except element 15 of every block, which gccvae_prep_x2_bf16 sets to 1.0, see gccvae_tap4_wg_bf16):
  * Conv2D(k4,s2,p1) over the image is a 2x2-tap stride-1 GEMM over the blocks and Conv2DTranspose(k4,s2,same)
  * produces its output directly in block form.  x may be uint8 (0..255): it is divided by 255 on the device
  * exactly as utils_data.py:57-59 does on the host. */
@@ -155,7 +156,9 @@ int gccvae_tap4_ls_bf16(int batch, int HB, int WB, int CB, const void* in2, cons
  * by producer warps (TMA is row-rate bound on 32-byte rows): conv1 forward and conv5t dgrad.  CS in {32, 64}. */
 int gccvae_c3conv_bf16(int batch, const void* in2, const void* Wp, int CS, const float* bias, int act, const void* mask,
                        void* out, void* stream);
-int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream);
+/* db (optional; in2 must be blocks written by gccvae_prep_x2_bf16, whose element 15 is the constant 1): the bias gradient
+ * db[cs] += sum over pixels of S - the ones row of the operand turns it into one more row of the same MMAs. */
+int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, float* db, void* stream);
 /* x_u8: 0 = x is the fp32 image [B,64,64,3], 1 = the uint8 image, 2 = the raw-byte blocks XB of gccvae_prep_x2_bf16 (one
  * 16-byte load per block instead of twelve 1-byte loads).
  * log_pxz_ready != 0: the caller has already set log_pxz[b] = -12288 ln 2 (gccvae_fill_f32), e.g. on a side stream */

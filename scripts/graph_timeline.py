@@ -21,7 +21,7 @@ cfg = dict(gate_type="fixed", gate_subtype="inferred", mu_init=mu, gating_reg=0.
 lrn = G.Learner((64, 64, 3), 45, 18, 18, 1000, 0.2, cfg, precision="bf16", graphs=True,
                 dp_exchange=os.environ.get("TIMELINE_DP_EXCHANGE", "peer"),
                 engine_options=dict(markers=int(os.environ.get("TIMELINE_MARKERS", "1"))))
-x = torch.rand(B, 64, 64, 3, device="cuda")
+x = torch.randint(0, 256, (B, 64, 64, 3), dtype=torch.uint8, device="cuda") if os.environ.get("TIMELINE_U8", "1") != "0" else torch.rand(B, 64, 64, 3, device="cuda")
 y = (torch.rand(B, 18, device="cuda") < 0.5).long()
 for sup in (True, False):
     for _ in range(5):

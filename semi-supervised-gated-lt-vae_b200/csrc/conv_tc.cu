@@ -916,6 +916,7 @@ struct alignas(64) WgParams {
   // from the [B,33,33,16] block tensor instead of 8 TMA boxes of 32-byte rows (TMA is row-rate bound)
   const uint4* in2;
   int s2d_cl;   // c4_rows == 3: channels per pixel of the s2d L operand
+  float* ones_db;   // c4_rows == 2: row 15 = (tap (0,0), slot (1,1), pad channel) is all ones in prep_x2's blocks: += column sums of S
 };
 
 __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
@@ -1116,6 +1117,11 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
           mrow = p.c4_rows == 2
                      ? ((2 * (m >> 5) + ((m >> 3) & 1)) * 4 + 2 * ((m >> 4) & 1) + ((m >> 2) & 1)) * 3 + (m & 3)
                      : (p.c4_rows ? ((m >> 2) * 3 + (m & 3)) : m);
+        }
+        if (p.ones_db != nullptr && m == 15) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i)
+            if (c0 + i < p.N) atomicAdd(p.ones_db + c0 + i, __uint_as_float(r[i]));
         }
         if (m < p.out.m_valid && !((p.c4_rows == 1 || p.c4_rows == 2) && (m & 3) == 3)) {
 #pragma unroll
@@ -1389,6 +1395,11 @@ template <>
 __device__ __forceinline__ float px_value<uint8_t>(uint8_t raw, const float* lut) { return lut[raw]; }
 
 // one thread per block (n, i, j): 4 pixels x 3 channels in, 32 bytes out
+// The pad channel of the block's LAST pixel slot (element 15) is the constant 1.0 instead of 0: the layers that read X2
+// have zero weights for the pad channels, and in conv1's weight gradient (gccvae_tap4_wg_bf16) the operand row of tap
+// (0, 0), slot (1, 1), pad channel is then a row of ones over all 32 x 32 output pixels - its product with the S operand
+// is the BIAS gradient, computed by MMAs that run anyway (a separate column-sum pass over the 67 MB of conv2's dgrad
+// output was the last launch of the step).
 // XB (uint8 images only, optional): the RAW bytes of the block, [B,33,33,16] uint8 = 4 pixels x 3 channels + 4 zero bytes
 // (zero outside the image) - what the fused likelihood kernel reads back with one 16-byte load per block.
 template <typename XT>
@@ -1420,7 +1431,7 @@ __global__ void __launch_bounds__(256) prep_x2_kernel(const XT* __restrict__ x, 
         for (int c = 0; c < 3; ++c) rb[(3 * q + c) >> 2] |= raw_byte<XT>(__ldg(px + c)) << (8 * ((3 * q + c) & 3));
       }
       w[2 * q] = pack_bf16x2(v0, v1);
-      w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
+      w[2 * q + 1] = pack_bf16x2(v2, q == 3 ? 1.0f : 0.0f);   // the block's last pad slot carries the constant 1 (see above)
     }
     X2[2 * idx] = make_uint4(w[0], w[1], w[2], w[3]);
     X2[2 * idx + 1] = make_uint4(w[4], w[5], w[6], w[7]);
@@ -1459,7 +1470,7 @@ __global__ void __launch_bounds__(256) prep_x2_u8_staged_kernel(const uint8_t* _
           for (int c = 0; c < 3; ++c) rb[(3 * q + c) >> 2] |= (uint32_t)px[c] << (8 * ((3 * q + c) & 3));
         }
         w[2 * q] = pack_bf16x2(v0, v1);
-        w[2 * q + 1] = pack_bf16x2(v2, 0.0f);
+        w[2 * q + 1] = pack_bf16x2(v2, q == 3 ? 1.0f : 0.0f);
       }
       const size_t o = ((size_t)n * 1089 + blk) * 2;
       X2[o] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -2704,7 +2715,8 @@ extern "C" int gccvae_sl_blk_bf16(int batch, int HS, int WS, int CS, const void*
 
 // dW[(kh,kw,c<3), cs] (fp32, Keras layout) += sum_pix gather4(in2)[pix, (a,b,dy,dx,c4)] * S[pix, cs]
 // in2 = [B,33,33,16] bf16 x2 blocks of a 3-channel 64x64 tensor, S = [B,32,32,CS] bf16.
-extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, void* stream) {
+// db (optional, blocks written by gccvae_prep_x2_bf16 only - element 15 of every block is 1.0): db[cs] += sum_pix S[pix, cs].
+extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, int CS, float* dW, float* db, void* stream) {
   GCC_REQUIRE(in2 && S && dW && batch > 0, "tap4_wg: null pointer");
   GCC_REQUIRE(CS % 32 == 0 && CS <= 256, "tap4_wg: CS=%d unsupported (multiple of 32, <= 256)", CS);
   WgParams p;
@@ -2733,6 +2745,7 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   p.N = CS;
   p.out.n_seg = 1; p.out.m_valid = 64;
   p.out.seg[0].col0 = 0; p.out.seg[0].ncols = CS; p.out.seg[0].ld = CS; p.out.seg[0].dst = dW;
+  p.ones_db = db;
   if (g_colsum != nullptr && g_colsum_mod < 0) {   // armed by gccvae_next_launch_colsum(ptr, n, -1): sums of S
     p.colsum = g_colsum; p.colsum_n = g_colsum_n; p.colsum_side = -g_colsum_mod;
     g_colsum = nullptr;

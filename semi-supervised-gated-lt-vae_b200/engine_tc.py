@@ -418,7 +418,7 @@ class EngineTC(Engine):
             u8 = int(x.dtype == torch.uint8)
             if not self.x2_ready:
                 self._run("prep_x2", (x, b["X2"]), lambda: self.prep_x2(x, b["X2"], st))
-        self._run("enc.conv1 fwd", (b["X2"], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
+        self._run("enc.conv1 fwd", (b["X2"][:B * 1089 * 16], b["enc.conv1.out"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["X2"]), ptr(self.wp["enc.conv1.x2"]), 32, ptr(v("enc.conv1.b")), ACT_RELU | OUT_S2D, None,
             ptr(b["enc.conv1.out"]), st))
         if begun:
@@ -498,7 +498,7 @@ class EngineTC(Engine):
         g4 = b["dec.conv4t.out"]
         # conv5t from the logit gradient in x2 block form (written by the fused forward)
         self._side(lambda: self._run("dec.conv5t wgrad", (b["D2"], g4), lambda: lib.gccvae_tap4_wg_bf16(
-            B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), _stream())), lane=self.dec_wgrad_plan[0])
+            B, ptr(b["D2"]), ptr(g4), 32, ptr(g_("dec.conv5t.w")), None, _stream())), lane=self.dec_wgrad_plan[0])
         self._run("dec.conv5t dgrad", (b["D2"], g4, b["dec.conv4t.dout"]), lambda: lib.gccvae_c3conv_bf16(
             B, ptr(b["D2"]), ptr(self.wp["dec.conv5t.x2"]), 32, None, ACT_NONE | OUT_S2D, ptr(g4),
             ptr(b["dec.conv4t.dout"]), st))
@@ -600,17 +600,16 @@ class EngineTC(Engine):
             for i in (0, 1):
                 sl = slice(i * h, (i + 1) * h)
                 self._sl("enc.conv2", geom_h, dout2[sl], None, ACT_NONE, mask2[sl], dh1[sl], 0, "enc.conv2 dgrad", mask_s2d=True)
-                def wg1(sl=sl):
-                    self._bias("enc.conv1", 32, dh1[sl])
-                    self._run("enc.conv1 wgrad", (X2[sl], dh1[sl]), lambda: lib.gccvae_tap4_wg_bf16(
-                        h, ptr(X2[sl]), ptr(dh1[sl]), 32, ptr(g_("enc.conv1.w")), _stream()))
+                def wg1(sl=sl, i=i):     # (the image blocks of half i: the first B x 1089 x 16 elements of the X2 buffer)
+                    self._run("enc.conv1 wgrad", (dh1[sl],), lambda: lib.gccvae_tap4_wg_bf16(
+                        h, ptr(X2) + i * h * 1089 * 32, ptr(dh1[sl]), 32, ptr(g_("enc.conv1.w")), ptr(g_("enc.conv1.b")),
+                        _stream()))
                 self._side(wg1, lane=self.wgrad_plan[5])
             self.join_side()
             return
-        def wg1():
-            self._bias("enc.conv1", 32, dh1)
-            self._run("enc.conv1 wgrad", (b["X2"], dh1), lambda: lib.gccvae_tap4_wg_bf16(
-                B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), _stream()))
+        def wg1():     # conv1's bias gradient comes out of the same launch (the ones slot of prep_x2's blocks)
+            self._run("enc.conv1 wgrad", (b["X2"][:B * 1089 * 16], dh1), lambda: lib.gccvae_tap4_wg_bf16(
+                B, ptr(b["X2"]), ptr(dh1), 32, ptr(g_("enc.conv1.w")), ptr(g_("enc.conv1.b")), _stream()))
         self._side(wg1, lane=self.wgrad_plan[5])
         self.join_side()
 

@@ -26,12 +26,17 @@ def bf(t):
     return t.to(torch.bfloat16).to(torch.float32)
 
 
-def x2_blocks(img):
-    """[B,64,64,3] -> [B,33,33,16] with X2[n,i,j,(dy,dx,c4)] = img[n,2i-1+dy,2j-1+dx,c] (zero outside / pad)."""
+def x2_blocks(img, ones=False):
+    """[B,64,64,3] -> [B,33,33,16] with X2[n,i,j,(dy,dx,c4)] = img[n,2i-1+dy,2j-1+dx,c] (zero outside / pad).
+    ones=True: as gccvae_prep_x2_bf16 writes the blocks - element 15 (pad channel of the last pixel slot) is 1.0, the
+    constant row that turns conv1's weight gradient into its bias gradient as well."""
     B = img.shape[0]
     pad = torch.zeros(B, 66, 66, 4, dtype=img.dtype)
     pad[:, 1:65, 1:65, :3] = img
     blk = pad.view(B, 33, 2, 33, 2, 4).permute(0, 1, 3, 2, 4, 5).reshape(B, 33, 33, 16)
+    if ones:
+        blk = blk.clone()
+        blk[..., 15] = 1
     return blk
 
 
@@ -59,7 +64,7 @@ def test_prep_x2(u8):
     X2 = torch.full((B, 33, 33, 16), float("nan"), dtype=torch.bfloat16, device=d)
     L.check(lib.gccvae_prep_x2_bf16(L.ptr(xin), int(u8), B, L.ptr(X2), None, _stream()))
     torch.cuda.synchronize()
-    want = x2_blocks(x).to(torch.bfloat16)
+    want = x2_blocks(x, ones=True).to(torch.bfloat16)
     assert torch.equal(X2.cpu().view(torch.int16), want.view(torch.int16)), "x2 block transform must be bit-exact"
     if u8:
         # the raw-byte blocks (image operand of the fused likelihood kernel): staged kernel (16-byte aligned image) and
@@ -151,12 +156,21 @@ def test_conv1_x2_forward_and_wgrad(impl):
     dh1 = torch.randn(B, 32, 32, 32, generator=g)
     dh1d = dh1.to(d).to(torch.bfloat16).contiguous()
     dW = torch.zeros(4, 4, 3, 32, device=d)
-    L.check(lib.gccvae_tap4_wg_bf16(B, L.ptr(X2), L.ptr(dh1d), 32, L.ptr(dW), _stream()))
+    db = torch.full((32,), 0.25, device=d)      # the kernel ADDS the bias gradient (ones slot of prep_x2's blocks)
+    L.check(lib.gccvae_tap4_wg_bf16(B, L.ptr(X2), L.ptr(dh1d), 32, L.ptr(dW), L.ptr(db), _stream()))
     torch.cuda.synchronize()
     Wg = torch.zeros(4, 4, 3, 32, dtype=torch.float64, requires_grad=True)
     (O._conv(bf(x).double(), Wg, None, 2, 1) * bf(dh1).double()).sum().backward()
     err = float((dW.cpu().double() - Wg.grad).abs().max() / Wg.grad.abs().max())
     assert err < 1e-4, ("conv1 x2 wgrad", err)
+    want_db = bf(dh1).double().sum((0, 1, 2))
+    err = float((db.cpu().double() - 0.25 - want_db).abs().max() / want_db.abs().max())
+    assert err < 1e-5, ("conv1 bias gradient from the ones row", err)
+    # without db the ones row is dropped like the other pad rows
+    dW2 = torch.zeros(4, 4, 3, 32, device=d)
+    L.check(lib.gccvae_tap4_wg_bf16(B, L.ptr(X2), L.ptr(dh1d), 32, L.ptr(dW2), None, _stream()))
+    torch.cuda.synchronize()
+    assert float((dW2 - dW).abs().max()) <= 1e-5 * float(dW.abs().max())
 
 
 @pytest.mark.parametrize("B", [5, 1, 70])
@@ -211,7 +225,7 @@ def test_fused_conv5t_recon(u8, B):
     dg4 = torch.empty(B, 32, 32, 32, dtype=torch.bfloat16, device=d)
     L.check(lib.gccvae_c3conv_bf16(B, L.ptr(D2), L.ptr(wp7), 32, None, L.ACT_NONE, L.ptr(g4d), L.ptr(dg4), _stream()))
     dW5 = torch.zeros(4, 4, 3, 32, device=d)
-    L.check(lib.gccvae_tap4_wg_bf16(B, L.ptr(D2), L.ptr(g4d), 32, L.ptr(dW5), _stream()))
+    L.check(lib.gccvae_tap4_wg_bf16(B, L.ptr(D2), L.ptr(g4d), 32, L.ptr(dW5), None, _stream()))
     torch.cuda.synchronize()
     want = O._conv(bf(dlogit.float()).double(), bf(W5).double(), None, 2, 1) * (bf(g4).double() > 0)
     err = float((dg4.float().cpu().double() - want).abs().max() / want.abs().max())
