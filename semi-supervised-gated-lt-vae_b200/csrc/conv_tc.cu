@@ -917,6 +917,7 @@ struct alignas(64) WgParams {
   const uint4* in2;
   int s2d_cl;   // c4_rows == 3: channels per pixel of the s2d L operand
   float* ones_db;   // c4_rows == 2: row 15 = (tap (0,0), slot (1,1), pad channel) is all ones in prep_x2's blocks: += column sums of S
+  long long* timeline;   // instrumented build only (scripts/timeline_wgrad.py)
 };
 
 __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant__ WgParams p) {
@@ -979,24 +980,43 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
       if (elect_one()) {
         int stage = 0;
         uint32_t ph = 0;
+        // everything that does not change from tile to tile is computed once, and the tile coordinates advance
+        // incrementally: the divisions by run-time values cost ~0.2 us of the ~0.35 us this thread needed per tile
+        // (scripts/timeline_wgrad.py), on the round trip of a pipeline that is two stages deep
+        const int n_bl = p.in2 != nullptr ? 0 : p.blocks_per_mtile;
+        int bl_c[8], bl_dw[8], bl_dh[8];
+        bool bl_real[8];
+#pragma unroll
+        for (int bl = 0; bl < 8; ++bl) {
+          const int bg = mtile * p.blocks_per_mtile + bl;
+          const int t = bg / p.blocks_per_tap;
+          // blocks past the last tap are loaded from out-of-range images: TMA zero-fills them
+          bl_real[bl] = t < p.taps;
+          bl_c[bl] = (bg - t * p.blocks_per_tap) * p.kcA;
+          bl_dw[bl] = bl_real[bl] ? p.a_dw[t] : 0;
+          bl_dh[bl] = bl_real[bl] ? p.a_dh[t] : 0;
+        }
+        const uint32_t tx = (uint32_t)((p.in2 != nullptr ? 0 : a_bytes) + b_bytes);
+        int grp = tile_beg / tiles_per_group, tin = tile_beg - grp * tiles_per_group;
+        int tw = tin % p.tiles_w, th = tin / p.tiles_w;
         for (int it = 0; it < n_tiles; ++it) {
-          const int tile = tile_beg + it;
-          const int grp = tile / tiles_per_group, tin = tile % tiles_per_group;
-          const int w0 = (tin % p.tiles_w) * p.BW, h0 = (tin / p.tiles_w) * p.BH, n0 = grp * p.BN;
+          const int w0 = tw * p.BW, h0 = th * p.BH, n0 = grp * p.BN;
           mbar_wait(&empty[stage], ph ^ 1);
-          mbar_expect_tx(&full[stage], (uint32_t)((p.in2 != nullptr ? 0 : a_bytes) + b_bytes));
-          for (int bl = 0; bl < (p.in2 != nullptr ? 0 : p.blocks_per_mtile); ++bl) {
-            const int bg = mtile * p.blocks_per_mtile + bl;
-            const int t = bg / p.blocks_per_tap, cb = bg % p.blocks_per_tap;
-            // blocks past the last tap are loaded from out-of-range images: TMA zero-fills them
-            const bool real = t < p.taps;
-            tma_load_4d(sA + stage * a_bytes + bl * a_slab, &p.tmA, &full[stage], cb * p.kcA,
-                        p.a_scale * w0 + (real ? p.a_dw[t] : 0), p.a_scale * h0 + (real ? p.a_dh[t] : 0),
-                        real ? n0 : 0x3fffff00);
-          }
+          if (blockIdx.y == 0) TL(it, 0);
+          mbar_expect_tx(&full[stage], tx);
+#pragma unroll
+          for (int bl = 0; bl < 8; ++bl)
+            if (bl < n_bl)
+              tma_load_4d(sA + stage * a_bytes + bl * a_slab, &p.tmA, &full[stage], bl_c[bl], p.a_scale * w0 + bl_dw[bl],
+                          p.a_scale * h0 + bl_dh[bl], bl_real[bl] ? n0 : 0x3fffff00);
           for (int h = 0; h < p.b_loads; ++h)
             tma_load_4d(sB + stage * b_bytes + h * b_slab, &p.tmB, &full[stage], h * p.kcB, w0, h0, n0);
+          if (blockIdx.y == 0) TL(it, 1);
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
+          if (++tw == p.tiles_w) {
+            tw = 0;
+            if (++th == p.tiles_h) { th = 0; ++grp; }
+          }
         }
       }
     } else if (warp == 1) {
@@ -1009,9 +1029,11 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         int stage = 0;
         uint32_t ph = 0;
         for (int it = 0; it < n_tiles; ++it) {
+          if (blockIdx.y == 0) TL(it, 2);
           mbar_wait(&full[stage], ph);
           asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // cp.async-built A tile -> async proxy
           tc_fence_after();
+          if (blockIdx.y == 0) TL(it, 3);
           const uint64_t ad = ad0 + (uint64_t)((uint32_t)stage * a16), bd = bd0 + (uint64_t)((uint32_t)stage * b16);
 #pragma unroll
           for (int kk = 0; kk < 8; ++kk)   // 16 pixels per MMA
@@ -1019,6 +1041,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
                       (it > 0 || kk > 0) ? 1u : 0u);
           umma_commit(&empty[stage]);
           if (it == n_tiles - 1) umma_commit(tmem_full);
+          if (blockIdx.y == 0) TL(it, 7);
           if (++stage == p.stages) { stage = 0; ph ^= 1; }
         }
       }
@@ -1103,6 +1126,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
       const int m = mtile * 128 + q * 32 + lane;
       mbar_wait(tmem_full, 0);
       tc_fence_after();
+      if (blockIdx.y == 0 && threadIdx.x == 64) TL(n_tiles < 31 ? n_tiles : 31, 4);
       for (int c0 = 0; c0 < p.N; c0 += 16) {
         uint32_t r[16];
         tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, r);
@@ -1146,6 +1170,7 @@ __global__ void __launch_bounds__(TG_THREADS) wgrad_kernel(const __grid_constant
         }
       }
       tc_fence_before();
+      if (blockIdx.y == 0 && threadIdx.x == 64) TL(n_tiles < 31 ? n_tiles : 31, 6);
     }
   }
   __syncthreads();
@@ -2469,6 +2494,7 @@ static int wg_bf16_impl(const gccvae_geom* g, const void* L, const void* S, cons
     attr_set = true;
   }
   dim3 grid(splits, mtiles, 1);
+  p.timeline = g_timeline;
   GCC_CUDA(launch_pdl(wgrad_kernel, grid, TG_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("wg_bf16");
   return GCCVAE_OK;
@@ -2770,6 +2796,7 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
     GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
+  p.timeline = g_timeline;
   GCC_CUDA(launch_pdl(wgrad_kernel, dim3(splits, 1, 1), TG_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("tap4_wg");
   return GCCVAE_OK;
@@ -2958,6 +2985,7 @@ extern "C" int gccvae_wg_s2d_bf16(int batch, int HS, int WS, int CL, const void*
     GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
     attr_set = true;
   }
+  p.timeline = g_timeline;
   GCC_CUDA(launch_pdl(wgrad_kernel, dim3(splits, mtiles, 1), TG_THREADS, smem, (cudaStream_t)stream, p));
   GCC_CHECK_LAUNCH("wg_s2d");
   return GCCVAE_OK;
