@@ -2752,8 +2752,12 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   if (!env_tma) {
     // A tile built by the (otherwise idle) epilogue warps: one 128-byte row per pixel, SWIZZLE_128B, which is an
     // MN-major operand with M = 64 (a,b,dy,dx,c4); the instruction's rows 64..127 come from the unused second slab
+    // Only ONE 16 KB slab per stage is built and reserved: the second slab the M = 128 instruction reads (LBO = 16 KB
+    // further on: the stage's B tile and the next stage, or the slack behind the last stage) feeds accumulator rows
+    // 64..127, which nobody reads.  24 KB stages instead of 40: four pipeline stages in the same 100 KB per CTA - the
+    // kernel is bound by the round trip of a stage (profiles/r02_timeline_wgrad.txt), so depth is what it needs.
     p.in2 = (const uint4*)in2;
-    p.kcA = 64; p.blocks_per_tap = 1; p.blocks_per_mtile = 2; p.taps = 1; p.c4_rows = 2;
+    p.kcA = 64; p.blocks_per_tap = 1; p.blocks_per_mtile = 1; p.taps = 1; p.c4_rows = 2;
   } else {
     p.kcA = 16; p.blocks_per_tap = 1; p.blocks_per_mtile = 8; p.taps = 4; p.c4_rows = 2;
   }
@@ -2785,12 +2789,15 @@ extern "C" int gccvae_tap4_wg_bf16(int batch, const void* in2, const void* S, in
   if (splits > p.tiles_total) splits = p.tiles_total;
   p.tiles_per_cta = (p.tiles_total + splits - 1) / splits;
   splits = (p.tiles_total + p.tiles_per_cta - 1) / p.tiles_per_cta;
-  const int stage_bytes = 128 * 128 * 2 + 128 * CS * 2;
+  const int stage_bytes = 128 * 128 * p.blocks_per_mtile + 128 * CS * 2;
   int stages = (wg_smem_kb() * 1024) / stage_bytes;   // default 100 KB: two CTAs per SM
+  if (stages > 8) stages = 8;
   if (stages > p.tiles_per_cta) stages = p.tiles_per_cta;
   if (stages < 1) stages = 1;
   p.stages = stages;
-  const size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
+  size_t smem = (size_t)stages * stage_bytes + 1024 + 256 + 1024;
+  // the unread second slab of the LAST stage's A tile must still lie inside the allocation (layout: [A stages][B stages])
+  if (!env_tma && smem < (size_t)(stages + 1) * 16384 + 1024) smem = (size_t)(stages + 1) * 16384 + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     GCC_CUDA(cudaFuncSetAttribute(wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(200 * 1024)));
